@@ -1,0 +1,56 @@
+"""Build libafa_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)                      # .../diffbinaural-binaural-audio-generation_b200
+_REPO = os.path.dirname(_ROOT)
+_CSRC = os.path.join(_ROOT, "csrc")
+_INCLUDE = os.path.join(_REPO, "include")
+LIB_NAME = "libafa_sm100.so"
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, LIB_NAME)
+
+
+def _sources():
+    return [os.path.join(_CSRC, "afa_capi.cu")]
+
+
+def _deps():
+    return _sources() + [os.path.join(_CSRC, "afa_kernels.cuh"), os.path.join(_INCLUDE, "afa_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libafa_sm100.so (there is no CPU fallback)")
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ -> afa_b200/libafa_sm100.so.  Rebuilds only when a source is newer."""
+    out = library_path()
+    if not force and os.path.exists(out):
+        t = os.path.getmtime(out)
+        if all(os.path.getmtime(d) <= t for d in _deps()):
+            return out
+    cmd = [
+        _nvcc(),
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-lineinfo", "-std=c++17",
+        "-Xptxas", "-v" if verbose else "-O3",
+        "-I", _INCLUDE, "-I", _CSRC,
+        "--shared", "-Xcompiler", "-fPIC",
+        "-o", out,
+    ] + _sources()
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return out

@@ -1,0 +1,632 @@
+// afa_kernels.cuh -- fused Activation1d (2x Kaiser-sinc upsample -> Snake/SnakeBeta -> 2x low-pass
+// downsample) forward and backward kernels for sm_100a.
+//
+// What it replaces (reference, /root/reference/BigVGAN): alias_free_activation/act.py:25-30, i.e.
+// resample.py:29-38 + activations.py:51-62/113-126 + filter.py:94-101, and their autograd backward.
+//
+// Design (DESIGN.md has the long form):
+//   * Rows (batch*channel) are independent.  Every row is cut into SEGMENTS of L = CH*VEC samples
+//     (VEC = elements per 16 bytes, CH odd).  One thread owns one segment and walks it in time order,
+//     keeping the 6-tap polyphase windows and the 6 live output accumulators in registers, so the
+//     2x-rate intermediate never leaves the register file.
+//   * Segments are numbered row-major; a CTA owns NT consecutive segments, which is one CONTIGUOUS
+//     range of the flat [rows*T] array.  That range (+8 halo elements either side) is staged in shared
+//     memory by ONE 1-D bulk TMA copy (cp.async.bulk + mbarrier, SASS UBLKCP); the result tile goes
+//     back with one bulk TMA store.  Global traffic is therefore perfectly coalesced 16-byte aligned
+//     bulk, and no thread spends issue slots on global loads/stores.
+//   * Thread i reads/writes shared memory at a stride of CH 16-byte chunks; CH odd makes every
+//     quarter-warp LDS.128/STS.128 hit 8 distinct 16-byte bank groups -> conflict-free without swizzle.
+//   * Replicate padding lives in two places: the x clamp and the clamp of the
+//     ACTIVATED 2x signal.  Warps whose segments all sit >= 5 samples from both row ends take the
+//     branch-free MODE 0 walk; warps touching a row end take MODE 1 (same static schedule, clamped
+//     loads + selects); rows whose length is not a multiple of VEC (no 16-byte alignment, TMA illegal)
+//     run the MODE 2 kernel (scalar staging), still inside this library.
+//   * No tensor cores: a depthwise 12-tap stencil is not a contraction (north_star).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace afa {
+
+constexpr int kHalo = 8;   // elements staged either side of a CTA's flat range (>= 5 needed)
+
+// Filter taps as kernel parameters (constant bank -> FFMA constant operands).
+struct FwdTaps {
+    float ue[6];   // ue[j] = 2*f_up[2j+1] : u[2m]   = sum_j ue[j] * x[m+2-j]
+    float uo[6];   // uo[j] = 2*f_up[2j]   : u[2m+1] = sum_j uo[j] * x[m+3-j]
+    float dn[12];  // f_dn[k]              : y[t]    = sum_k dn[k] * s[2t+k-5]
+};
+struct BwdTaps {
+    float ue[6], uo[6];   // as above: recompute u, and scatter du -> dx (same 2*f_up taps)
+    float de[6], dod[6];  // de[j] = f_dn[2j+1], dod[j] = f_dn[2j] : ds[2m], ds[2m+1] from gy
+    float lo[3];          // folded taps of the left  replicate pad of s: gy[0], gy[1], gy[2]
+    float hi[3];          // folded taps of the right replicate pad of s: gy[T-1], gy[T-2], gy[T-3]
+};
+
+struct FwdArgs {
+    const void* x;
+    void* y;
+    const float* alpha;
+    const float* beta;
+    FwdTaps taps;
+    int64_t total;        // rows * T
+    uint32_t total_segs;  // rows * nseg
+    uint32_t nseg;        // segments per row
+    int32_t T;
+    int32_t C;
+    int32_t flags;
+};
+struct BwdArgs {
+    const void* x;
+    const void* gy;
+    void* gx;
+    const float* alpha;
+    const float* beta;
+    float* part;          // [2][total_segs] per-segment parameter-gradient partials
+    BwdTaps taps;
+    int64_t total;
+    uint32_t total_segs;
+    uint32_t nseg;
+    int32_t T;
+    int32_t C;
+    int32_t flags;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk TMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, completes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, bulk-group completion
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// element I/O on shared memory
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct IO;
+template <>
+struct IO<float> {
+    static constexpr int VEC = 4;
+    static __device__ __forceinline__ void load_chunk(const float* p, float* o) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    static __device__ __forceinline__ void store_chunk(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    static __device__ __forceinline__ float load1(const float* p) { return *p; }
+    static __device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+};
+template <>
+struct IO<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ void load_chunk(const __nv_bfloat16* p, float* o) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = __uint_as_float(w[i] << 16);
+            o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store_chunk(__nv_bfloat16* p, const float* v) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// Snake / SnakeBeta: u + sin^2(alpha*u) / (beta + 1e-9)            activations.py:60, :124
+__device__ __forceinline__ float snake_f(float u, float a, float ib) {
+    const float sn = __sinf(u * a);
+    return fmaf(ib, sn * sn, u);
+}
+
+// effective parameters of one channel                              activations.py:119-123
+__device__ __forceinline__ void load_params(const float* alpha, const float* beta, int c, int flags, float& a_eff,
+                                            float& b_eff, float& ib) {
+    float a = __ldg(alpha + c);
+    float b = (flags & 2) ? a : __ldg(beta + c);
+    if (flags & 1) {
+        a = expf(a);
+        b = expf(b);
+    }
+    a_eff = a;
+    b_eff = b;
+    ib = 1.0f / (b + 0.000000001f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward walk of one segment.  MODE 0: interior (branch-free); 1: touches a row end (16B-aligned
+// rows); 2: rows not 16B-aligned (scalar smem I/O).  xo / yo: offsets of this row's sample 0 inside
+// the staged input / output tiles (may be negative; only in-range positions are ever touched).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CH, int MODE>
+__device__ __forceinline__ void walk_fwd(const T* __restrict__ sx, T* __restrict__ sy, int xo, int yo, int t0,
+                                         int Tlen, float a, float ib, const FwdTaps& tp) {
+    constexpr int VEC = IO<T>::VEC;
+    constexpr int L = CH * VEC;
+    constexpr int NX = L + 16;  // X[j] = x[t0 - 8 + j]
+    float X[NX];
+    float s_first = 0.f, s_last = 0.f;
+
+    if (MODE == 0) {
+        const T* base = sx + xo + t0 - 8;
+#pragma unroll
+        for (int c = 0; c < 16 / VEC; ++c) IO<T>::load_chunk(base + c * VEC, &X[c * VEC]);
+    } else {
+        const T* row = sx + xo;
+#pragma unroll
+        for (int j = 2; j < L + 14; ++j) {
+            const int t = min(max(t0 - 8 + j, 0), Tlen - 1);  // replicate pad of x      resample.py:32
+            X[j] = IO<T>::load1(row + t);
+        }
+        if (t0 == 0) {  // s[0]: the value the left replicate pad of s repeats             filter.py:98
+            float u = tp.ue[0] * X[10];
+#pragma unroll
+            for (int j = 1; j < 6; ++j) u = fmaf(tp.ue[j], X[10 - j], u);
+            s_first = snake_f(u, a, ib);
+        }
+        if (Tlen <= t0 + L + 3) {  // s[2T-1]: the value the right replicate pad repeats
+            float u = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int t = min(max(Tlen + 2 - j, 0), Tlen - 1);
+                u = fmaf(tp.uo[j], IO<T>::load1(row + t), u);
+            }
+            s_last = snake_f(u, a, ib);
+        }
+    }
+
+    float acc[L];
+#pragma unroll
+    for (int q = 0; q < L + 6; ++q) {  // pair index m = t0 - 3 + q : produces s[2m], s[2m+1]
+        if (MODE == 0) {
+            if ((q + 8) % VEC == 0 && (q + 8) >= 16) {
+                IO<T>::load_chunk(sx + xo + t0 + q, &X[q + 8]);
+            }
+        }
+        float ue = tp.ue[0] * X[q + 7];
+        float uo = tp.uo[0] * X[q + 8];
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+            ue = fmaf(tp.ue[j], X[q + 7 - j], ue);
+            uo = fmaf(tp.uo[j], X[q + 8 - j], uo);
+        }
+        float se = snake_f(ue, a, ib);
+        float so = snake_f(uo, a, ib);
+        if (MODE != 0) {
+            const int m = t0 - 3 + q;
+            if (q < 3) {
+                if (m < 0) { se = s_first; so = s_first; }
+            }
+            if (m >= Tlen) { se = s_last; so = s_last; }
+        }
+        // scatter into the (at most 6 live) output accumulators: s[2m+1] -> y[m+3-j] (tap 2j),
+        // s[2m] -> y[m+2-j] (tap 2j+1)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int o = q - j;
+            if (o >= 0 && o < L) acc[o] = (j == 0) ? tp.dn[0] * so : fmaf(tp.dn[2 * j], so, acc[o]);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int o = q - 1 - j;
+            if (o >= 0 && o < L) acc[o] = fmaf(tp.dn[2 * j + 1], se, acc[o]);
+        }
+        // y[t0 + q - 6] is complete now
+        const int od = q - 6;
+        if (MODE != 2) {
+            if (od >= 0 && (od % VEC) == VEC - 1) {
+                const int c0 = od - (VEC - 1);
+                if (MODE == 0 || t0 + c0 < Tlen) IO<T>::store_chunk(sy + yo + t0 + c0, &acc[c0]);
+            }
+        } else {
+            if (od >= 0 && t0 + od < Tlen) IO<T>::store1(sy + yo + t0 + od, acc[od]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward walk of one segment: recomputes u from x, forms ds from gy, du = ds*(1 + a*ib*sin(2 a u)),
+// scatters du into dx, and accumulates the segment's share of d/dalpha_eff, d/dbeta_eff.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CH, int MODE>
+__device__ __forceinline__ void walk_bwd(const T* __restrict__ sx, const T* __restrict__ sg, T* __restrict__ sy,
+                                         int xo, int yo, int t0, int Tlen, float a, float ib, const BwdTaps& tp,
+                                         float& ga_out, float& gb_out) {
+    constexpr int VEC = IO<T>::VEC;
+    constexpr int L = CH * VEC;
+    constexpr int NX = L + 16;
+    float X[NX], G[NX];
+    float d_lo = 0.f, d_hi = 0.f;
+
+    if (MODE == 0) {
+        const T* bx = sx + xo + t0 - 8;
+        const T* bg = sg + xo + t0 - 8;
+#pragma unroll
+        for (int c = 0; c < 16 / VEC; ++c) {
+            IO<T>::load_chunk(bx + c * VEC, &X[c * VEC]);
+            IO<T>::load_chunk(bg + c * VEC, &G[c * VEC]);
+        }
+    } else {
+        const T* rx = sx + xo;
+        const T* rg = sg + xo;
+#pragma unroll
+        for (int j = 2; j < L + 14; ++j) {
+            const int t = t0 - 8 + j;
+            const int tc = min(max(t, 0), Tlen - 1);
+            X[j] = IO<T>::load1(rx + tc);                                   // replicate pad of x
+            const float g = IO<T>::load1(rg + tc);
+            G[j] = (t >= 0 && t < Tlen) ? g : 0.f;                          // gy does not extend
+        }
+        if (t0 == 0) d_lo = fmaf(tp.lo[2], G[10], fmaf(tp.lo[1], G[9], tp.lo[0] * G[8]));
+        if (Tlen - 1 <= t0 + L + 2) {  // the walk reaches pair m = T-1, whose odd member s[2T-1] carries the fold
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int t = Tlen - 1 - i;
+                const float g = IO<T>::load1(rg + max(t, 0));
+                d_hi = fmaf(tp.hi[i], (t >= 0) ? g : 0.f, d_hi);
+            }
+        }
+    }
+
+    const float a2 = 2.0f * a;
+    const float iba = ib * a;
+    float ga = 0.f, gb = 0.f;
+    constexpr int AO = (MODE == 0) ? 0 : 3;  // accumulators cover o in [-AO, L + AO)
+    float acc[L + 2 * AO];
+    if (MODE != 0) {
+        acc[0] = 0.f; acc[1] = 0.f; acc[2] = 0.f;
+    }
+
+#pragma unroll
+    for (int q = 0; q < L + 6; ++q) {
+        if (MODE == 0) {
+            if ((q + 8) % VEC == 0 && (q + 8) >= 16) {
+                IO<T>::load_chunk(sx + xo + t0 + q, &X[q + 8]);
+                IO<T>::load_chunk(sg + xo + t0 + q, &G[q + 8]);
+            }
+        }
+        float ue = tp.ue[0] * X[q + 7];
+        float uo = tp.uo[0] * X[q + 8];
+        float de = tp.de[0] * G[q + 7];
+        float dd = tp.dod[0] * G[q + 8];
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+            ue = fmaf(tp.ue[j], X[q + 7 - j], ue);
+            uo = fmaf(tp.uo[j], X[q + 8 - j], uo);
+            de = fmaf(tp.de[j], G[q + 7 - j], de);
+            dd = fmaf(tp.dod[j], G[q + 8 - j], dd);
+        }
+        if (MODE != 0) {
+            const int m = t0 - 3 + q;
+            if (q < 3) {
+                if (m < 0) { de = 0.f; dd = 0.f; }
+            }
+            if (m >= Tlen) { de = 0.f; dd = 0.f; }
+            if (q == 3) {
+                if (t0 == 0) de += d_lo;
+            }
+            if (m == Tlen - 1) dd += d_hi;
+        }
+        const bool own = (q >= 3 && q < L + 3);  // s[2m], s[2m+1] belong to this segment
+        float due, duo;
+        {
+            const float ph = a2 * ue;
+            const float sn = __sinf(ph), cs = __cosf(ph);
+            const float p = de * sn;
+            due = fmaf(p, iba, de);
+            if (own) {
+                ga = fmaf(p, ue, ga);
+                gb += fmaf(-de, cs, de);
+            }
+        }
+        {
+            const float ph = a2 * uo;
+            const float sn = __sinf(ph), cs = __cosf(ph);
+            const float p = dd * sn;
+            duo = fmaf(p, iba, dd);
+            if (own) {
+                ga = fmaf(p, uo, ga);
+                gb += fmaf(-dd, cs, dd);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int o = q - j;
+            if (o >= -AO && o < L + AO) acc[o + AO] = (j == 0) ? tp.uo[0] * duo : fmaf(tp.uo[j], duo, acc[o + AO]);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int o = q - 1 - j;
+            if (o >= -AO && o < L + AO) acc[o + AO] = fmaf(tp.ue[j], due, acc[o + AO]);
+        }
+        const int od = q - 6;
+        if (od >= 0) {
+            if (MODE != 0) {
+                // fold the adjoint of the x replicate pad onto the row's first / last sample
+                if (od == 0) {
+                    if (t0 == 0) acc[AO] += acc[0] + acc[1] + acc[2];
+                }
+                if (t0 + od == Tlen - 1) acc[od + AO] += acc[od + AO + 1] + acc[od + AO + 2] + acc[od + AO + 3];
+            }
+            if (MODE != 2) {
+                if ((od % VEC) == VEC - 1) {
+                    const int c0 = od - (VEC - 1);
+                    if (MODE == 0 || t0 + c0 < Tlen) IO<T>::store_chunk(sy + yo + t0 + c0, &acc[c0 + AO]);
+                }
+            } else {
+                if (t0 + od < Tlen) IO<T>::store1(sy + yo + t0 + od, acc[od + AO]);
+            }
+        }
+    }
+    ga_out = ga * ib;                 // sum ds * ib * u * sin(2 a u)
+    gb_out = -0.5f * ib * ib * gb;    // -sum ds * sin^2(a u) * ib^2,  sin^2 = (1 - cos 2au)/2
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA frame shared by forward and backward
+// ------------------------------------------------------------------------------------------------
+struct TileHdr {
+    uint64_t bar;
+    int64_t flat_lo, flat_hi;  // output range of this CTA in the flat [rows*T] array
+    int64_t ld_lo, ld_hi;      // staged input range (flat range + halo, clipped)
+};
+
+template <int NT>
+__device__ __forceinline__ void cta_ranges(TileHdr* h, uint32_t total_segs, uint32_t nseg, int T, int L,
+                                           int64_t total, int align_elems) {
+    const uint32_t g0 = blockIdx.x * NT;
+    const uint32_t g1 = min(g0 + NT, total_segs) - 1;
+    const uint32_t ra = g0 / nseg, sa = g0 - ra * nseg;
+    const uint32_t rb = g1 / nseg, sb = g1 - rb * nseg;
+    const int64_t lo = (int64_t)ra * T + (int64_t)sa * L;
+    const int64_t hi = (int64_t)rb * T + min((int64_t)T, (int64_t)(sb + 1) * L);
+    int64_t llo = lo - kHalo, lhi = hi + kHalo;
+    if (llo < 0) llo = 0;
+    if (lhi > total) lhi = total;
+    (void)align_elems;
+    h->flat_lo = lo;
+    h->flat_hi = hi;
+    h->ld_lo = llo;
+    h->ld_hi = lhi;
+}
+
+template <typename T, int CH, int NT>
+struct Tile {
+    static constexpr int VEC = IO<T>::VEC;
+    static constexpr int L = CH * VEC;
+    static constexpr int kInElems = NT * L + 2 * kHalo + 2 * VEC;  // staged input tile (+ slack for chunk over-read)
+    static constexpr int kOutElems = NT * L;
+    static constexpr int kHdrBytes = 128;
+    static constexpr size_t fwd_smem() { return kHdrBytes + sizeof(T) * (size_t)(kInElems + kOutElems); }
+    static constexpr size_t bwd_smem() { return kHdrBytes + sizeof(T) * (size_t)(2 * kInElems + kOutElems); }
+};
+
+template <typename T, int CH, int NT, bool ALIGNED>
+__global__ void __launch_bounds__(NT) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
+    using TL = Tile<T, CH, NT>;
+    constexpr int L = TL::L;
+    extern __shared__ __align__(128) unsigned char smem[];
+    TileHdr* hdr = reinterpret_cast<TileHdr*>(smem);
+    T* s_in = reinterpret_cast<T*>(smem + TL::kHdrBytes);
+    T* s_out = s_in + TL::kInElems;
+
+    const int tid = threadIdx.x;
+    const T* gx = static_cast<const T*>(args.x);
+    T* gy = static_cast<T*>(args.y);
+
+    if (tid == 0) {
+        cta_ranges<NT>(hdr, args.total_segs, args.nseg, args.T, L, args.total, TL::VEC);
+        if (ALIGNED) {
+            mbar_init(&hdr->bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = (uint32_t)((hdr->ld_hi - hdr->ld_lo) * (int64_t)sizeof(T));
+            mbar_expect_tx(&hdr->bar, bytes);
+            tma_load_1d(s_in, gx + hdr->ld_lo, bytes, &hdr->bar);
+        }
+    }
+
+    // per-thread segment coordinates and channel parameters (overlaps the bulk copy)
+    const uint32_t gid = blockIdx.x * NT + tid;
+    const bool active = gid < args.total_segs;
+    uint32_t row = 0, seg = 0;
+    float a_eff = 1.f, b_eff = 1.f, ib = 1.f;
+    if (active) {
+        row = gid / args.nseg;
+        seg = gid - row * args.nseg;
+        load_params(args.alpha, args.beta, (int)(row % (uint32_t)args.C), args.flags, a_eff, b_eff, ib);
+    }
+    const int t0 = (int)seg * L;
+    __syncthreads();
+    const int64_t flat_lo = hdr->flat_lo, flat_hi = hdr->flat_hi, ld_lo = hdr->ld_lo, ld_hi = hdr->ld_hi;
+    const int xo = (int)((int64_t)row * args.T - ld_lo);
+    const int yo = (int)((int64_t)row * args.T - flat_lo);
+
+    if (ALIGNED) {
+        mbar_wait(&hdr->bar, 0);
+        const bool fast = active && t0 >= 5 && (t0 + L + 5 < args.T);
+        if (__all_sync(0xffffffffu, fast)) {
+            walk_fwd<T, CH, 0>(s_in, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps);
+        } else if (active) {
+            walk_fwd<T, CH, 1>(s_in, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(gy + flat_lo, s_out, (uint32_t)((flat_hi - flat_lo) * (int64_t)sizeof(T)));
+            tma_store_commit_and_wait();
+        }
+    } else {
+        const int n_in = (int)(ld_hi - ld_lo);
+        for (int i = tid; i < n_in; i += NT) s_in[i] = gx[ld_lo + i];
+        __syncthreads();
+        if (active) walk_fwd<T, CH, 2>(s_in, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps);
+        __syncthreads();
+        const int n_out = (int)(flat_hi - flat_lo);
+        for (int i = tid; i < n_out; i += NT) gy[flat_lo + i] = s_out[i];
+    }
+}
+
+template <typename T, int CH, int NT, bool ALIGNED>
+__global__ void __launch_bounds__(NT) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
+    using TL = Tile<T, CH, NT>;
+    constexpr int L = TL::L;
+    extern __shared__ __align__(128) unsigned char smem[];
+    TileHdr* hdr = reinterpret_cast<TileHdr*>(smem);
+    T* s_x = reinterpret_cast<T*>(smem + TL::kHdrBytes);
+    T* s_g = s_x + TL::kInElems;
+    T* s_out = s_g + TL::kInElems;
+
+    const int tid = threadIdx.x;
+    const T* px = static_cast<const T*>(args.x);
+    const T* pg = static_cast<const T*>(args.gy);
+    T* po = static_cast<T*>(args.gx);
+
+    if (tid == 0) {
+        cta_ranges<NT>(hdr, args.total_segs, args.nseg, args.T, L, args.total, TL::VEC);
+        if (ALIGNED) {
+            mbar_init(&hdr->bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = (uint32_t)((hdr->ld_hi - hdr->ld_lo) * (int64_t)sizeof(T));
+            mbar_expect_tx(&hdr->bar, 2 * bytes);
+            tma_load_1d(s_x, px + hdr->ld_lo, bytes, &hdr->bar);
+            tma_load_1d(s_g, pg + hdr->ld_lo, bytes, &hdr->bar);
+        }
+    }
+
+    const uint32_t gid = blockIdx.x * NT + tid;
+    const bool active = gid < args.total_segs;
+    uint32_t row = 0, seg = 0;
+    float a_eff = 1.f, b_eff = 1.f, ib = 1.f;
+    if (active) {
+        row = gid / args.nseg;
+        seg = gid - row * args.nseg;
+        load_params(args.alpha, args.beta, (int)(row % (uint32_t)args.C), args.flags, a_eff, b_eff, ib);
+    }
+    const int t0 = (int)seg * L;
+    __syncthreads();
+    const int64_t flat_lo = hdr->flat_lo, flat_hi = hdr->flat_hi, ld_lo = hdr->ld_lo, ld_hi = hdr->ld_hi;
+    const int xo = (int)((int64_t)row * args.T - ld_lo);
+    const int yo = (int)((int64_t)row * args.T - flat_lo);
+    float ga = 0.f, gb = 0.f;
+
+    if (ALIGNED) {
+        mbar_wait(&hdr->bar, 0);
+        const bool fast = active && t0 >= 5 && (t0 + L + 5 < args.T);
+        if (__all_sync(0xffffffffu, fast)) {
+            walk_bwd<T, CH, 0>(s_x, s_g, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps, ga, gb);
+        } else if (active) {
+            walk_bwd<T, CH, 1>(s_x, s_g, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps, ga, gb);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(po + flat_lo, s_out, (uint32_t)((flat_hi - flat_lo) * (int64_t)sizeof(T)));
+            tma_store_commit_and_wait();
+        }
+    } else {
+        const int n_in = (int)(ld_hi - ld_lo);
+        for (int i = tid; i < n_in; i += NT) {
+            s_x[i] = px[ld_lo + i];
+            s_g[i] = pg[ld_lo + i];
+        }
+        __syncthreads();
+        if (active) walk_bwd<T, CH, 2>(s_x, s_g, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps, ga, gb);
+        __syncthreads();
+        const int n_out = (int)(flat_hi - flat_lo);
+        for (int i = tid; i < n_out; i += NT) po[flat_lo + i] = s_out[i];
+    }
+    if (active) {
+        // gradients w.r.t. the RAW parameters: d exp(p)/dp = exp(p)            activations.py:121-123
+        if (args.flags & 1) {
+            ga *= a_eff;
+            gb *= b_eff;
+        }
+        args.part[gid] = ga;
+        args.part[(size_t)args.total_segs + gid] = gb;
+    }
+}
+
+// Second stage of the deterministic parameter-gradient reduction: one warp per channel sums the
+// per-segment partials of every (batch, segment) of that channel in a fixed order.
+__global__ void afa_param_grad_finalize(const float* __restrict__ part, float* __restrict__ galpha,
+                                        float* __restrict__ gbeta, uint32_t total_segs, uint32_t nseg, int batch,
+                                        int C, int snake) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    float sa = 0.f, sb = 0.f;
+    for (int b = 0; b < batch; ++b) {
+        const size_t base = ((size_t)b * C + warp) * nseg;
+        for (uint32_t s = lane; s < nseg; s += 32) {
+            sa += part[base + s];
+            sb += part[(size_t)total_segs + base + s];
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, off);
+        sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+    if (lane == 0) {
+        if (snake) {
+            galpha[warp] = sa + sb;  // beta aliases alpha                           activations.py:57-60
+        } else {
+            galpha[warp] = sa;
+            gbeta[warp] = sb;
+        }
+    }
+}
+
+}  // namespace afa

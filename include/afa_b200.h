@@ -1,0 +1,101 @@
+/*
+ * afa_b200.h -- C ABI of libafa_sm100.so: the fused anti-aliased activation (Activation1d) for
+ * NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the one hot path this repository accelerates.  Each entry point
+ * replaces the torch-op sequence behind a reference interface (paths relative to the reference tree):
+ *
+ *   afa_activation1d_fwd   <->  Activation1d.forward            BigVGAN/alias_free_activation/act.py:25-30
+ *                               = UpSample1d.forward            BigVGAN/alias_free_activation/resample.py:29-38
+ *                               + Snake/SnakeBeta.forward       BigVGAN/activations.py:51-62, 113-126
+ *                               + LowPassFilter1d.forward       BigVGAN/alias_free_activation/filter.py:94-101
+ *   afa_activation1d_bwd   <->  autograd backward of the above, triggered at
+ *                               BigVGAN/train_binaural_mel.py:787 (loss_gen_all.backward())
+ *
+ * The reference reaches this boundary through `alias_free_activation.cuda.activation1d.Activation1d`
+ * (BigVGAN/bigvgan.py:94-102, 194-202, 272-280); the Python module of that name in this repository
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All device pointers are BORROWED: the library
+ *     never allocates, frees or retains device memory.
+ *   - x / y / gy / gx are dense row-major [batch, channels, T] device arrays of `dtype`
+ *     (AFA_DTYPE_F32 or AFA_DTYPE_BF16; bf16 I/O computes in fp32).
+ *   - alpha / beta are the RAW per-channel parameters (float32 [channels], device) exactly as stored
+ *     in `act.alpha` / `act.beta`; AFA_FLAG_LOGSCALE applies exp() (activations.py:119-123);
+ *     AFA_FLAG_SNAKE means beta aliases alpha (activations.py:57-60) and `beta` is ignored.
+ *   - taps_up12 / taps_down12 are HOST pointers to the 12 filter taps held in the module buffers
+ *     `upsample.filter` / `downsample.lowpass.filter` (resample.py:23-26, filter.py:90-91).
+ *   - `stream` is a cudaStream_t (NULL = default stream).  Launches are asynchronous; nothing
+ *     synchronises the device, so calls are CUDA-graph capturable.
+ *   - return 0 on success; a negative AFA_ERR_* for argument errors; a positive cudaError_t for
+ *     CUDA failures.  afa_last_error() returns a thread-local description.  Nothing throws or exits.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef AFA_B200_H_
+#define AFA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFA_VERSION 100            /* 0.1.0 */
+
+#define AFA_DTYPE_F32 0
+#define AFA_DTYPE_BF16 1
+
+#define AFA_FLAG_LOGSCALE 1        /* act.alpha_logscale                        activations.py:42,98  */
+#define AFA_FLAG_SNAKE 2           /* Snake (beta := alpha) instead of SnakeBeta  activations.py:51-62  */
+
+#define AFA_ERR_BAD_ARG (-1)
+#define AFA_ERR_BAD_DTYPE (-2)
+#define AFA_ERR_TOO_LARGE (-3)
+#define AFA_ERR_WORKSPACE (-4)
+#define AFA_ERR_ALIGNMENT (-5)
+
+int afa_version(void);
+const char *afa_last_error(void);
+
+/* y = down2x(snake(up2x(x))).  x, y: [batch, channels, T] of dtype; y may not alias x. */
+int afa_activation1d_fwd(const void *x, void *y,
+                         const float *alpha, const float *beta,
+                         const float *taps_up12, const float *taps_down12,
+                         int64_t batch, int64_t channels, int64_t T,
+                         int dtype, int flags, void *stream);
+
+/* Scratch the backward needs (per-segment parameter-gradient partials), in bytes. */
+size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int dtype);
+
+/*
+ * gx = d<y,gy>/dx ; galpha / gbeta = gradients w.r.t. the RAW parameters (float32 [channels],
+ * log-scale chain rule and Snake aliasing applied; gbeta may be NULL with AFA_FLAG_SNAKE).
+ * The intermediate 2x-rate signal is recomputed from x; only x is needed from the forward.
+ * Reductions are two-stage and deterministic (no atomics).
+ */
+int afa_activation1d_bwd(const void *x, const void *gy, void *gx,
+                         float *galpha, float *gbeta,
+                         const float *alpha, const float *beta,
+                         const float *taps_up12, const float *taps_down12,
+                         int64_t batch, int64_t channels, int64_t T,
+                         int dtype, int flags,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).
+ * afa_set_tuning: which=0 forward, 1 backward; chunks = 16-byte chunks per thread segment
+ * (odd, one of the compiled values), threads = CTA size.  0 keeps the built-in choice.
+ * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
+ * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects.
+ */
+int afa_set_tuning(int which, int chunks, int threads);
+int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t afa_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFA_B200_H_ */

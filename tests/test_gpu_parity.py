@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python mirror) against the oracle.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8d), E = max|y - ref| / max|ref|:
+    fp32 forward and gx   : E <= 1e-5   (vs the reference's own fp32 output AND vs fp64 truth)
+    bf16 I/O, fp32 math   : E <= 1e-2   (vs fp64 truth evaluated on the bf16-rounded input)
+    galpha / gbeta (fp32) : E <= 1e-4   (long reductions)
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import afa_oracle as O
+from oracle import torch_path as TP
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-2
+TOL_PGRAD = 1e-4
+
+
+def _mods():
+    import afa_b200
+    from afa_b200 import _lib, functional
+    from afa_b200.activations import Snake, SnakeBeta
+
+    return afa_b200, _lib, functional, Snake, SnakeBeta
+
+
+def _make(C, kind, logscale, alpha, beta, dev):
+    afa_b200, _, _, Snake, SnakeBeta = _mods()
+    act = (SnakeBeta if kind == "snakebeta" else Snake)(C, alpha_logscale=logscale)
+    with torch.no_grad():
+        act.alpha.copy_(torch.as_tensor(alpha))
+        if kind == "snakebeta":
+            act.beta.copy_(torch.as_tensor(beta))
+    return afa_b200.Activation1d(activation=act).to(dev)
+
+
+def _run(m, x, gy=None):
+    x = x.clone().requires_grad_(gy is not None)
+    y = m(x)
+    if gy is None:
+        return y.detach(), None, None, None
+    for p in m.parameters():
+        p.grad = None
+    y.backward(gy)
+    gb = m.act.beta.grad if hasattr(m.act, "beta") else None
+    return y.detach(), x.grad, m.act.alpha.grad, gb
+
+
+def test_golden_vectors_fp32(golden, golden_cases):
+    """Every vector the unmodified reference produced (tests/golden/make_golden.py), forward and backward."""
+    dev = torch.device("cuda:0")
+    for name, c in golden_cases.items():
+        B, C, T, is_beta, logscale = [int(v) for v in c["meta"]]
+        kind = "snakebeta" if is_beta else "snake"
+        m = _make(C, kind, bool(logscale), c["alpha"], c.get("beta"), dev)
+        np.testing.assert_array_equal(m.upsample.filter.cpu().numpy().reshape(-1), golden["taps_f32"])
+        y, gx, ga, gb = _run(m, torch.from_numpy(c["x"]).to(dev), torch.from_numpy(c["gy"]).to(dev))
+        for ref in ("y_f32", "y_f64"):
+            assert O.max_normalised_error(y.cpu().numpy(), c[ref]) <= TOL_F32, (name, ref)
+        for ref in ("gx_f32", "gx_f64"):
+            assert O.max_normalised_error(gx.cpu().numpy(), c[ref]) <= TOL_F32, (name, ref)
+        assert O.max_normalised_error(ga.cpu().numpy(), c["galpha_f64"]) <= TOL_PGRAD, name
+        if is_beta:
+            assert O.max_normalised_error(gb.cpu().numpy(), c["gbeta_f64"]) <= TOL_PGRAD, name
+
+
+EDGE_T = [1, 2, 3, 4, 5, 8, 11, 12, 31, 35, 36, 37, 40, 44, 71, 72, 73, 76, 127, 128, 129, 144, 148, 1000, 3444]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind,logscale", [("snakebeta", True), ("snake", True), ("snakebeta", False), ("snake", False)])
+def test_edge_lengths_forward_backward(dtype, kind, logscale):
+    """Ragged / tiny / odd row lengths around every segment boundary (L = 20, 36 fp32; 40, 72 bf16)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1234)
+    taps = TP.make_taps().reshape(-1).numpy().astype(np.float64)
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    for T in EDGE_T:
+        for B, C in ((1, 1), (2, 3), (3, 24)):
+            if logscale:
+                alpha = (torch.randn(C, generator=g) * 0.5).numpy()
+                beta = (torch.randn(C, generator=g) * 0.5).numpy()
+            else:
+                alpha = (torch.rand(C, generator=g) * 2 + 0.25).numpy()
+                beta = (torch.rand(C, generator=g) * 2 + 0.25).numpy()
+            beta_ = beta if kind == "snakebeta" else None
+            x = torch.randn(B, C, T, generator=g).to(dtype)
+            gy = torch.randn(B, C, T, generator=g).to(dtype)
+            m = _make(C, kind, logscale, alpha, beta, dev)
+            y, gx, ga, gb = _run(m, x.to(dev), gy.to(dev))
+            xr, gr = x.float().numpy(), gy.float().numpy()
+            y_ref = O.activation1d_forward(xr, alpha, beta_, logscale, taps, taps)
+            gx_ref, ga_ref, gb_ref = O.activation1d_backward(xr, gr, alpha, beta_, logscale, taps, taps)
+            tag = (T, B, C, str(dtype))
+            assert y.dtype == dtype and y.shape == (B, C, T)
+            assert O.max_normalised_error(y.float().cpu().numpy(), y_ref) <= tol, tag
+            assert O.max_normalised_error(gx.float().cpu().numpy(), gx_ref) <= tol, tag
+            ptol = TOL_PGRAD if dtype == torch.float32 else TOL_BF16
+            assert O.max_normalised_error(ga.cpu().numpy(), ga_ref) <= ptol, tag
+            if beta_ is not None:
+                assert O.max_normalised_error(gb.cpu().numpy(), gb_ref) <= ptol, tag
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_unaligned_base_pointer_and_noncontiguous(dtype):
+    """A view that starts 1 element into an allocation (not 16-byte aligned) and a transposed view."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    C, T = 5, 256
+    taps = TP.make_taps().reshape(-1).numpy().astype(np.float64)
+    alpha, beta = np.full(C, 0.3, np.float32), np.full(C, -0.2, np.float32)
+    m = _make(C, "snakebeta", True, alpha, beta, dev)
+    buf = torch.randn(2 * C * T + 1, device=dev).to(dtype)
+    x = buf[1:].view(2, C, T)
+    assert x.data_ptr() % 16 != 0
+    y = m(x)
+    ref = O.activation1d_forward(x.float().cpu().numpy(), alpha, beta, True, taps, taps)
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    assert O.max_normalised_error(y.float().cpu().numpy(), ref) <= tol
+    xt = torch.randn(2, T, C, device=dev).to(dtype).transpose(1, 2)
+    assert not xt.is_contiguous()
+    yt = m(xt)
+    assert yt.is_contiguous()
+    ref = O.activation1d_forward(xt.float().cpu().numpy(), alpha, beta, True, taps, taps)
+    assert O.max_normalised_error(yt.float().cpu().numpy(), ref) <= tol
+
+
+def test_large_argument_range_reduction():
+    """|alpha*x| in the hundreds: the fast-sine path must stay inside the fp32 budget."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    C, T = 4, 4096
+    alpha = np.array([1.5, 1.0, 0.5, 0.0], np.float32)
+    beta = np.array([0.0, 0.5, -0.5, 1.0], np.float32)
+    taps = TP.make_taps().reshape(-1).numpy().astype(np.float64)
+    m = _make(C, "snakebeta", True, alpha, beta, dev)
+    x = torch.randn(2, C, T) * 10.0
+    y = m(x.to(dev))
+    ref = O.activation1d_forward(x.numpy(), alpha, beta, True, taps, taps)
+    assert O.max_normalised_error(y.cpu().numpy(), ref) <= TOL_F32
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 8192), (2, 768, 3444), (2, 24, 220416), (32, 96, 2048)])
+def test_full_size_vs_torch_oracle_on_device(shape):
+    """BASELINE.json sizes: compare with the torch-op oracle executed on the same device (fp32), plus the
+    DC identity (constant rows pass through as c + sin^2(alpha c)/beta)."""
+    dev = torch.device("cuda:0")
+    B, C, T = shape
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    alpha = torch.randn(C, generator=g) * 0.5
+    beta = torch.randn(C, generator=g) * 0.5
+    m = _make(C, "snakebeta", True, alpha.numpy(), beta.numpy(), dev)
+    x = torch.randn(B, C, T, generator=g).to(dev)
+    y = m(x)
+    taps = m.upsample.filter
+    with torch.no_grad():
+        ref = TP.activation1d_torch(x, alpha.to(dev), beta.to(dev), True, taps, taps)
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= TOL_F32, err
+    # backward at full size against autograd of the oracle
+    gy = torch.randn(B, C, T, generator=g).to(dev)
+    xg = x.clone().requires_grad_(True)
+    m.zero_grad()
+    m(xg).backward(gy)
+    gx_ref, ga_ref, gb_ref = TP.activation1d_torch_grads(x, gy, alpha.to(dev), beta.to(dev), True, taps, taps)
+    assert ((xg.grad - gx_ref).abs().max() / gx_ref.abs().max()).item() <= TOL_F32
+    assert ((m.act.alpha.grad - ga_ref).abs().max() / ga_ref.abs().max()).item() <= TOL_PGRAD
+    assert ((m.act.beta.grad - gb_ref).abs().max() / gb_ref.abs().max()).item() <= TOL_PGRAD
+    # DC identity
+    c = torch.linspace(-2, 2, C, device=dev).view(1, C, 1).expand(B, C, T).contiguous()
+    yc = m(c)
+    expect = c + torch.sin(torch.exp(alpha.to(dev)).view(1, C, 1) * c) ** 2 / (torch.exp(beta.to(dev)).view(1, C, 1) + 1e-9)
+    assert (yc - expect).abs().max().item() <= 2e-6 * max(1.0, expect.abs().max().item())
+
+
+def test_segmentation_invariance_bitwise():
+    """The per-sample arithmetic does not depend on how rows are cut into segments: every compiled
+    segment size, and the aligned (TMA) vs unaligned (scalar staging) kernels, agree bit for bit."""
+    _, _lib, _, _, _ = _mods()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    C, T = 6, 1024
+    alpha, beta = np.linspace(-0.5, 0.5, C).astype(np.float32), np.linspace(0.4, -0.4, C).astype(np.float32)
+    m = _make(C, "snakebeta", True, alpha, beta, dev)
+    for dtype in (torch.float32, torch.bfloat16):
+        big = torch.randn(2 * C * T + 8, device=dev).to(dtype)
+        x_al = big[: 2 * C * T].view(2, C, T)
+        x_un = big[1 : 2 * C * T + 1].view(2, C, T)
+        x_un.copy_(x_al.clone())
+        x_al = x_un.clone()
+        outs = []
+        for which_x in (x_al, x_un):
+            for ch in (5, 9):
+                _lib.set_tuning(0, ch, 0)
+                outs.append(m(which_x).clone())
+        _lib.set_tuning(0, 0, 0)
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+
+
+def test_cuda_graph_capture_and_streams():
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    C, T = 24, 2048
+    m = _make(C, "snakebeta", True, np.zeros(C, np.float32), np.zeros(C, np.float32), dev)
+    x = torch.randn(2, C, T, device=dev)
+    y_ref = m(x).clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y_side = m(x)
+    s.synchronize()
+    assert torch.equal(y_side, y_ref)
+    static_x = x.clone()
+    g = torch.cuda.CUDAGraph()
+    m(static_x)  # warm-up (host tap cache, attribute setup) outside capture
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        static_y = m(static_x)
+    static_x.copy_(x * 0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_y, m(x * 0.5))
+
+
+def test_c_abi_direct_call_and_errors():
+    """Straight through ctypes, no Python mirror: argument errors come back as codes + messages."""
+    _, _lib, functional, _, _ = _mods()
+    lib = _lib.load_library()
+    dev = torch.device("cuda:0")
+    B, C, T = 2, 3, 100
+    x = torch.randn(B, C, T, device=dev)
+    y = torch.empty_like(x)
+    a = torch.zeros(C, device=dev)
+    taps = functional.host_taps(TP.make_taps())
+    rc = lib.afa_activation1d_fwd(x.data_ptr(), y.data_ptr(), a.data_ptr(), a.data_ptr(), taps, taps, B, C, T, 0, 1, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = O.activation1d_forward(x.cpu().numpy(), np.zeros(C), np.zeros(C), True)
+    assert O.max_normalised_error(y.cpu().numpy(), ref) <= TOL_F32
+    assert lib.afa_activation1d_fwd(x.data_ptr(), x.data_ptr(), a.data_ptr(), a.data_ptr(), taps, taps, B, C, T, 0, 1, None) == -1
+    assert b"alias" in lib.afa_last_error()
+    assert lib.afa_activation1d_fwd(x.data_ptr(), y.data_ptr(), a.data_ptr(), None, taps, taps, B, C, T, 0, 1, None) == -1
+    assert lib.afa_activation1d_fwd(x.data_ptr(), y.data_ptr(), a.data_ptr(), a.data_ptr(), taps, taps, B, C, T, 7, 1, None) == -2
+    ws = torch.empty(8, dtype=torch.uint8, device=dev)
+    rc = lib.afa_activation1d_bwd(x.data_ptr(), x.data_ptr(), y.data_ptr(), a.data_ptr(), a.data_ptr(), a.data_ptr(),
+                                  a.data_ptr(), taps, taps, B, C, T, 0, 1, ws.data_ptr(), 8, None)
+    assert rc == -4 and b"workspace" in lib.afa_last_error()
+    # empty tensors are a no-op
+    assert lib.afa_activation1d_fwd(x.data_ptr(), y.data_ptr(), a.data_ptr(), a.data_ptr(), taps, taps, 0, C, T, 0, 1, None) == 0
+    assert lib.afa_activation1d_fwd(x.data_ptr(), y.data_ptr(), a.data_ptr(), a.data_ptr(), taps, taps, B, C, 0, 0, 1, None) == 0
+    info = _lib.kernel_info(0, 0, 8192)
+    assert info["registers"] > 0 and info["ctas_per_sm"] >= 1
+    assert _lib.launch_count() >= 1
+
+
+def test_module_semantics_on_device():
+    afa_b200, _, _, Snake, SnakeBeta = _mods()
+    dev = torch.device("cuda:0")
+    C = 8
+    m = afa_b200.Activation1d(activation=SnakeBeta(C, alpha_logscale=True)).to(dev)
+    assert sorted(m.state_dict().keys()) == ["act.alpha", "act.beta", "downsample.lowpass.filter", "upsample.filter"]
+    x = torch.randn(2, C, 64, device=dev)
+    with torch.no_grad():
+        y0 = m(x)
+    with torch.inference_mode():
+        y1 = m(x)
+    assert torch.equal(y0, y1)
+    with pytest.raises(ValueError):
+        m(torch.randn(C, 64, device=dev))
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, C + 1, 64, device=dev))
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, C, 64))
+    with pytest.raises(TypeError):
+        m(x.double())
+    # whole-module bf16 cast (cfg 3: generator.bfloat16()): parameters are read back in fp32 inside the op
+    mb = afa_b200.Activation1d(activation=SnakeBeta(C, alpha_logscale=True)).to(dev).bfloat16()
+    yb = mb(x.bfloat16())
+    assert yb.dtype == torch.bfloat16
+    assert O.max_normalised_error(yb.float().cpu().numpy(), y0.cpu().numpy()) <= TOL_BF16
+    # Snake: single parameter receives the summed gradient
+    ms = afa_b200.Activation1d(activation=Snake(C, alpha_logscale=False)).to(dev)
+    xs = x.clone().requires_grad_(True)
+    ms(xs).sum().backward()
+    assert ms.act.alpha.grad is not None and xs.grad is not None
