@@ -1,0 +1,506 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric: Activation1d HBM GB/s on the BigVGAN AMP shapes.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the reference's torch CPU path, host cores)
+    python bench.py --table                                  (per-shape table, fp32/bf16, fwd/bwd; extra)
+
+A STEP is one pass of the hot path over one batch of synthetic input: the 109 Activation1d forwards of
+one `bigvgan_binaural_22khz_80band_256x` generator pass (reference: BigVGAN/bigvgan.py:361-387 with
+configs/bigvgan_binaural_22khz_80band_256x.json: channels 768..24, T = T_mel x 4..256, 18 calls per
+stage + activation_post) for `--clips` 10-second binaural clips per GPU (B = 2 x clips rows per channel,
+T_mel = 861), fp32, through the C ABI (afa_activation1d_fwd).  `value` is algorithmic GB/s
+(8 B per element: read x, write y) with inputs resident in HBM; every call's tensors are larger than
+L2 (and rotate), so launches are L2-cold.  `e2e` is the same metric through the nn.Module mirror with
+HOST buffers (pinned H2D of every call's input and D2H of every call's output inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.join(REPO, "diffbinaural-binaural-audio-generation_b200")
+for _p in (REPO, PKG_ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# (channels, T / T_mel, calls per generator pass)   bigvgan.py:302-328, :345; SURVEY.md section 8a
+AMP_STAGES = [(768, 4, 18), (384, 16, 18), (192, 32, 18), (96, 64, 18), (48, 128, 18), (24, 256, 19)]
+T_MEL_10S = 861
+METRIC = "activation1d_hbm_gbps"
+UNIT = "GB/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def stage_shapes(clips: int, t_mel: int):
+    return [(2 * clips, c, mult * t_mel, calls) for (c, mult, calls) in AMP_STAGES]
+
+
+def step_elements(clips: int, t_mel: int) -> int:
+    return sum(b * c * t * calls for (b, c, t, calls) in stage_shapes(clips, t_mel))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's torch CPU path (oracle/torch_path.py port)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_pass(t_mel: int, clips: int = 1, repeats: int = 1, threads: int | None = None):
+    """One bounded sample: one Activation1d call per AMP stage shape (6 calls) for `clips` clip(s), fp32, torch CPU."""
+    import torch
+
+    from oracle import torch_path as TP
+
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    taps = TP.make_taps()
+    work = []
+    for (b, c, t, _calls) in stage_shapes(clips, t_mel):
+        work.append((torch.randn(b, c, t), torch.randn(c) * 0.5, torch.randn(c) * 0.5))
+    elems = sum(x.numel() for x, _, _ in work)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for x, a, b_ in work:
+                TP.activation1d_torch(x, a, b_, True, taps, taps)
+            times.append(time.perf_counter() - t0)
+    return elems, times
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = torch.get_num_threads()
+    t_mel = args.t_mel
+    sample = (f"one Activation1d call per AMP stage shape (6 calls, B=2 i.e. one binaural clip, T_mel={t_mel}, fp32) "
+              f"per step, torch CPU ops, {cores} threads")
+    elems, _ = cpu_reference_pass(t_mel, 1, repeats=max(1, args.warmup))
+    elems, times = cpu_reference_pass(t_mel, 1, repeats=args.steps)
+    total_s = sum(times)
+    value = elems * 8 * len(times) / total_s / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total_s / len(times), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bigvgan_binaural_22khz_80band_256x AMP Activation1d shapes, T_mel={t_mel}",
+                   "arm": "reference torch CPU path (oracle/torch_path.py port of alias_free_activation/*.py)"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class Workload:
+    """Device tensors + modules for one generator pass worth of Activation1d calls."""
+
+    def __init__(self, dev, clips: int, t_mel: int, dtype, rotate: int = 2):
+        import torch
+
+        from afa_b200 import Activation1d
+        from afa_b200.activations import SnakeBeta
+
+        self.dev, self.dtype = dev, dtype
+        self.stages = []
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        for (b, c, t, calls) in stage_shapes(clips, t_mel):
+            act = SnakeBeta(c, alpha_logscale=True)                       # configs/...256x.json:20-21
+            with torch.no_grad():
+                act.alpha.copy_(torch.randn(c, generator=g) * 0.5)
+                act.beta.copy_(torch.randn(c, generator=g) * 0.5)
+            mod = Activation1d(activation=act).to(dev)
+            xs = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(rotate)]
+            ys = [torch.empty_like(xs[0]) for _ in range(rotate)]
+            self.stages.append({"shape": (b, c, t), "calls": calls, "mod": mod, "xs": xs, "ys": ys})
+        self.elements = sum(s["shape"][0] * s["shape"][1] * s["shape"][2] * s["calls"] for s in self.stages)
+        self.launches = sum(s["calls"] for s in self.stages)
+
+    def step_device(self):
+        """109 calls through the C ABI on resident tensors (the library launches on the current stream)."""
+        from afa_b200 import functional as Fn
+
+        for s in self.stages:
+            m = s["mod"]
+            tu, td = m._host_taps()
+            a, b = m.act.alpha.detach(), m.act.beta.detach()
+            for k in range(s["calls"]):
+                Fn.activation1d_forward_raw(s["xs"][k % len(s["xs"])], a, b, tu, td, True, out=s["ys"][k % len(s["ys"])])
+
+
+def run_e2e(wl: Workload, steps: int, warmup: int):
+    """Same step through the nn.Module mirror with HOST buffers: H2D of every call's input, D2H of every output."""
+    import torch
+
+    dev = wl.dev
+    host = []
+    for s in wl.stages:
+        b, c, t = s["shape"]
+        hx = torch.randn(b, c, t).to(wl.dtype).pin_memory()
+        hy = torch.empty(b, c, t, dtype=wl.dtype).pin_memory()
+        host.append((hx, hy))
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    h2d = sum(hx.numel() * hx.element_size() * s["calls"] for (hx, _), s in zip(host, wl.stages))
+
+    def one_step():
+        for (hx, hy), s in zip(host, wl.stages):
+            m = s["mod"]
+            n = len(s["xs"])
+            ev_in = [None] * n
+            ev_done = [None] * n
+            ev_out = [None] * n
+            for k in range(s["calls"]):
+                i = k % n
+                with torch.cuda.stream(s_in):
+                    if ev_done[i] is not None:
+                        s_in.wait_event(ev_done[i])           # device input slot free again
+                    s["xs"][i].copy_(hx, non_blocking=True)
+                    ev_in[i] = torch.cuda.Event()
+                    ev_in[i].record(s_in)
+                cur.wait_event(ev_in[i])
+                if ev_out[i] is not None:
+                    cur.wait_event(ev_out[i])                 # previous result in this slot already copied out
+                with torch.no_grad():
+                    y = m(s["xs"][i])                         # public API: Activation1d.forward
+                s["ys"][i] = y
+                ev_done[i] = torch.cuda.Event()
+                ev_done[i].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[i])
+                    hy.copy_(y, non_blocking=True)
+                    ev_out[i] = torch.cuda.Event()
+                    ev_out[i].record(s_out)
+                    y.record_stream(s_out)
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return dt / steps, h2d, h2d
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from afa_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device for the GPU arm (there is no CPU fallback); use --impl reference")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    _lib.load_library()
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    esize = 4 if args.dtype == "fp32" else 2
+
+    wl = Workload(dev, args.clips, args.t_mel, dtype)
+    bytes_per_step = wl.elements * 2 * esize
+
+    # warm-up (also fills the host tap caches), then capture the step in a CUDA graph
+    for _ in range(max(1, args.warmup if not args.graph else 1)):
+        wl.step_device()
+    torch.cuda.synchronize(dev)
+    graph = None
+    if args.graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            wl.step_device()
+        for _ in range(args.warmup):
+            graph.replay()
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                wl.step_device()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    lib_launches = _lib.launch_count() - launches0
+    gpu_launches = args.steps * wl.launches if graph is not None else lib_launches
+
+    # roofline of the dominant kernel (every launch in the step is afa_fwd_kernel; average over the timed region)
+    peak, peak_src = measured_peak()
+    per_launch_bytes = bytes_per_step / wl.launches
+    per_launch_us = ms_per_step * 1e3 / wl.launches
+    achieved = per_launch_bytes / (per_launch_us * 1e-6) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        key = f"fwd_{args.dtype}_clips{args.clips}"
+        if key in tj:
+            traffic = tj[key]
+    except Exception:
+        pass
+    kinfo = _lib.kernel_info(0, 0 if args.dtype == "fp32" else 1, 4 * args.t_mel * 16)
+
+    # e2e through the module with host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        sec, h2d, d2h = run_e2e(wl, e2e_steps, 1)
+        t2 = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * bytes_per_step / float(t2.item()) / 1e9, 3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": round(float(t2.item()) * 1e3, 3),
+               "api": "afa_b200.Activation1d.forward (ctypes -> afa_activation1d_fwd), pinned host buffers"}
+
+    cpu_base = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        cpu_reference_pass(args.t_mel, 1, repeats=1)
+        elems, times = cpu_reference_pass(args.t_mel, 1, repeats=args.cpu_repeats)
+        cpu_base = {"value": round(elems * 8 / min(times) / 1e9, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": (f"one Activation1d call per AMP stage shape (6 calls, B=2, T_mel={args.t_mel}, fp32, "
+                               f"{elems} elements), torch CPU ops (oracle/torch_path.py), best of {args.cpu_repeats}")}
+
+    if world > 1:
+        # the only collective: gather one checksum per rank (stands in for gathering finished waveforms)
+        chk = torch.stack([s["ys"][0].float().abs().mean() for s in wl.stages]).sum().reshape(1)
+        outs = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(outs, chk)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16 I/O, f32 math", "data": "synthetic",
+            "config": {
+                "workload": (f"bigvgan_binaural_22khz_80band_256x: all 109 AMP Activation1d forwards of one generator pass, "
+                             f"{args.clips} x 10 s binaural clips per GPU (B={2 * args.clips}, T_mel={args.t_mel}), SnakeBeta logscale"),
+                "shapes_BCT_calls": [list(s["shape"]) + [s["calls"]] for s in wl.stages],
+                "elements_per_step": wl.elements, "algorithmic_bytes_per_step": bytes_per_step,
+                "l2": "every call's tensors exceed L2 (>=%.0f MB in + out per call) and rotate over 2 buffer sets" % (
+                    min(s["shape"][0] * s["shape"][1] * s["shape"][2] for s in wl.stages) * esize * 2 / 1e6),
+                "cuda_graph": bool(graph is not None), "parallelism": f"clip-sharded dp{world}, no collective in the path",
+            },
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "afa::afa_fwd_kernel", "avg_launch_us": round(per_launch_us, 3),
+                         "algorithmic_bytes_per_launch": int(per_launch_bytes), "kernel_info": kinfo},
+            "cpu_baseline": cpu_base,
+            "e2e": e2e,
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks.summary(),
+            "audio_sec_per_sec_activation_only": round(world * args.clips * 10.0 / (ms_per_step * 1e-3), 2),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# per-shape table (extra; not the driver's contract)
+# ----------------------------------------------------------------------------------------------
+def run_table(args):
+    import torch
+
+    from afa_b200 import Activation1d, _lib
+    from afa_b200 import functional as Fn
+    from afa_b200.activations import SnakeBeta
+    from oracle import torch_path as TP
+
+    dev = torch.device("cuda:0")
+    peak, _ = measured_peak()
+    rows = []
+    shapes = [(2, 512, 8192)]
+    for clips in (1, 8):
+        shapes += [(b, c, t) for (b, c, t, _) in stage_shapes(clips, args.t_mel)]
+    shapes += [(32, c, mult * 32) for (c, mult, _) in AMP_STAGES]
+    for dtype, dname in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        es = 4 if dname == "fp32" else 2
+        for which in ("fwd", "bwd"):
+            for (b, c, t) in shapes:
+                act = SnakeBeta(c, alpha_logscale=True)
+                with torch.no_grad():
+                    act.alpha.normal_(0, 0.5)
+                    act.beta.normal_(0, 0.5)
+                m = Activation1d(activation=act).to(dev)
+                n = b * c * t
+                nbuf = max(2, min(24, int(1.0e9 // (n * es * 2))))
+                xs = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(nbuf)]
+                ys = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(nbuf)]
+                tu, td = m._host_taps()
+                a_, b_ = m.act.alpha.detach(), m.act.beta.detach()
+                if which == "fwd":
+                    def call(i):
+                        Fn.activation1d_forward_raw(xs[i % nbuf], a_, b_, tu, td, True, out=ys[i % nbuf])
+                else:
+                    def call(i):
+                        Fn.activation1d_backward_raw(xs[i % nbuf], ys[i % nbuf], a_, b_, tu, td, True)
+                iters = 2 * nbuf
+                call(0)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(iters):
+                        call(i)
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / (3 * iters)
+                bpe = (2 if which == "fwd" else 3) * es
+                gbs = n * bpe / us / 1e3
+                row = {"dtype": dname, "dir": which, "B": b, "C": c, "T": t, "us": round(us, 2), "GBps": round(gbs, 1),
+                       "frac_of_measured_peak": round(gbs / peak, 3), "Gelem_per_s": round(n / us / 1e3, 1)}
+                if args.torch_baseline and which == "fwd":
+                    taps = m.upsample.filter.to(dtype)
+                    with torch.no_grad():
+                        TP.activation1d_torch(xs[0], a_.to(dtype), b_.to(dtype), True, taps, taps)
+                        torch.cuda.synchronize()
+                        e0.record()
+                        for i in range(3):
+                            TP.activation1d_torch(xs[i % nbuf], a_.to(dtype), b_.to(dtype), True, taps, taps)
+                        e1.record()
+                        torch.cuda.synchronize()
+                    row["torch_ops_gpu_us"] = round(e0.elapsed_time(e1) * 1e3 / 3, 1)
+                rows.append(row)
+                print(json.dumps(row), file=sys.stderr, flush=True)
+                del xs, ys, g
+                torch.cuda.empty_cache()
+    out = os.path.join(REPO, "gpurun_out", "shape_table.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as f:
+        json.dump(rows, f, indent=1)
+    print(json.dumps({"table_rows": len(rows), "written": out}))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--clips", type=int, default=8, help="10 s binaural clips per GPU (B = 2 x clips)")
+    ap.add_argument("--t-mel", dest="t_mel", type=int, default=T_MEL_10S)
+    ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-repeats", type=int, default=3)
+    ap.add_argument("--table", action="store_true")
+    ap.add_argument("--torch-baseline", action="store_true", help="with --table: also time the torch-op path on the GPU")
+    args = ap.parse_args()
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, 3)      # timing rule: at least 3 untimed warm-up steps
+    if args.table:
+        return run_table(args)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -253,10 +253,8 @@ int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha,
     a.flags = flags;
     int rc = dtype == AFA_DTYPE_F32 ? launch_bwd<float>(pl, a, st) : launch_bwd<__nv_bfloat16>(pl, a, st);
     if (rc) return rc;
-    const int warps_per_block = 4;
-    const int blocks = (int)((channels + warps_per_block - 1) / warps_per_block);
-    afa::afa_param_grad_finalize<<<blocks, warps_per_block * 32, 0, st>>>(a.part, galpha, gbeta, pl.total_segs, pl.nseg,
-                                                                        (int)batch, (int)channels, snake ? 1 : 0);
+    afa::afa_param_grad_finalize<<<(unsigned)channels, afa::kFinalizeThreads, 0, st>>>(
+        a.part, galpha, gbeta, pl.total_segs, pl.nseg, (int)batch, (int)channels, snake ? 1 : 0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_param_grad_finalize launch");

@@ -598,33 +598,46 @@ __global__ void __launch_bounds__(NT) afa_bwd_kernel(const __grid_constant__ Bwd
     }
 }
 
-// Second stage of the deterministic parameter-gradient reduction: one warp per channel sums the
-// per-segment partials of every (batch, segment) of that channel in a fixed order.
-__global__ void afa_param_grad_finalize(const float* __restrict__ part, float* __restrict__ galpha,
-                                        float* __restrict__ gbeta, uint32_t total_segs, uint32_t nseg, int batch,
-                                        int C, int snake) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= C) return;
+// Second stage of the deterministic parameter-gradient reduction: one CTA per channel sums the
+// per-segment partials of every (batch, segment) of that channel in a fixed order (thread-strided
+// serial sums, then a fixed shuffle/shared-memory tree), so results are run-to-run identical.
+constexpr int kFinalizeThreads = 256;
+__global__ void __launch_bounds__(kFinalizeThreads)
+afa_param_grad_finalize(const float* __restrict__ part, float* __restrict__ galpha, float* __restrict__ gbeta,
+                        uint32_t total_segs, uint32_t nseg, int batch, int C, int snake) {
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x;
+    const uint32_t per_channel = (uint32_t)batch * nseg;
     float sa = 0.f, sb = 0.f;
-    for (int b = 0; b < batch; ++b) {
-        const size_t base = ((size_t)b * C + warp) * nseg;
-        for (uint32_t s = lane; s < nseg; s += 32) {
-            sa += part[base + s];
-            sb += part[(size_t)total_segs + base + s];
-        }
+    for (uint32_t i = tid; i < per_channel; i += kFinalizeThreads) {
+        const uint32_t b = i / nseg, s = i - b * nseg;
+        const size_t idx = ((size_t)b * C + c) * nseg + s;
+        sa += part[idx];
+        sb += part[(size_t)total_segs + idx];
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         sa += __shfl_xor_sync(0xffffffffu, sa, off);
         sb += __shfl_xor_sync(0xffffffffu, sb, off);
     }
-    if (lane == 0) {
+    __shared__ float red[2][kFinalizeThreads / 32];
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = sa;
+        red[1][tid >> 5] = sb;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < kFinalizeThreads / 32; ++w) {
+            ta += red[0][w];
+            tb += red[1][w];
+        }
         if (snake) {
-            galpha[warp] = sa + sb;  // beta aliases alpha                           activations.py:57-60
+            galpha[c] = ta + tb;  // beta aliases alpha                              activations.py:57-60
         } else {
-            galpha[warp] = sa;
-            gbeta[warp] = sb;
+            galpha[c] = ta;
+            gbeta[c] = tb;
         }
     }
 }

@@ -200,6 +200,35 @@ def activation1d_backward(x, gy, alpha, beta=None, logscale=True, taps_up=None, 
     return gx, ga_raw, gb_raw
 
 
+def param_grad_mass(x, gy, alpha, beta=None, logscale=True, taps_up=None, taps_down=None):
+    """Sum of |terms| of the two parameter-gradient reductions (per channel, chain rule applied).
+
+    The reductions sum signed terms that can cancel almost completely (e.g. one short row), so an
+    fp32 reduction's error scales with this mass, not with the result; tests use it as a second
+    normaliser next to max|g|.
+    """
+    x = np.asarray(x, dtype=np.float64)
+    gy = np.asarray(gy, dtype=np.float64)
+    taps_up = default_taps() if taps_up is None else np.asarray(taps_up, dtype=np.float64).reshape(-1)
+    taps_down = default_taps() if taps_down is None else np.asarray(taps_down, dtype=np.float64).reshape(-1)
+    a, b = effective_params(alpha, beta, logscale)
+    a3, b3 = a[None, :, None], b[None, :, None]
+    u = upsample2x(x, taps_up)
+    T = x.shape[-1]
+    gsp = np.zeros(u.shape[:-1] + (2 * T + 11,), dtype=np.float64)
+    for k in range(12):
+        gsp[..., k : k + 2 * T : 2] += taps_down[k] * gy
+    gs = _pad_replicate_adjoint(gsp, 5, 6)
+    ib = 1.0 / (b3 + NO_DIV_BY_ZERO)
+    ma = np.abs(gs * ib * u * np.sin(2.0 * u * a3)).sum(axis=(0, 2))
+    mb = np.abs(gs * np.sin(u * a3) ** 2 * ib**2).sum(axis=(0, 2))
+    if logscale:
+        ma, mb = ma * a, mb * b
+    if beta is None:
+        return ma + mb, None
+    return ma, mb
+
+
 def max_normalised_error(y, y_ref) -> float:
     """E = max|y - y_ref| / max|y_ref|  (pointwise relative error is ill-posed at zero crossings)."""
     y = np.asarray(y, dtype=np.float64)

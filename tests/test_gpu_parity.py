@@ -19,6 +19,16 @@ pytestmark = pytest.mark.gpu
 TOL_F32 = 1e-5
 TOL_BF16 = 1e-2
 TOL_PGRAD = 1e-4
+TOL_PGRAD_MASS = 1e-5  # |g - ref| / sum|terms|: the bound that still means something when the sum cancels
+
+
+def _pgrad_ok(g, ref, mass, tol=TOL_PGRAD):
+    """Parameter-gradient check: max-normalised error <= tol, or (for sums that cancel, e.g. one short
+    row and one channel) error small against the mass of the reduction."""
+    g = np.asarray(g, dtype=np.float64)
+    if O.max_normalised_error(g, ref) <= tol:
+        return True
+    return bool(np.all(np.abs(g - ref) <= TOL_PGRAD_MASS * np.maximum(mass, 1e-30)))
 
 
 def _mods():
@@ -61,7 +71,7 @@ def test_golden_vectors_fp32(golden, golden_cases):
         np.testing.assert_array_equal(m.upsample.filter.cpu().numpy().reshape(-1), golden["taps_f32"])
         y, gx, ga, gb = _run(m, torch.from_numpy(c["x"]).to(dev), torch.from_numpy(c["gy"]).to(dev))
         for ref in ("y_f32", "y_f64"):
-            assert O.max_normalised_error(y.cpu().numpy(), c[ref]) <= TOL_F32, (name, ref)
+            assert O.max_normalised_error(y.detach().cpu().numpy(), c[ref]) <= TOL_F32, (name, ref)
         for ref in ("gx_f32", "gx_f64"):
             assert O.max_normalised_error(gx.cpu().numpy(), c[ref]) <= TOL_F32, (name, ref)
         assert O.max_normalised_error(ga.cpu().numpy(), c["galpha_f64"]) <= TOL_PGRAD, name
@@ -98,12 +108,12 @@ def test_edge_lengths_forward_backward(dtype, kind, logscale):
             gx_ref, ga_ref, gb_ref = O.activation1d_backward(xr, gr, alpha, beta_, logscale, taps, taps)
             tag = (T, B, C, str(dtype))
             assert y.dtype == dtype and y.shape == (B, C, T)
-            assert O.max_normalised_error(y.float().cpu().numpy(), y_ref) <= tol, tag
-            assert O.max_normalised_error(gx.float().cpu().numpy(), gx_ref) <= tol, tag
-            ptol = TOL_PGRAD if dtype == torch.float32 else TOL_BF16
-            assert O.max_normalised_error(ga.cpu().numpy(), ga_ref) <= ptol, tag
+            assert O.max_normalised_error(y.detach().float().cpu().numpy(), y_ref) <= tol, tag
+            assert O.max_normalised_error(gx.detach().float().cpu().numpy(), gx_ref) <= tol, tag
+            ma, mb = O.param_grad_mass(xr, gr, alpha, beta_, logscale, taps, taps)
+            assert _pgrad_ok(ga.cpu().numpy(), ga_ref, ma), tag
             if beta_ is not None:
-                assert O.max_normalised_error(gb.cpu().numpy(), gb_ref) <= ptol, tag
+                assert _pgrad_ok(gb.cpu().numpy(), gb_ref, mb), tag
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -121,13 +131,13 @@ def test_unaligned_base_pointer_and_noncontiguous(dtype):
     y = m(x)
     ref = O.activation1d_forward(x.float().cpu().numpy(), alpha, beta, True, taps, taps)
     tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
-    assert O.max_normalised_error(y.float().cpu().numpy(), ref) <= tol
+    assert O.max_normalised_error(y.detach().float().cpu().numpy(), ref) <= tol
     xt = torch.randn(2, T, C, device=dev).to(dtype).transpose(1, 2)
     assert not xt.is_contiguous()
     yt = m(xt)
     assert yt.is_contiguous()
     ref = O.activation1d_forward(xt.float().cpu().numpy(), alpha, beta, True, taps, taps)
-    assert O.max_normalised_error(yt.float().cpu().numpy(), ref) <= tol
+    assert O.max_normalised_error(yt.detach().float().cpu().numpy(), ref) <= tol
 
 
 def test_large_argument_range_reduction():
@@ -142,7 +152,7 @@ def test_large_argument_range_reduction():
     x = torch.randn(2, C, T) * 10.0
     y = m(x.to(dev))
     ref = O.activation1d_forward(x.numpy(), alpha, beta, True, taps, taps)
-    assert O.max_normalised_error(y.cpu().numpy(), ref) <= TOL_F32
+    assert O.max_normalised_error(y.detach().cpu().numpy(), ref) <= TOL_F32
 
 
 @pytest.mark.parametrize("shape", [(2, 512, 8192), (2, 768, 3444), (2, 24, 220416), (32, 96, 2048)])
@@ -241,7 +251,7 @@ def test_c_abi_direct_call_and_errors():
     assert rc == 0
     torch.cuda.synchronize()
     ref = O.activation1d_forward(x.cpu().numpy(), np.zeros(C), np.zeros(C), True)
-    assert O.max_normalised_error(y.cpu().numpy(), ref) <= TOL_F32
+    assert O.max_normalised_error(y.detach().cpu().numpy(), ref) <= TOL_F32
     assert lib.afa_activation1d_fwd(x.data_ptr(), x.data_ptr(), a.data_ptr(), a.data_ptr(), taps, taps, B, C, T, 0, 1, None) == -1
     assert b"alias" in lib.afa_last_error()
     assert lib.afa_activation1d_fwd(x.data_ptr(), y.data_ptr(), a.data_ptr(), None, taps, taps, B, C, T, 0, 1, None) == -1
@@ -282,7 +292,7 @@ def test_module_semantics_on_device():
     mb = afa_b200.Activation1d(activation=SnakeBeta(C, alpha_logscale=True)).to(dev).bfloat16()
     yb = mb(x.bfloat16())
     assert yb.dtype == torch.bfloat16
-    assert O.max_normalised_error(yb.float().cpu().numpy(), y0.cpu().numpy()) <= TOL_BF16
+    assert O.max_normalised_error(yb.detach().float().cpu().numpy(), y0.detach().cpu().numpy()) <= TOL_BF16
     # Snake: single parameter receives the summed gradient
     ms = afa_b200.Activation1d(activation=Snake(C, alpha_logscale=False)).to(dev)
     xs = x.clone().requires_grad_(True)
