@@ -34,7 +34,8 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
-constexpr int kNT = 128;
+constexpr int kNW = 4;            // warps per CTA (each warp is an autonomous pipeline)
+constexpr int kNT = kNW * 32;
 
 struct Plan {
     int dtype;
@@ -44,8 +45,58 @@ struct Plan {
     bool aligned;
     uint32_t nseg;
     uint32_t total_segs;
-    uint32_t grid;
+    uint32_t n_wtiles;
 };
+
+afa::FastDiv make_fastdiv(uint32_t d) {
+    afa::FastDiv f;
+    f.d = d;
+    if (d <= 1) {
+        f.mul = 0;
+        f.shr = 0;
+        return f;
+    }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;                         // ceil(log2 d)
+    const unsigned p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);         // exact for 0 <= n < 2^31
+    f.shr = p - 32;
+    return f;
+}
+
+afa::Geometry make_geometry(const Plan& pl, int64_t batch, int64_t channels, int64_t T, int flags);
+
+// Persistent grid: as many CTAs as stay resident, trimmed so that every warp owns the same number of
+// warp tiles (no straggler wave).
+int grid_for(const void* kernel, size_t smem, uint32_t n_wtiles, uint32_t* grid) {
+    struct Cache { const void* k; int dev; int ctas; };
+    static thread_local Cache cache[32];
+    static thread_local int n_cache = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    int ctas = 0;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].k == kernel && cache[i].dev == dev) ctas = cache[i].ctas;
+    if (!ctas) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        int occ = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kNT, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(MultiProcessorCount)");
+        if (occ < 1) return fail(AFA_ERR_BAD_ARG, "kernel does not fit on an SM (smem %zu)", smem);
+        ctas = occ * sms;
+        if (n_cache < 32) cache[n_cache++] = Cache{kernel, dev, ctas};
+    }
+    const uint64_t max_warps = (uint64_t)ctas * kNW;
+    const uint64_t tiles_per_warp = (n_wtiles + max_warps - 1) / max_warps;
+    const uint64_t warps = (n_wtiles + tiles_per_warp - 1) / tiles_per_warp;
+    *grid = (uint32_t)((warps + kNW - 1) / kNW);
+    return 0;
+}
+
 
 int default_chunks(int which, int dtype) {
     (void)which;
@@ -66,10 +117,10 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     const int64_t rows = batch * channels;
     const int64_t nseg = T > 0 ? (T + pl->L - 1) / pl->L : 0;
     const int64_t total_segs = rows * nseg;
-    if (total_segs >= (1ll << 31) - kNT) return fail(AFA_ERR_TOO_LARGE, "batch*channels*ceil(T/%d)=%lld exceeds 2^31", pl->L, (long long)total_segs);
+    if (total_segs >= (1ll << 31) - 64) return fail(AFA_ERR_TOO_LARGE, "batch*channels*ceil(T/%d)=%lld exceeds 2^31", pl->L, (long long)total_segs);
     pl->nseg = (uint32_t)nseg;
     pl->total_segs = (uint32_t)total_segs;
-    pl->grid = (uint32_t)((total_segs + kNT - 1) / kNT);
+    pl->n_wtiles = (uint32_t)((total_segs + 31) / 32);
     const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
     const uintptr_t ptr_or = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
     if (ptr_or & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
@@ -100,37 +151,35 @@ void fold_bwd_taps(const float* up, const float* dn, afa::BwdTaps* t) {
     t->hi[2] = dn[11];
 }
 
-template <typename K>
-int prepare(K kernel, size_t smem) {
-    // set the attribute once per (kernel, device) per thread
-    static thread_local const void* last = nullptr;
-    static thread_local int last_dev = -1;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    if (last == (const void*)kernel && last_dev == dev) return 0;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    last = (const void*)kernel;
-    last_dev = dev;
-    return 0;
+afa::Geometry make_geometry(const Plan& pl, int64_t batch, int64_t channels, int64_t T, int flags) {
+    afa::Geometry g;
+    g.total = batch * channels * T;
+    g.total_segs = pl.total_segs;
+    g.n_wtiles = pl.n_wtiles;
+    g.nseg = make_fastdiv(pl.nseg);
+    g.chan = make_fastdiv((uint32_t)channels);
+    g.T = (int32_t)T;
+    g.flags = flags;
+    return g;
 }
 
 template <typename T, int CH, bool AL>
-int launch_fwd_t(const afa::FwdArgs& a, uint32_t grid, cudaStream_t st) {
-    auto k = afa::afa_fwd_kernel<T, CH, kNT, AL>;
-    const size_t smem = afa::Tile<T, CH, kNT>::fwd_smem();
-    if (int rc = prepare(k, smem)) return rc;
+int launch_fwd_t(const afa::FwdArgs& a, cudaStream_t st) {
+    auto k = afa::afa_fwd_kernel<T, CH, kNW, AL>;
+    const size_t smem = afa::WarpTile<T, CH>::fwd_smem(kNW);
+    uint32_t grid = 0;
+    if (int rc = grid_for((const void*)k, smem, a.g.n_wtiles, &grid)) return rc;
     k<<<grid, kNT, smem, st>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_fwd_kernel launch");
 }
 template <typename T, int CH, bool AL>
-int launch_bwd_t(const afa::BwdArgs& a, uint32_t grid, cudaStream_t st) {
-    auto k = afa::afa_bwd_kernel<T, CH, kNT, AL>;
-    const size_t smem = afa::Tile<T, CH, kNT>::bwd_smem();
-    if (int rc = prepare(k, smem)) return rc;
+int launch_bwd_t(const afa::BwdArgs& a, cudaStream_t st) {
+    auto k = afa::afa_bwd_kernel<T, CH, kNW, AL>;
+    const size_t smem = afa::WarpTile<T, CH>::bwd_smem(kNW);
+    uint32_t grid = 0;
+    if (int rc = grid_for((const void*)k, smem, a.g.n_wtiles, &grid)) return rc;
     k<<<grid, kNT, smem, st>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
@@ -141,7 +190,7 @@ template <typename T>
 int launch_fwd(const Plan& pl, const afa::FwdArgs& a, cudaStream_t st) {
 #define X(CH)                                                                                   \
     if (pl.chunks == CH)                                                                        \
-        return pl.aligned ? launch_fwd_t<T, CH, true>(a, pl.grid, st) : launch_fwd_t<T, CH, false>(a, pl.grid, st);
+        return pl.aligned ? launch_fwd_t<T, CH, true>(a, st) : launch_fwd_t<T, CH, false>(a, st);
     AFA_CHUNK_LIST(X)
 #undef X
     return fail(AFA_ERR_BAD_ARG, "no kernel compiled for %d chunks per segment", pl.chunks);
@@ -150,7 +199,7 @@ template <typename T>
 int launch_bwd(const Plan& pl, const afa::BwdArgs& a, cudaStream_t st) {
 #define X(CH)                                                                                   \
     if (pl.chunks == CH)                                                                        \
-        return pl.aligned ? launch_bwd_t<T, CH, true>(a, pl.grid, st) : launch_bwd_t<T, CH, false>(a, pl.grid, st);
+        return pl.aligned ? launch_bwd_t<T, CH, true>(a, st) : launch_bwd_t<T, CH, false>(a, st);
     AFA_CHUNK_LIST(X)
 #undef X
     return fail(AFA_ERR_BAD_ARG, "no kernel compiled for %d chunks per segment", pl.chunks);
@@ -158,12 +207,12 @@ int launch_bwd(const Plan& pl, const afa::BwdArgs& a, cudaStream_t st) {
 
 template <typename T, int CH>
 const void* kernel_ptr(int which, bool aligned) {
-    if (which == 0) return aligned ? (const void*)afa::afa_fwd_kernel<T, CH, kNT, true> : (const void*)afa::afa_fwd_kernel<T, CH, kNT, false>;
-    return aligned ? (const void*)afa::afa_bwd_kernel<T, CH, kNT, true> : (const void*)afa::afa_bwd_kernel<T, CH, kNT, false>;
+    if (which == 0) return aligned ? (const void*)afa::afa_fwd_kernel<T, CH, kNW, true> : (const void*)afa::afa_fwd_kernel<T, CH, kNW, false>;
+    return aligned ? (const void*)afa::afa_bwd_kernel<T, CH, kNW, true> : (const void*)afa::afa_bwd_kernel<T, CH, kNW, false>;
 }
 template <typename T, int CH>
 size_t kernel_smem(int which) {
-    return which == 0 ? afa::Tile<T, CH, kNT>::fwd_smem() : afa::Tile<T, CH, kNT>::bwd_smem();
+    return which == 0 ? afa::WarpTile<T, CH>::fwd_smem(kNW) : afa::WarpTile<T, CH>::bwd_smem(kNW);
 }
 
 }  // namespace
@@ -202,12 +251,7 @@ int afa_activation1d_fwd(const void* x, void* y, const float* alpha, const float
     a.alpha = alpha;
     a.beta = beta;
     fold_fwd_taps(taps_up12, taps_down12, &a.taps);
-    a.total = batch * channels * T;
-    a.total_segs = pl.total_segs;
-    a.nseg = pl.nseg;
-    a.T = (int32_t)T;
-    a.C = (int32_t)channels;
-    a.flags = flags;
+    a.g = make_geometry(pl, batch, channels, T, flags);
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == AFA_DTYPE_F32 ? launch_fwd<float>(pl, a, st) : launch_fwd<__nv_bfloat16>(pl, a, st);
 }
@@ -245,12 +289,7 @@ int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha,
     a.beta = beta;
     a.part = (float*)workspace;
     fold_bwd_taps(taps_up12, taps_down12, &a.taps);
-    a.total = batch * channels * T;
-    a.total_segs = pl.total_segs;
-    a.nseg = pl.nseg;
-    a.T = (int32_t)T;
-    a.C = (int32_t)channels;
-    a.flags = flags;
+    a.g = make_geometry(pl, batch, channels, T, flags);
     int rc = dtype == AFA_DTYPE_F32 ? launch_bwd<float>(pl, a, st) : launch_bwd<__nv_bfloat16>(pl, a, st);
     if (rc) return rc;
     afa::afa_param_grad_finalize<<<(unsigned)channels, afa::kFinalizeThreads, 0, st>>>(

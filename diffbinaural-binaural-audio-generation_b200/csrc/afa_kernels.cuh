@@ -7,20 +7,24 @@
 // Design (DESIGN.md has the long form):
 //   * Rows (batch*channel) are independent.  Every row is cut into SEGMENTS of L = CH*VEC samples
 //     (VEC = elements per 16 bytes, CH odd).  One thread owns one segment and walks it in time order,
-//     keeping the 6-tap polyphase windows and the 6 live output accumulators in registers, so the
+//     keeping the 6-tap polyphase windows and the 7 live output accumulators in register RINGS, so the
 //     2x-rate intermediate never leaves the register file.
-//   * Segments are numbered row-major; a CTA owns NT consecutive segments, which is one CONTIGUOUS
-//     range of the flat [rows*T] array.  That range (+8 halo elements either side) is staged in shared
-//     memory by ONE 1-D bulk TMA copy (cp.async.bulk + mbarrier, SASS UBLKCP); the result tile goes
-//     back with one bulk TMA store.  Global traffic is therefore perfectly coalesced 16-byte aligned
-//     bulk, and no thread spends issue slots on global loads/stores.
-//   * Thread i reads/writes shared memory at a stride of CH 16-byte chunks; CH odd makes every
-//     quarter-warp LDS.128/STS.128 hit 8 distinct 16-byte bank groups -> conflict-free without swizzle.
+//   * Segments are numbered row-major; a WARP owns 32 consecutive segments (a "warp tile"), which is
+//     one CONTIGUOUS range of the flat [rows*T] array.  That range (+8 halo elements either side) is
+//     staged in shared memory by ONE 1-D bulk TMA copy (cp.async.bulk + mbarrier, SASS UBLKCP), the
+//     result is written IN PLACE over the staged input and leaves with one bulk TMA store.
+//   * Warps are autonomous and persistent: each has two stages and two mbarriers of its own, loops
+//     over warp tiles round-robin, and prefetches tile i+1 (TMA) while it walks tile i.  There is no
+//     CTA-wide barrier after start-up and no global load/store instruction in the steady state.
+//   * Lane i touches shared memory at a stride of CH 16-byte chunks; CH odd makes every quarter-warp
+//     LDS.128/STS.128 hit 8 distinct 16-byte bank groups -> conflict-free without swizzle.
+//   * The walk is a ROLLED loop whose body is S steps (S = ring size) with static register indices:
+//     ~7 KB of SASS per mode instead of the 57 KB of a fully unrolled walk (v1 was I-cache bound).
 //   * Replicate padding lives in two places: the x clamp and the clamp of the
 //     ACTIVATED 2x signal.  Warps whose segments all sit >= 5 samples from both row ends take the
-//     branch-free MODE 0 walk; warps touching a row end take MODE 1 (same static schedule, clamped
-//     loads + selects); rows whose length is not a multiple of VEC (no 16-byte alignment, TMA illegal)
-//     run the MODE 2 kernel (scalar staging), still inside this library.
+//     branch-free MODE 0 walk; warps touching a row end take MODE 1 (same schedule + selects); rows
+//     whose length is not a multiple of VEC (no 16-byte alignment, TMA illegal) run the MODE 2 kernel
+//     (scalar staging), still inside this library.
 //   * No tensor cores: a depthwise 12-tap stencil is not a contraction (north_star).
 #pragma once
 #include <cuda_bf16.h>
@@ -29,7 +33,7 @@
 
 namespace afa {
 
-constexpr int kHalo = 8;   // elements staged either side of a CTA's flat range (>= 5 needed)
+constexpr int kHalo = 8;  // elements staged either side of a warp tile's flat range (>= 5 needed)
 
 // Filter taps as kernel parameters (constant bank -> FFMA constant operands).
 struct FwdTaps {
@@ -44,18 +48,29 @@ struct BwdTaps {
     float hi[3];          // folded taps of the right replicate pad of s: gy[T-1], gy[T-2], gy[T-3]
 };
 
+// n / d for 0 <= n < 2^31 by multiply-high (host computes mul/shr; d == 1 -> mul = 0)
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul ? (__umulhi(n, mul) >> shr) : n; }
+};
+
+struct Geometry {
+    int64_t total;        // rows * T
+    uint32_t total_segs;  // rows * nseg
+    uint32_t n_wtiles;    // ceil(total_segs / 32)
+    FastDiv nseg;         // segments per row
+    FastDiv chan;         // channels
+    int32_t T;
+    int32_t flags;
+};
+
 struct FwdArgs {
     const void* x;
     void* y;
     const float* alpha;
     const float* beta;
     FwdTaps taps;
-    int64_t total;        // rows * T
-    uint32_t total_segs;  // rows * nseg
-    uint32_t nseg;        // segments per row
-    int32_t T;
-    int32_t C;
-    int32_t flags;
+    Geometry g;
 };
 struct BwdArgs {
     const void* x;
@@ -63,14 +78,9 @@ struct BwdArgs {
     void* gx;
     const float* alpha;
     const float* beta;
-    float* part;          // [2][total_segs] per-segment parameter-gradient partials
+    float* part;  // [2][total_segs] per-segment parameter-gradient partials
     BwdTaps taps;
-    int64_t total;
-    uint32_t total_segs;
-    uint32_t nseg;
-    int32_t T;
-    int32_t C;
-    int32_t flags;
+    Geometry g;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -114,10 +124,9 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_and_wait() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -171,11 +180,11 @@ __device__ __forceinline__ float snake_f(float u, float a, float ib) {
     return fmaf(ib, sn * sn, u);
 }
 
-// effective parameters of one channel                              activations.py:119-123
-__device__ __forceinline__ void load_params(const float* alpha, const float* beta, int c, int flags, float& a_eff,
-                                            float& b_eff, float& ib) {
-    float a = __ldg(alpha + c);
-    float b = (flags & 2) ? a : __ldg(beta + c);
+// effective parameters of one channel from the raw ones           activations.py:119-123
+__device__ __forceinline__ void effective_params(float a_raw, float b_raw, int flags, float& a_eff, float& b_eff,
+                                                 float& ib) {
+    float a = a_raw;
+    float b = (flags & 2) ? a_raw : b_raw;
     if (flags & 1) {
         a = expf(a);
         b = expf(b);
@@ -185,181 +194,300 @@ __device__ __forceinline__ void load_params(const float* alpha, const float* bet
     ib = 1.0f / (b + 0.000000001f);
 }
 
+// What a walk needs to know to prefetch the warp's NEXT tile once its previous bulk store has
+// drained (issued by lane 0 after the first loop iteration of the walk).
+struct Prefetch {
+    const void* src0;
+    const void* src1;    // second tensor (backward: gy), or nullptr
+    uint32_t dst0, dst1; // shared-memory addresses of the stage being refilled
+    uint32_t bar;        // shared-memory address of that stage's mbarrier
+    uint32_t bytes;      // per tensor; 0 = nothing to prefetch
+};
+__device__ __forceinline__ void issue_prefetch(const Prefetch& pf) {
+    if (pf.bytes) {
+        tma_store_wait_read();   // the stage being refilled was the source of the previous bulk store
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pf.bar),
+                     "r"(pf.src1 ? 2 * pf.bytes : pf.bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pf.dst0),
+                     "l"(pf.src0), "r"(pf.bytes), "r"(pf.bar)
+                     : "memory");
+        if (pf.src1)
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pf.dst1),
+                "l"(pf.src1), "r"(pf.bytes), "r"(pf.bar)
+                : "memory");
+    }
+}
+
+template <int VEC>
+struct RingCfg {
+    static constexpr int S = (VEC == 4) ? 12 : 16;  // ring size = steps per loop body (>= 6 + VEC, multiple of VEC)
+};
+
 // ------------------------------------------------------------------------------------------------
-// forward walk of one segment.  MODE 0: interior (branch-free); 1: touches a row end (16B-aligned
-// rows); 2: rows not 16B-aligned (scalar smem I/O).  xo / yo: offsets of this row's sample 0 inside
-// the staged input / output tiles (may be negative; only in-range positions are ever touched).
+// forward walk of one segment, in place.  MODE 0: interior (branch-free); 1: touches a row end
+// (16B-aligned rows); 2: rows not 16B-aligned (scalar smem I/O).  `row0` points at this row's sample 0
+// inside the staged tile (may lie outside the tile; only in-range positions are touched).
+// Step q handles the 2x-rate pair m = t0 - 3 + q and completes y[t0 + q - 6].
+// X ring: x[t0 - 8 + j] lives in xr[j % S];  accumulator ring: y[t0 + o] lives in ac[o % S].
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
-__device__ __forceinline__ void walk_fwd(const T* __restrict__ sx, T* __restrict__ sy, int xo, int yo, int t0,
-                                         int Tlen, float a, float ib, const FwdTaps& tp) {
-    constexpr int VEC = IO<T>::VEC;
+__device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen, float a, float ib, const FwdTaps& tp,
+                                         const Prefetch& pf, int lane, uint32_t mask) {
+    using io = IO<T>;
+    constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
-    constexpr int NX = L + 16;  // X[j] = x[t0 - 8 + j]
-    float X[NX];
-    float s_first = 0.f, s_last = 0.f;
+    constexpr int S = RingCfg<VEC>::S;
+    constexpr int NFULL = L / S, REM = L % S;
+    T* seg = row0 + t0;
+    float xr[S], ac[S], hold[8];
+    float s_first = 0.f, s_last = 0.f, x_last = 0.f;
 
-    if (MODE == 0) {
-        const T* base = sx + xo + t0 - 8;
+    // ---- preload x[t0-8 .. t0-1] and the edge constants; nothing below reads a neighbour's first 8
+    //      samples again before the final __syncwarp, and nobody overwrites them before it (hold[]).
+    if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < 16 / VEC; ++c) IO<T>::load_chunk(base + c * VEC, &X[c * VEC]);
+        for (int c = 0; c < 8 / VEC; ++c) io::load_chunk(seg - 8 + c * VEC, &xr[c * VEC]);
     } else {
-        const T* row = sx + xo;
 #pragma unroll
-        for (int j = 2; j < L + 14; ++j) {
-            const int t = min(max(t0 - 8 + j, 0), Tlen - 1);  // replicate pad of x      resample.py:32
-            X[j] = IO<T>::load1(row + t);
-        }
-        if (t0 == 0) {  // s[0]: the value the left replicate pad of s repeats             filter.py:98
-            float u = tp.ue[0] * X[10];
+        for (int j = 2; j < 8; ++j) xr[j] = io::load1(row0 + min(max(t0 - 8 + j, 0), Tlen - 1));
+    }
+    if (MODE != 0) {
+        if (t0 == 0) {  // left replicate pad of x, and s[0] which the left pad of s repeats      filter.py:98
+            const float x0 = io::load1(row0);
+            const float x1 = io::load1(row0 + min(1, Tlen - 1));
+            const float x2 = io::load1(row0 + min(2, Tlen - 1));
+            if (MODE == 1) {
 #pragma unroll
-            for (int j = 1; j < 6; ++j) u = fmaf(tp.ue[j], X[10 - j], u);
+                for (int j = 0; j < 8; ++j) xr[j] = x0;
+            }
+            float u = tp.ue[0] * x2;
+            u = fmaf(tp.ue[1], x1, u);
+#pragma unroll
+            for (int j = 2; j < 6; ++j) u = fmaf(tp.ue[j], x0, u);
             s_first = snake_f(u, a, ib);
         }
-        if (Tlen <= t0 + L + 3) {  // s[2T-1]: the value the right replicate pad repeats
-            float u = 0.f;
+        if (Tlen - 1 <= t0 + L + 5) {  // the row ends inside this walk's reach
+            x_last = io::load1(row0 + Tlen - 1);
+            float u = 0.f;             // s[2T-1]: the value the right pad of s repeats
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const int t = min(max(Tlen + 2 - j, 0), Tlen - 1);
-                u = fmaf(tp.uo[j], IO<T>::load1(row + t), u);
-            }
+            for (int j = 0; j < 6; ++j) u = fmaf(tp.uo[j], io::load1(row0 + min(max(Tlen + 2 - j, 0), Tlen - 1)), u);
             s_last = snake_f(u, a, ib);
         }
     }
+    __syncwarp(mask);
 
-    float acc[L];
+    // one step; Q is the static part of the step index (ring positions), q the dynamic step number
+    auto step = [&](const int Q, const int q, const bool first_iter) {
+        // --- bring in x[t0+q .. ] = X[q+8 ..]
+        if (MODE != 2) {
+            if ((Q + 8) % VEC == 0) {
+                float* dst = &xr[(Q + 8) % S];
+                io::load_chunk(seg + q, dst);
+                if (MODE == 1) {
 #pragma unroll
-    for (int q = 0; q < L + 6; ++q) {  // pair index m = t0 - 3 + q : produces s[2m], s[2m+1]
-        if (MODE == 0) {
-            if ((q + 8) % VEC == 0 && (q + 8) >= 16) {
-                IO<T>::load_chunk(sx + xo + t0 + q, &X[q + 8]);
+                    for (int e = 0; e < VEC; ++e) dst[e] = (t0 + q + e > Tlen - 1) ? x_last : dst[e];
+                }
             }
+        } else {
+            xr[(Q + 8) % S] = io::load1(row0 + min(t0 + q, Tlen - 1));
         }
-        float ue = tp.ue[0] * X[q + 7];
-        float uo = tp.uo[0] * X[q + 8];
+        // --- polyphase upsample: u[2m] from x[m-3..m+2], u[2m+1] from x[m-2..m+3]     resample.py:32-36
+        float ue = tp.ue[0] * xr[(Q + 7) % S];
+        float uo = tp.uo[0] * xr[(Q + 8) % S];
 #pragma unroll
         for (int j = 1; j < 6; ++j) {
-            ue = fmaf(tp.ue[j], X[q + 7 - j], ue);
-            uo = fmaf(tp.uo[j], X[q + 8 - j], uo);
+            ue = fmaf(tp.ue[j], xr[(Q + 7 - j + S) % S], ue);
+            uo = fmaf(tp.uo[j], xr[(Q + 8 - j + S) % S], uo);
         }
         float se = snake_f(ue, a, ib);
         float so = snake_f(uo, a, ib);
         if (MODE != 0) {
             const int m = t0 - 3 + q;
-            if (q < 3) {
+            if (Q < 3 && first_iter) {
                 if (m < 0) { se = s_first; so = s_first; }
             }
             if (m >= Tlen) { se = s_last; so = s_last; }
         }
-        // scatter into the (at most 6 live) output accumulators: s[2m+1] -> y[m+3-j] (tap 2j),
-        // s[2m] -> y[m+2-j] (tap 2j+1)
+        // --- scatter into the live accumulators: s[2m+1] -> y[m+3-j] (tap 2j), s[2m] -> y[m+2-j] (tap 2j+1)
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const int o = q - j;
-            if (o >= 0 && o < L) acc[o] = (j == 0) ? tp.dn[0] * so : fmaf(tp.dn[2 * j], so, acc[o]);
+            if (!(first_iter && Q - j < 0)) {
+                float& acc = ac[(Q - j + 2 * S) % S];
+                acc = (j == 0) ? tp.dn[0] * so : fmaf(tp.dn[2 * j], so, acc);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const int o = q - 1 - j;
-            if (o >= 0 && o < L) acc[o] = fmaf(tp.dn[2 * j + 1], se, acc[o]);
+            if (!(first_iter && Q - 1 - j < 0)) {
+                float& acc = ac[(Q - 1 - j + 2 * S) % S];
+                acc = fmaf(tp.dn[2 * j + 1], se, acc);
+            }
         }
-        // y[t0 + q - 6] is complete now
-        const int od = q - 6;
+        // --- y[t0 + q - 6] is complete
         if (MODE != 2) {
-            if (od >= 0 && (od % VEC) == VEC - 1) {
-                const int c0 = od - (VEC - 1);
-                if (MODE == 0 || t0 + c0 < Tlen) IO<T>::store_chunk(sy + yo + t0 + c0, &acc[c0]);
+            if ((Q - 6 + 2 * S) % VEC == VEC - 1 && !(first_iter && Q < 6)) {
+                const int c0 = q - 6 - (VEC - 1);                     // first sample of the finished chunk
+                float v[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[e] = ac[(Q - 6 - (VEC - 1) + e + 2 * S) % S];
+                if (c0 < 8) {                                          // a neighbour may still need these x
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = v[e];
+                } else if (MODE == 0 || t0 + c0 < Tlen) {
+                    io::store_chunk(seg + c0, v);
+                }
             }
         } else {
-            if (od >= 0 && t0 + od < Tlen) IO<T>::store1(sy + yo + t0 + od, acc[od]);
+            if (!(first_iter && Q < 6)) {
+                const int o = q - 6;
+                const float v = ac[(Q - 6 + 2 * S) % S];
+                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = v;
+                else if (t0 + o < Tlen) io::store1(seg + o, v);
+            }
         }
+    };
+
+    // prologue: q = 0..5 (static; dead work is eliminated)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) step(q, q, true);
+    // main loop: q = 6 .. L+5, S steps per trip, ring positions static inside the body
+#pragma unroll 1
+    for (int it = 0; it < NFULL + (REM ? 1 : 0); ++it) {
+        const int qb = 6 + it * S;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            if (REM != 0 && k == REM) {
+                if (it == NFULL) break;
+            }
+            step(6 + k, qb + k, false);
+        }
+        if (it == 0 && lane == 0) issue_prefetch(pf);
+    }
+    __syncwarp(mask);  // every lane has finished reading its right halo: now the first 8 outputs may land
+    if (MODE != 2) {
+#pragma unroll
+        for (int c = 0; c < 8 / VEC; ++c)
+            if (MODE == 0 || t0 + c * VEC < Tlen) io::store_chunk(seg + c * VEC, &hold[c * VEC]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            if (t0 + o < Tlen) io::store1(seg + o, hold[o]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward walk of one segment: recomputes u from x, forms ds from gy, du = ds*(1 + a*ib*sin(2 a u)),
-// scatters du into dx, and accumulates the segment's share of d/dalpha_eff, d/dbeta_eff.
+// scatters du into dx (written in place over x), and accumulates the segment's share of
+// d/dalpha_eff, d/dbeta_eff.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
-__device__ __forceinline__ void walk_bwd(const T* __restrict__ sx, const T* __restrict__ sg, T* __restrict__ sy,
-                                         int xo, int yo, int t0, int Tlen, float a, float ib, const BwdTaps& tp,
+__device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restrict__ grow0, int t0, int Tlen, float a,
+                                         float ib, const BwdTaps& tp, const Prefetch& pf, int lane, uint32_t mask,
                                          float& ga_out, float& gb_out) {
-    constexpr int VEC = IO<T>::VEC;
+    using io = IO<T>;
+    constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
-    constexpr int NX = L + 16;
-    float X[NX], G[NX];
-    float d_lo = 0.f, d_hi = 0.f;
+    constexpr int S = RingCfg<VEC>::S;
+    constexpr int NFULL = L / S, REM = L % S;
+    T* seg = row0 + t0;
+    const T* gseg = grow0 + t0;
+    float xr[S], gr[S], ac[S], hold[8];
+    float d_lo = 0.f, d_hi = 0.f, x_last = 0.f;
 
-    if (MODE == 0) {
-        const T* bx = sx + xo + t0 - 8;
-        const T* bg = sg + xo + t0 - 8;
+    if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < 16 / VEC; ++c) {
-            IO<T>::load_chunk(bx + c * VEC, &X[c * VEC]);
-            IO<T>::load_chunk(bg + c * VEC, &G[c * VEC]);
+        for (int c = 0; c < 8 / VEC; ++c) {
+            io::load_chunk(seg - 8 + c * VEC, &xr[c * VEC]);
+            io::load_chunk(gseg - 8 + c * VEC, &gr[c * VEC]);
         }
     } else {
-        const T* rx = sx + xo;
-        const T* rg = sg + xo;
 #pragma unroll
-        for (int j = 2; j < L + 14; ++j) {
+        for (int j = 2; j < 8; ++j) {
             const int t = t0 - 8 + j;
-            const int tc = min(max(t, 0), Tlen - 1);
-            X[j] = IO<T>::load1(rx + tc);                                   // replicate pad of x
-            const float g = IO<T>::load1(rg + tc);
-            G[j] = (t >= 0 && t < Tlen) ? g : 0.f;                          // gy does not extend
+            xr[j] = io::load1(row0 + min(max(t, 0), Tlen - 1));
+            gr[j] = (t >= 0) ? io::load1(grow0 + max(t, 0)) : 0.f;
         }
-        if (t0 == 0) d_lo = fmaf(tp.lo[2], G[10], fmaf(tp.lo[1], G[9], tp.lo[0] * G[8]));
-        if (Tlen - 1 <= t0 + L + 2) {  // the walk reaches pair m = T-1, whose odd member s[2T-1] carries the fold
+    }
+    if (MODE != 0) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < S; ++i) ac[i] = 0.f;   // accumulators left of the row start only ever see FMAs
+        if (t0 == 0) {
+            if (MODE == 1) {
+                const float x0 = io::load1(row0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { xr[j] = x0; gr[j] = 0.f; }   // replicate x, gy does not extend
+            }
+            // adjoint of the left replicate pad of s: taps that fell on the pad fold onto s[0]
+            const float g0 = io::load1(grow0);
+            const float g1 = (Tlen > 1) ? io::load1(grow0 + min(1, Tlen - 1)) : 0.f;
+            const float g2 = (Tlen > 2) ? io::load1(grow0 + min(2, Tlen - 1)) : 0.f;
+            d_lo = fmaf(tp.lo[2], g2, fmaf(tp.lo[1], g1, tp.lo[0] * g0));
+        }
+        if (Tlen - 1 <= t0 + L + 5) {
+            x_last = io::load1(row0 + Tlen - 1);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {   // adjoint of the right pad of s folds onto s[2T-1]
                 const int t = Tlen - 1 - i;
-                const float g = IO<T>::load1(rg + max(t, 0));
+                const float g = io::load1(grow0 + max(t, 0));
                 d_hi = fmaf(tp.hi[i], (t >= 0) ? g : 0.f, d_hi);
             }
         }
     }
+    __syncwarp(mask);
 
     const float a2 = 2.0f * a;
     const float iba = ib * a;
     float ga = 0.f, gb = 0.f;
-    constexpr int AO = (MODE == 0) ? 0 : 3;  // accumulators cover o in [-AO, L + AO)
-    float acc[L + 2 * AO];
-    if (MODE != 0) {
-        acc[0] = 0.f; acc[1] = 0.f; acc[2] = 0.f;
-    }
 
+    auto step = [&](const int Q, const int q, const bool first_iter) {
+        if (MODE != 2) {
+            if ((Q + 8) % VEC == 0) {
+                float* dx = &xr[(Q + 8) % S];
+                float* dg = &gr[(Q + 8) % S];
+                io::load_chunk(seg + q, dx);
+                io::load_chunk(gseg + q, dg);
+                if (MODE == 1) {
 #pragma unroll
-    for (int q = 0; q < L + 6; ++q) {
-        if (MODE == 0) {
-            if ((q + 8) % VEC == 0 && (q + 8) >= 16) {
-                IO<T>::load_chunk(sx + xo + t0 + q, &X[q + 8]);
-                IO<T>::load_chunk(sg + xo + t0 + q, &G[q + 8]);
+                    for (int e = 0; e < VEC; ++e) {
+                        const bool past = t0 + q + e > Tlen - 1;
+                        dx[e] = past ? x_last : dx[e];
+                        dg[e] = past ? 0.f : dg[e];
+                    }
+                }
             }
+        } else {
+            const int t = t0 + q;
+            xr[(Q + 8) % S] = io::load1(row0 + min(t, Tlen - 1));
+            const float g = io::load1(grow0 + min(t, Tlen - 1));
+            gr[(Q + 8) % S] = (t < Tlen) ? g : 0.f;
         }
-        float ue = tp.ue[0] * X[q + 7];
-        float uo = tp.uo[0] * X[q + 8];
-        float de = tp.de[0] * G[q + 7];
-        float dd = tp.dod[0] * G[q + 8];
+        float ue = tp.ue[0] * xr[(Q + 7) % S];
+        float uo = tp.uo[0] * xr[(Q + 8) % S];
+        float de = tp.de[0] * gr[(Q + 7) % S];
+        float dd = tp.dod[0] * gr[(Q + 8) % S];
 #pragma unroll
         for (int j = 1; j < 6; ++j) {
-            ue = fmaf(tp.ue[j], X[q + 7 - j], ue);
-            uo = fmaf(tp.uo[j], X[q + 8 - j], uo);
-            de = fmaf(tp.de[j], G[q + 7 - j], de);
-            dd = fmaf(tp.dod[j], G[q + 8 - j], dd);
+            ue = fmaf(tp.ue[j], xr[(Q + 7 - j + S) % S], ue);
+            uo = fmaf(tp.uo[j], xr[(Q + 8 - j + S) % S], uo);
+            de = fmaf(tp.de[j], gr[(Q + 7 - j + S) % S], de);
+            dd = fmaf(tp.dod[j], gr[(Q + 8 - j + S) % S], dd);
         }
+        const int m = t0 - 3 + q;
         if (MODE != 0) {
-            const int m = t0 - 3 + q;
-            if (q < 3) {
+            if (Q < 3 && first_iter) {
                 if (m < 0) { de = 0.f; dd = 0.f; }
             }
             if (m >= Tlen) { de = 0.f; dd = 0.f; }
-            if (q == 3) {
+            if (Q == 3 && first_iter) {
                 if (t0 == 0) de += d_lo;
             }
             if (m == Tlen - 1) dd += d_hi;
         }
-        const bool own = (q >= 3 && q < L + 3);  // s[2m], s[2m+1] belong to this segment
+        // s[2m], s[2m+1] belong to this segment for q in [3, L+3)
+        const bool own = first_iter ? (Q >= 3) : (q < L + 3);
         float due, duo;
         {
             const float ph = a2 * ue;
@@ -381,221 +509,345 @@ __device__ __forceinline__ void walk_bwd(const T* __restrict__ sx, const T* __re
                 gb += fmaf(-dd, cs, dd);
             }
         }
+        constexpr int LOW = (MODE == 0) ? 0 : -3;   // edge modes also keep dx_ext[-3..-1] (folded below)
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const int o = q - j;
-            if (o >= -AO && o < L + AO) acc[o + AO] = (j == 0) ? tp.uo[0] * duo : fmaf(tp.uo[j], duo, acc[o + AO]);
+            if (!(first_iter && Q - j < LOW)) {
+                float& acc = ac[(Q - j + 2 * S) % S];
+                acc = (j == 0) ? tp.uo[0] * duo : fmaf(tp.uo[j], duo, acc);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const int o = q - 1 - j;
-            if (o >= -AO && o < L + AO) acc[o + AO] = fmaf(tp.ue[j], due, acc[o + AO]);
+            if (!(first_iter && Q - 1 - j < LOW)) {
+                float& acc = ac[(Q - 1 - j + 2 * S) % S];
+                acc = fmaf(tp.ue[j], due, acc);
+            }
         }
-        const int od = q - 6;
-        if (od >= 0) {
+        if (!(first_iter && Q < 6)) {
+            const int o = q - 6;
+            float& done = ac[(Q - 6 + 2 * S) % S];
             if (MODE != 0) {
-                // fold the adjoint of the x replicate pad onto the row's first / last sample
-                if (od == 0) {
-                    if (t0 == 0) acc[AO] += acc[0] + acc[1] + acc[2];
+                // adjoint of the x replicate pad: fold dx_ext beyond the row onto its first / last sample
+                if (Q == 6 && o == 0) {
+                    if (t0 == 0) done += ac[(2 * S - 3) % S] + ac[(2 * S - 2) % S] + ac[(2 * S - 1) % S];
                 }
-                if (t0 + od == Tlen - 1) acc[od + AO] += acc[od + AO + 1] + acc[od + AO + 2] + acc[od + AO + 3];
+                if (t0 + o == Tlen - 1)
+                    done += ac[(Q - 5 + 2 * S) % S] + ac[(Q - 4 + 2 * S) % S] + ac[(Q - 3 + 2 * S) % S];
             }
             if (MODE != 2) {
-                if ((od % VEC) == VEC - 1) {
-                    const int c0 = od - (VEC - 1);
-                    if (MODE == 0 || t0 + c0 < Tlen) IO<T>::store_chunk(sy + yo + t0 + c0, &acc[c0 + AO]);
+                if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
+                    const int c0 = o - (VEC - 1);
+                    float v[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) v[e] = ac[(Q - 6 - (VEC - 1) + e + 2 * S) % S];
+                    if (c0 < 8) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = v[e];
+                    } else if (MODE == 0 || t0 + c0 < Tlen) {
+                        io::store_chunk(seg + c0, v);
+                    }
                 }
             } else {
-                if (t0 + od < Tlen) IO<T>::store1(sy + yo + t0 + od, acc[od + AO]);
+                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = done;
+                else if (t0 + o < Tlen) io::store1(seg + o, done);
             }
         }
+    };
+
+#pragma unroll
+    for (int q = 0; q < 6; ++q) step(q, q, true);
+#pragma unroll 1
+    for (int it = 0; it < NFULL + (REM ? 1 : 0); ++it) {
+        const int qb = 6 + it * S;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            if (REM != 0 && k == REM) {
+                if (it == NFULL) break;
+            }
+            step(6 + k, qb + k, false);
+        }
+        if (it == 0 && lane == 0) issue_prefetch(pf);
     }
-    ga_out = ga * ib;                 // sum ds * ib * u * sin(2 a u)
-    gb_out = -0.5f * ib * ib * gb;    // -sum ds * sin^2(a u) * ib^2,  sin^2 = (1 - cos 2au)/2
+    __syncwarp(mask);
+    if (MODE != 2) {
+#pragma unroll
+        for (int c = 0; c < 8 / VEC; ++c)
+            if (MODE == 0 || t0 + c * VEC < Tlen) io::store_chunk(seg + c * VEC, &hold[c * VEC]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            if (t0 + o < Tlen) io::store1(seg + o, hold[o]);
+    }
+    ga_out = ga * ib;               // sum ds * ib * u * sin(2 a u)
+    gb_out = -0.5f * ib * ib * gb;  // -sum ds * sin^2(a u) * ib^2,  sin^2 = (1 - cos 2au)/2
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA frame shared by forward and backward
+// warp-tile bookkeeping
 // ------------------------------------------------------------------------------------------------
-struct TileHdr {
-    uint64_t bar;
-    int64_t flat_lo, flat_hi;  // output range of this CTA in the flat [rows*T] array
-    int64_t ld_lo, ld_hi;      // staged input range (flat range + halo, clipped)
+struct TileDesc {
+    int64_t flat_lo, flat_hi;  // this warp tile's output range in the flat [rows*T] array
+    int64_t ld_lo, ld_hi;      // staged range (flat range + halo, clipped to the array)
+    int64_t row_base;          // row * T of this lane's row
+    uint32_t gid, row;
+    int32_t t0;
+    bool active;               // this lane owns a segment
 };
 
-template <int NT>
-__device__ __forceinline__ void cta_ranges(TileHdr* h, uint32_t total_segs, uint32_t nseg, int T, int L,
-                                           int64_t total, int align_elems) {
-    const uint32_t g0 = blockIdx.x * NT;
-    const uint32_t g1 = min(g0 + NT, total_segs) - 1;
-    const uint32_t ra = g0 / nseg, sa = g0 - ra * nseg;
-    const uint32_t rb = g1 / nseg, sb = g1 - rb * nseg;
-    const int64_t lo = (int64_t)ra * T + (int64_t)sa * L;
-    const int64_t hi = (int64_t)rb * T + min((int64_t)T, (int64_t)(sb + 1) * L);
-    int64_t llo = lo - kHalo, lhi = hi + kHalo;
-    if (llo < 0) llo = 0;
-    if (lhi > total) lhi = total;
-    (void)align_elems;
-    h->flat_lo = lo;
-    h->flat_hi = hi;
-    h->ld_lo = llo;
-    h->ld_hi = lhi;
+template <int L>
+__device__ __forceinline__ TileDesc describe_tile(uint32_t wt, int lane, const Geometry& g) {
+    TileDesc d;
+    const uint32_t gid_first = wt * 32u;
+    const uint32_t last_lane = min(31u, g.total_segs - 1u - gid_first);
+    d.gid = gid_first + (uint32_t)lane;
+    d.active = (uint32_t)lane <= last_lane;
+    const uint32_t gidc = d.active ? d.gid : gid_first + last_lane;
+    d.row = g.nseg.div(gidc);
+    const uint32_t seg = gidc - d.row * g.nseg.d;
+    d.t0 = (int32_t)(seg * (uint32_t)L);
+    d.row_base = (int64_t)d.row * g.T;
+    const int64_t lo = d.row_base + d.t0;
+    const int64_t hi = d.row_base + min((int64_t)g.T, (int64_t)d.t0 + L);
+    d.flat_lo = __shfl_sync(0xffffffffu, lo, 0);
+    d.flat_hi = __shfl_sync(0xffffffffu, hi, (int)last_lane);
+    d.ld_lo = max((int64_t)0, d.flat_lo - kHalo);
+    d.ld_hi = min(g.total, d.flat_hi + kHalo);
+    return d;
 }
 
-template <typename T, int CH, int NT>
-struct Tile {
+template <typename T, int CH>
+struct WarpTile {
     static constexpr int VEC = IO<T>::VEC;
     static constexpr int L = CH * VEC;
-    static constexpr int kInElems = NT * L + 2 * kHalo + 2 * VEC;  // staged input tile (+ slack for chunk over-read)
-    static constexpr int kOutElems = NT * L;
-    static constexpr int kHdrBytes = 128;
-    static constexpr size_t fwd_smem() { return kHdrBytes + sizeof(T) * (size_t)(kInElems + kOutElems); }
-    static constexpr size_t bwd_smem() { return kHdrBytes + sizeof(T) * (size_t)(2 * kInElems + kOutElems); }
+    static constexpr int kStageElems = 32 * L + 2 * kHalo;               // one tensor, one stage
+    static constexpr size_t kStageBytes = sizeof(T) * (size_t)kStageElems;  // multiple of 16
+    static constexpr size_t fwd_smem(int nw) { return 128 + (size_t)nw * 2 * kStageBytes; }
+    static constexpr size_t bwd_smem(int nw) { return 128 + (size_t)nw * 2 * 2 * kStageBytes; }
 };
 
-template <typename T, int CH, int NT, bool ALIGNED>
-__global__ void __launch_bounds__(NT) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
-    using TL = Tile<T, CH, NT>;
-    constexpr int L = TL::L;
+// ------------------------------------------------------------------------------------------------
+// forward kernel: persistent, one autonomous pipeline per warp
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CH, int NW, bool ALIGNED>
+__global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? 6 : 5) : 1) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
+    using WT = WarpTile<T, CH>;
+    constexpr int L = WT::L;
+    static_assert(NW * 2 * sizeof(uint64_t) <= 128, "barrier block");
     extern __shared__ __align__(128) unsigned char smem[];
-    TileHdr* hdr = reinterpret_cast<TileHdr*>(smem);
-    T* s_in = reinterpret_cast<T*>(smem + TL::kHdrBytes);
-    T* s_out = s_in + TL::kInElems;
-
-    const int tid = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * 2;
+    T* stages = reinterpret_cast<T*>(smem + 128) + (size_t)warp * 2 * WT::kStageElems;
+    const Geometry& g = args.g;
     const T* gx = static_cast<const T*>(args.x);
     T* gy = static_cast<T*>(args.y);
 
-    if (tid == 0) {
-        cta_ranges<NT>(hdr, args.total_segs, args.nseg, args.T, L, args.total, TL::VEC);
-        if (ALIGNED) {
-            mbar_init(&hdr->bar, 1);
-            fence_mbar_init();
-            const uint32_t bytes = (uint32_t)((hdr->ld_hi - hdr->ld_lo) * (int64_t)sizeof(T));
-            mbar_expect_tx(&hdr->bar, bytes);
-            tma_load_1d(s_in, gx + hdr->ld_lo, bytes, &hdr->bar);
-        }
-    }
-
-    // per-thread segment coordinates and channel parameters (overlaps the bulk copy)
-    const uint32_t gid = blockIdx.x * NT + tid;
-    const bool active = gid < args.total_segs;
-    uint32_t row = 0, seg = 0;
-    float a_eff = 1.f, b_eff = 1.f, ib = 1.f;
-    if (active) {
-        row = gid / args.nseg;
-        seg = gid - row * args.nseg;
-        load_params(args.alpha, args.beta, (int)(row % (uint32_t)args.C), args.flags, a_eff, b_eff, ib);
-    }
-    const int t0 = (int)seg * L;
-    __syncthreads();
-    const int64_t flat_lo = hdr->flat_lo, flat_hi = hdr->flat_hi, ld_lo = hdr->ld_lo, ld_hi = hdr->ld_hi;
-    const int xo = (int)((int64_t)row * args.T - ld_lo);
-    const int yo = (int)((int64_t)row * args.T - flat_lo);
+    const uint32_t GW = gridDim.x * NW;
+    uint32_t wt = blockIdx.x * NW + warp;
+    if (wt >= g.n_wtiles) return;
 
     if (ALIGNED) {
-        mbar_wait(&hdr->bar, 0);
-        const bool fast = active && t0 >= 5 && (t0 + L + 5 < args.T);
-        if (__all_sync(0xffffffffu, fast)) {
-            walk_fwd<T, CH, 0>(s_in, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps);
-        } else if (active) {
-            walk_fwd<T, CH, 1>(s_in, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps);
+        if (lane == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_mbar_init();
         }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_1d(gy + flat_lo, s_out, (uint32_t)((flat_hi - flat_lo) * (int64_t)sizeof(T)));
-            tma_store_commit_and_wait();
-        }
-    } else {
-        const int n_in = (int)(ld_hi - ld_lo);
-        for (int i = tid; i < n_in; i += NT) s_in[i] = gx[ld_lo + i];
-        __syncthreads();
-        if (active) walk_fwd<T, CH, 2>(s_in, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps);
-        __syncthreads();
-        const int n_out = (int)(flat_hi - flat_lo);
-        for (int i = tid; i < n_out; i += NT) gy[flat_lo + i] = s_out[i];
+        __syncwarp();
     }
+    float a_raw = 0.f, b_raw = 0.f;
+    {
+        const TileDesc d0 = describe_tile<L>(wt, lane, g);
+        if (ALIGNED && lane == 0) {
+            const uint32_t bytes = (uint32_t)((d0.ld_hi - d0.ld_lo) * (int64_t)sizeof(T));
+            mbar_expect_tx(&bars[0], bytes);
+            tma_load_1d(stages, gx + d0.ld_lo, bytes, &bars[0]);
+        }
+        const uint32_t c = d0.row - g.chan.div(d0.row) * g.chan.d;
+        a_raw = __ldg(args.alpha + c);
+        b_raw = (g.flags & 2) ? a_raw : __ldg(args.beta + c);
+    }
+    uint32_t phase = 0;  // bit s = parity to wait for on stage s
+    int st = 0;
+    for (;;) {
+        const uint32_t nwt = wt + GW;
+        const bool has_next = nwt < g.n_wtiles;
+        float a_nraw = 0.f, b_nraw = 0.f;
+        Prefetch pf{nullptr, nullptr, 0u, 0u, 0u, 0u};
+        if (has_next) {
+            const TileDesc nxt = describe_tile<L>(nwt, lane, g);
+            const uint32_t c = nxt.row - g.chan.div(nxt.row) * g.chan.d;
+            a_nraw = __ldg(args.alpha + c);
+            b_nraw = (g.flags & 2) ? a_nraw : __ldg(args.beta + c);
+            if (ALIGNED) {
+                pf.src0 = gx + nxt.ld_lo;
+                pf.dst0 = smem_u32(stages + (size_t)(st ^ 1) * WT::kStageElems);
+                pf.bar = smem_u32(&bars[st ^ 1]);
+                pf.bytes = (uint32_t)((nxt.ld_hi - nxt.ld_lo) * (int64_t)sizeof(T));
+            }
+        }
+        const TileDesc cur = describe_tile<L>(wt, lane, g);
+        T* tile = stages + (size_t)st * WT::kStageElems;
+        float a_eff, b_eff, ib;
+        effective_params(a_raw, b_raw, g.flags, a_eff, b_eff, ib);
+        T* row0 = tile + (cur.row_base - cur.ld_lo);
+        const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
+
+        if (ALIGNED) {
+            mbar_wait(&bars[st], (phase >> st) & 1u);
+            phase ^= (1u << st);
+            const bool fast = cur.active && cur.t0 >= 5 && (cur.t0 + L + 5 < g.T);
+            if (__all_sync(0xffffffffu, fast)) {
+                walk_fwd<T, CH, 0>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, 0xffffffffu);
+            } else if (cur.active) {
+                walk_fwd<T, CH, 1>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_1d(gy + cur.flat_lo, tile + (cur.flat_lo - cur.ld_lo),
+                             (uint32_t)((cur.flat_hi - cur.flat_lo) * (int64_t)sizeof(T)));
+                tma_store_commit();
+            }
+        } else {
+            const int n_in = (int)(cur.ld_hi - cur.ld_lo);
+            for (int i = lane; i < n_in; i += 32) tile[i] = gx[cur.ld_lo + i];
+            __syncwarp();
+            if (cur.active) walk_fwd<T, CH, 2>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask);
+            __syncwarp();
+            const int n_out = (int)(cur.flat_hi - cur.flat_lo);
+            const T* src = tile + (cur.flat_lo - cur.ld_lo);
+            for (int i = lane; i < n_out; i += 32) gy[cur.flat_lo + i] = src[i];
+            __syncwarp();
+        }
+        if (!has_next) break;
+        wt = nwt;
+        a_raw = a_nraw;
+        b_raw = b_nraw;
+        st ^= 1;
+    }
+    if (ALIGNED && lane == 0) tma_store_wait_read();  // shared memory must outlive the last bulk store's reads
 }
 
-template <typename T, int CH, int NT, bool ALIGNED>
-__global__ void __launch_bounds__(NT) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
-    using TL = Tile<T, CH, NT>;
-    constexpr int L = TL::L;
+// ------------------------------------------------------------------------------------------------
+// backward kernel: same frame, two staged tensors (x, gy), gx written in place over x
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CH, int NW, bool ALIGNED>
+__global__ void __launch_bounds__(NW * 32, ALIGNED ? 4 : 1) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
+    using WT = WarpTile<T, CH>;
+    constexpr int L = WT::L;
+    static_assert(NW * 2 * sizeof(uint64_t) <= 128, "barrier block");
     extern __shared__ __align__(128) unsigned char smem[];
-    TileHdr* hdr = reinterpret_cast<TileHdr*>(smem);
-    T* s_x = reinterpret_cast<T*>(smem + TL::kHdrBytes);
-    T* s_g = s_x + TL::kInElems;
-    T* s_out = s_g + TL::kInElems;
-
-    const int tid = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * 2;
+    // per warp: [stage 0: x | gy][stage 1: x | gy]
+    T* stages = reinterpret_cast<T*>(smem + 128) + (size_t)warp * 4 * WT::kStageElems;
+    const Geometry& g = args.g;
     const T* px = static_cast<const T*>(args.x);
     const T* pg = static_cast<const T*>(args.gy);
     T* po = static_cast<T*>(args.gx);
 
-    if (tid == 0) {
-        cta_ranges<NT>(hdr, args.total_segs, args.nseg, args.T, L, args.total, TL::VEC);
-        if (ALIGNED) {
-            mbar_init(&hdr->bar, 1);
-            fence_mbar_init();
-            const uint32_t bytes = (uint32_t)((hdr->ld_hi - hdr->ld_lo) * (int64_t)sizeof(T));
-            mbar_expect_tx(&hdr->bar, 2 * bytes);
-            tma_load_1d(s_x, px + hdr->ld_lo, bytes, &hdr->bar);
-            tma_load_1d(s_g, pg + hdr->ld_lo, bytes, &hdr->bar);
-        }
-    }
-
-    const uint32_t gid = blockIdx.x * NT + tid;
-    const bool active = gid < args.total_segs;
-    uint32_t row = 0, seg = 0;
-    float a_eff = 1.f, b_eff = 1.f, ib = 1.f;
-    if (active) {
-        row = gid / args.nseg;
-        seg = gid - row * args.nseg;
-        load_params(args.alpha, args.beta, (int)(row % (uint32_t)args.C), args.flags, a_eff, b_eff, ib);
-    }
-    const int t0 = (int)seg * L;
-    __syncthreads();
-    const int64_t flat_lo = hdr->flat_lo, flat_hi = hdr->flat_hi, ld_lo = hdr->ld_lo, ld_hi = hdr->ld_hi;
-    const int xo = (int)((int64_t)row * args.T - ld_lo);
-    const int yo = (int)((int64_t)row * args.T - flat_lo);
-    float ga = 0.f, gb = 0.f;
+    const uint32_t GW = gridDim.x * NW;
+    uint32_t wt = blockIdx.x * NW + warp;
+    if (wt >= g.n_wtiles) return;
 
     if (ALIGNED) {
-        mbar_wait(&hdr->bar, 0);
-        const bool fast = active && t0 >= 5 && (t0 + L + 5 < args.T);
-        if (__all_sync(0xffffffffu, fast)) {
-            walk_bwd<T, CH, 0>(s_x, s_g, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps, ga, gb);
-        } else if (active) {
-            walk_bwd<T, CH, 1>(s_x, s_g, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps, ga, gb);
+        if (lane == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_mbar_init();
         }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_1d(po + flat_lo, s_out, (uint32_t)((flat_hi - flat_lo) * (int64_t)sizeof(T)));
-            tma_store_commit_and_wait();
-        }
-    } else {
-        const int n_in = (int)(ld_hi - ld_lo);
-        for (int i = tid; i < n_in; i += NT) {
-            s_x[i] = px[ld_lo + i];
-            s_g[i] = pg[ld_lo + i];
-        }
-        __syncthreads();
-        if (active) walk_bwd<T, CH, 2>(s_x, s_g, s_out, xo, yo, t0, args.T, a_eff, ib, args.taps, ga, gb);
-        __syncthreads();
-        const int n_out = (int)(flat_hi - flat_lo);
-        for (int i = tid; i < n_out; i += NT) po[flat_lo + i] = s_out[i];
+        __syncwarp();
     }
-    if (active) {
-        // gradients w.r.t. the RAW parameters: d exp(p)/dp = exp(p)            activations.py:121-123
-        if (args.flags & 1) {
-            ga *= a_eff;
-            gb *= b_eff;
+    float a_raw = 0.f, b_raw = 0.f;
+    {
+        const TileDesc d0 = describe_tile<L>(wt, lane, g);
+        if (ALIGNED && lane == 0) {
+            const uint32_t bytes = (uint32_t)((d0.ld_hi - d0.ld_lo) * (int64_t)sizeof(T));
+            mbar_expect_tx(&bars[0], 2 * bytes);
+            tma_load_1d(stages, px + d0.ld_lo, bytes, &bars[0]);
+            tma_load_1d(stages + WT::kStageElems, pg + d0.ld_lo, bytes, &bars[0]);
         }
-        args.part[gid] = ga;
-        args.part[(size_t)args.total_segs + gid] = gb;
+        const uint32_t c = d0.row - g.chan.div(d0.row) * g.chan.d;
+        a_raw = __ldg(args.alpha + c);
+        b_raw = (g.flags & 2) ? a_raw : __ldg(args.beta + c);
     }
+    uint32_t phase = 0;
+    int st = 0;
+    for (;;) {
+        const uint32_t nwt = wt + GW;
+        const bool has_next = nwt < g.n_wtiles;
+        float a_nraw = 0.f, b_nraw = 0.f;
+        Prefetch pf{nullptr, nullptr, 0u, 0u, 0u, 0u};
+        if (has_next) {
+            const TileDesc nxt = describe_tile<L>(nwt, lane, g);
+            const uint32_t c = nxt.row - g.chan.div(nxt.row) * g.chan.d;
+            a_nraw = __ldg(args.alpha + c);
+            b_nraw = (g.flags & 2) ? a_nraw : __ldg(args.beta + c);
+            if (ALIGNED) {
+                pf.src0 = px + nxt.ld_lo;
+                pf.src1 = pg + nxt.ld_lo;
+                pf.dst0 = smem_u32(stages + (size_t)(st ^ 1) * 2 * WT::kStageElems);
+                pf.dst1 = pf.dst0 + (uint32_t)WT::kStageBytes;
+                pf.bar = smem_u32(&bars[st ^ 1]);
+                pf.bytes = (uint32_t)((nxt.ld_hi - nxt.ld_lo) * (int64_t)sizeof(T));
+            }
+        }
+        const TileDesc cur = describe_tile<L>(wt, lane, g);
+        T* tile_x = stages + (size_t)st * 2 * WT::kStageElems;
+        T* tile_g = tile_x + WT::kStageElems;
+        float a_eff, b_eff, ib;
+        effective_params(a_raw, b_raw, g.flags, a_eff, b_eff, ib);
+        T* row0 = tile_x + (cur.row_base - cur.ld_lo);
+        const T* grow0 = tile_g + (cur.row_base - cur.ld_lo);
+        float ga = 0.f, gb = 0.f;
+        const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
+
+        if (ALIGNED) {
+            mbar_wait(&bars[st], (phase >> st) & 1u);
+            phase ^= (1u << st);
+            const bool fast = cur.active && cur.t0 >= 5 && (cur.t0 + L + 5 < g.T);
+            if (__all_sync(0xffffffffu, fast)) {
+                walk_bwd<T, CH, 0>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, 0xffffffffu, ga, gb);
+            } else if (cur.active) {
+                walk_bwd<T, CH, 1>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask, ga, gb);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_1d(po + cur.flat_lo, tile_x + (cur.flat_lo - cur.ld_lo),
+                             (uint32_t)((cur.flat_hi - cur.flat_lo) * (int64_t)sizeof(T)));
+                tma_store_commit();
+            }
+        } else {
+            const int n_in = (int)(cur.ld_hi - cur.ld_lo);
+            for (int i = lane; i < n_in; i += 32) {
+                tile_x[i] = px[cur.ld_lo + i];
+                tile_g[i] = pg[cur.ld_lo + i];
+            }
+            __syncwarp();
+            if (cur.active) walk_bwd<T, CH, 2>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask, ga, gb);
+            __syncwarp();
+            const int n_out = (int)(cur.flat_hi - cur.flat_lo);
+            const T* src = tile_x + (cur.flat_lo - cur.ld_lo);
+            for (int i = lane; i < n_out; i += 32) po[cur.flat_lo + i] = src[i];
+            __syncwarp();
+        }
+        if (cur.active) {
+            // gradients w.r.t. the RAW parameters: d exp(p)/dp = exp(p)        activations.py:121-123
+            if (g.flags & 1) {
+                ga *= a_eff;
+                gb *= b_eff;
+            }
+            args.part[cur.gid] = ga;
+            args.part[(size_t)g.total_segs + cur.gid] = gb;
+        }
+        if (!has_next) break;
+        wt = nwt;
+        a_raw = a_nraw;
+        b_raw = b_nraw;
+        st ^= 1;
+    }
+    if (ALIGNED && lane == 0) tma_store_wait_read();
 }
 
 // Second stage of the deterministic parameter-gradient reduction: one CTA per channel sums the
