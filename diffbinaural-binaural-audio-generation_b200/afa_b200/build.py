@@ -32,9 +32,10 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libafa_sm100.so (there is no CPU fallback)")
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/ -> afa_b200/libafa_sm100.so.  Rebuilds only when a source is newer."""
-    out = library_path()
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """Compile csrc/ -> afa_b200/libafa_sm100.so.  Rebuilds only when a source is newer.
+    `out` / `defines` build an experimental variant elsewhere (tuning sweeps)."""
+    out = out or library_path()
     if not force and os.path.exists(out):
         t = os.path.getmtime(out)
         if all(os.path.getmtime(d) <= t for d in _deps()):
@@ -47,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         "-I", _INCLUDE, "-I", _CSRC,
         "--shared", "-Xcompiler", "-fPIC",
         "-o", out,
-    ] + _sources()
+    ] + [f"-D{d}" for d in defines] + _sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

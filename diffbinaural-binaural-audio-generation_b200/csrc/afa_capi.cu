@@ -128,20 +128,21 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     return 0;
 }
 
-void fold_fwd_taps(const float* up, const float* dn, afa::FwdTaps* t) {
+void fold_pair_taps(const float* up, const float* dn, afa::PairTaps* t) {
     for (int j = 0; j < 6; ++j) {
-        t->ue[j] = 2.0f * up[2 * j + 1];   // ratio * conv_transpose taps            resample.py:33
-        t->uo[j] = 2.0f * up[2 * j];
+        t->cu[j] = make_float2(2.0f * up[2 * j], 2.0f * up[2 * j + 1]);   // ratio * conv_transpose taps   resample.py:33
+        t->cd[j] = make_float2(dn[2 * j], dn[2 * j + 1]);
     }
-    for (int k = 0; k < 12; ++k) t->dn[k] = dn[k];
 }
-void fold_bwd_taps(const float* up, const float* dn, afa::BwdTaps* t) {
+void fold_fwd_taps(const float* up, const float* dn, afa::FwdTaps* t) {
+    fold_pair_taps(up, dn, &t->p);
     for (int j = 0; j < 6; ++j) {
         t->ue[j] = 2.0f * up[2 * j + 1];
         t->uo[j] = 2.0f * up[2 * j];
-        t->de[j] = dn[2 * j + 1];
-        t->dod[j] = dn[2 * j];
     }
+}
+void fold_bwd_taps(const float* up, const float* dn, afa::BwdTaps* t) {
+    fold_pair_taps(up, dn, &t->p);
     // adjoint of the replicate pad of the activated signal (filter.py:98): taps that fall on the pad
     t->lo[0] = dn[0] + dn[1] + dn[2] + dn[3] + dn[4];
     t->lo[1] = dn[0] + dn[1] + dn[2];

@@ -35,15 +35,36 @@ namespace afa {
 
 constexpr int kHalo = 8;  // elements staged either side of a warp tile's flat range (>= 5 needed)
 
-// Filter taps as kernel parameters (constant bank -> FFMA constant operands).
+// Resident CTAs per SM the aligned kernels are compiled for (register cap = 65536 / (128 * n)).
+#ifndef AFA_FWD_MINB_F32
+#define AFA_FWD_MINB_F32 5
+#endif
+#ifndef AFA_FWD_MINB_BF16
+#define AFA_FWD_MINB_BF16 4
+#endif
+#ifndef AFA_BWD_MINB
+#define AFA_BWD_MINB 4
+#endif
+
+// Filter taps as kernel parameters, pre-paired for packed f32x2 math (they become uniform-register
+// operands of FFMA2).  The 2x-rate signal is handled as pairs (s[2m-1], s[2m]): both members read the
+// same six inputs x[m-3..m+2] and feed the same six outputs y[m-3..m+2], so every tap is ONE FFMA2 whose
+// other operand is a scalar broadcast -- no register-pair alignment constraints anywhere.
+//   cu[j] = (2*f_up[2j], 2*f_up[2j+1]) : (u[2m-1], u[2m])  = sum_j cu[j] * x[m+2-j]
+//   cd[j] = (  f_dn[2j],   f_dn[2j+1]) : (yo, ye)[m+2-j]  += cd[j] * (s[2m-1], s[2m]),  y = yo + ye
+// The backward reuses both: (ds[2m-1], ds[2m]) = sum_j cd[j] * gy[m+2-j] and
+// (dxo, dxe)[m+2-j] += cu[j] * (du[2m-1], du[2m]).
+struct PairTaps {
+    float2 cu[6];
+    float2 cd[6];
+};
 struct FwdTaps {
-    float ue[6];   // ue[j] = 2*f_up[2j+1] : u[2m]   = sum_j ue[j] * x[m+2-j]
-    float uo[6];   // uo[j] = 2*f_up[2j]   : u[2m+1] = sum_j uo[j] * x[m+3-j]
-    float dn[12];  // f_dn[k]              : y[t]    = sum_k dn[k] * s[2t+k-5]
+    PairTaps p;
+    float ue[6];          // 2*f_up[2j+1]  (scalar copies for the edge constants s[0], s[2T-1])
+    float uo[6];          // 2*f_up[2j]
 };
 struct BwdTaps {
-    float ue[6], uo[6];   // as above: recompute u, and scatter du -> dx (same 2*f_up taps)
-    float de[6], dod[6];  // de[j] = f_dn[2j+1], dod[j] = f_dn[2j] : ds[2m], ds[2m+1] from gy
+    PairTaps p;
     float lo[3];          // folded taps of the left  replicate pad of s: gy[0], gy[1], gy[2]
     float hi[3];          // folded taps of the right replicate pad of s: gy[T-1], gy[T-2], gy[T-3]
 };
@@ -226,12 +247,16 @@ struct RingCfg {
     static constexpr int S = (VEC == 4) ? 12 : 16;  // ring size = steps per loop body (>= 6 + VEC, multiple of VEC)
 };
 
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
 // ------------------------------------------------------------------------------------------------
 // forward walk of one segment, in place.  MODE 0: interior (branch-free); 1: touches a row end
 // (16B-aligned rows); 2: rows not 16B-aligned (scalar smem I/O).  `row0` points at this row's sample 0
 // inside the staged tile (may lie outside the tile; only in-range positions are touched).
-// Step q handles the 2x-rate pair m = t0 - 3 + q and completes y[t0 + q - 6].
-// X ring: x[t0 - 8 + j] lives in xr[j % S];  accumulator ring: y[t0 + o] lives in ac[o % S].
+// Step q (1 <= q <= L+5) handles the 2x-rate pair (s[2m-1], s[2m]), m = t0 - 3 + q, and completes
+// y[t0 + q - 6].  X ring: x[t0 - 8 + j] lives in xr[j % S]; accumulator ring: the two partial sums of
+// y[t0 + o] (odd-phase taps, even-phase taps: two fixed 6-term FMA chains, then one add) live in
+// ac[o % S] -- so results do not depend on how rows are cut into segments.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen, float a, float ib, const FwdTaps& tp,
@@ -242,7 +267,9 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     constexpr int S = RingCfg<VEC>::S;
     constexpr int NFULL = L / S, REM = L % S;
     T* seg = row0 + t0;
-    float xr[S], ac[S], hold[8];
+    float xr[S];
+    float2 ac[S];
+    float hold[8], yb[VEC];
     float s_first = 0.f, s_last = 0.f, x_last = 0.f;
 
     // ---- preload x[t0-8 .. t0-1] and the edge constants; nothing below reads a neighbour's first 8
@@ -279,81 +306,73 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     }
     __syncwarp(mask);
 
-    // one step; Q is the static part of the step index (ring positions), q the dynamic step number
+    // one step; Q is the static part of the step index (ring slots), q the dynamic step number
     auto step = [&](const int Q, const int q, const bool first_iter) {
-        // --- bring in x[t0+q .. ] = X[q+8 ..]
+        // --- bring in X[q+7 ..] = x[t0 + q - 1 ..]
         if (MODE != 2) {
-            if ((Q + 8) % VEC == 0) {
-                float* dst = &xr[(Q + 8) % S];
-                io::load_chunk(seg + q, dst);
+            if ((Q + 7) % VEC == 0) {
+                float* dst = &xr[(Q + 7) % S];
+                io::load_chunk(seg + q - 1, dst);
                 if (MODE == 1) {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) dst[e] = (t0 + q + e > Tlen - 1) ? x_last : dst[e];
+                    for (int e = 0; e < VEC; ++e) dst[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : dst[e];
                 }
             }
         } else {
-            xr[(Q + 8) % S] = io::load1(row0 + min(t0 + q, Tlen - 1));
+            xr[(Q + 7) % S] = io::load1(row0 + min(t0 + q - 1, Tlen - 1));
         }
-        // --- polyphase upsample: u[2m] from x[m-3..m+2], u[2m+1] from x[m-2..m+3]     resample.py:32-36
-        float ue = tp.ue[0] * xr[(Q + 7) % S];
-        float uo = tp.uo[0] * xr[(Q + 8) % S];
+        // --- polyphase upsample: (u[2m-1], u[2m]) from x[m-3 .. m+2]                  resample.py:32-36
+        float2 u2 = __fmul2_rn(tp.p.cu[0], bcast2(xr[(Q + 7) % S]));
 #pragma unroll
-        for (int j = 1; j < 6; ++j) {
-            ue = fmaf(tp.ue[j], xr[(Q + 7 - j + S) % S], ue);
-            uo = fmaf(tp.uo[j], xr[(Q + 8 - j + S) % S], uo);
-        }
-        float se = snake_f(ue, a, ib);
-        float so = snake_f(uo, a, ib);
+        for (int j = 1; j < 6; ++j) u2 = __ffma2_rn(tp.p.cu[j], bcast2(xr[(Q + 7 - j + S) % S]), u2);
+        // --- Snake / SnakeBeta on the pair                                          activations.py:124
+        const float2 th = __fmul2_rn(u2, bcast2(a));
+        const float2 sn = make_float2(__sinf(th.x), __sinf(th.y));
+        float2 s2 = __ffma2_rn(bcast2(ib), __fmul2_rn(sn, sn), u2);
         if (MODE != 0) {
             const int m = t0 - 3 + q;
-            if (Q < 3 && first_iter) {
-                if (m < 0) { se = s_first; so = s_first; }
+            if (Q <= 3 && first_iter) {   // s[n] for n < 0 repeats s[0]
+                if (m <= 0) s2.x = s_first;
+                if (m < 0) s2.y = s_first;
             }
-            if (m >= Tlen) { se = s_last; so = s_last; }
+            if (m > Tlen) s2.x = s_last;   // s[n] for n >= 2T repeats s[2T-1]
+            if (m >= Tlen) s2.y = s_last;
         }
-        // --- scatter into the live accumulators: s[2m+1] -> y[m+3-j] (tap 2j), s[2m] -> y[m+2-j] (tap 2j+1)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            if (!(first_iter && Q - j < 0)) {
-                float& acc = ac[(Q - j + 2 * S) % S];
-                acc = (j == 0) ? tp.dn[0] * so : fmaf(tp.dn[2 * j], so, acc);
-            }
-        }
+        // --- scatter: (yo, ye)[m+2-j] += cd[j] * (s[2m-1], s[2m])                       filter.py:98-99
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             if (!(first_iter && Q - 1 - j < 0)) {
-                float& acc = ac[(Q - 1 - j + 2 * S) % S];
-                acc = fmaf(tp.dn[2 * j + 1], se, acc);
+                float2& acc = ac[(Q - 1 - j + 2 * S) % S];
+                acc = (j == 0) ? __fmul2_rn(tp.p.cd[0], s2) : __ffma2_rn(tp.p.cd[j], s2, acc);
             }
         }
         // --- y[t0 + q - 6] is complete
-        if (MODE != 2) {
-            if ((Q - 6 + 2 * S) % VEC == VEC - 1 && !(first_iter && Q < 6)) {
-                const int c0 = q - 6 - (VEC - 1);                     // first sample of the finished chunk
-                float v[VEC];
+        if (!(first_iter && Q < 6)) {
+            const int o = q - 6;
+            const float2 done = ac[(Q - 6 + 2 * S) % S];
+            const float yv = done.x + done.y;
+            if (MODE != 2) {
+                yb[(Q - 6 + 2 * S) % VEC] = yv;
+                if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
+                    const int c0 = o - (VEC - 1);                     // first sample of the finished chunk
+                    if (c0 < 8) {                                      // a neighbour may still need these x
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) v[e] = ac[(Q - 6 - (VEC - 1) + e + 2 * S) % S];
-                if (c0 < 8) {                                          // a neighbour may still need these x
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = v[e];
-                } else if (MODE == 0 || t0 + c0 < Tlen) {
-                    io::store_chunk(seg + c0, v);
+                        for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = yb[e];
+                    } else if (MODE == 0 || t0 + c0 < Tlen) {
+                        io::store_chunk(seg + c0, yb);
+                    }
                 }
-            }
-        } else {
-            if (!(first_iter && Q < 6)) {
-                const int o = q - 6;
-                const float v = ac[(Q - 6 + 2 * S) % S];
-                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = v;
-                else if (t0 + o < Tlen) io::store1(seg + o, v);
+            } else {
+                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = yv;
+                else if (t0 + o < Tlen) io::store1(seg + o, yv);
             }
         }
     };
 
-    // prologue: q = 0..5 (static; dead work is eliminated)
+    // prologue: q = 1..5 (static; dead work is eliminated)
 #pragma unroll
-    for (int q = 0; q < 6; ++q) step(q, q, true);
-    // main loop: q = 6 .. L+5, S steps per trip, ring positions static inside the body
+    for (int q = 1; q < 6; ++q) step(q, q, true);
+    // main loop: q = 6 .. L+5, S steps per trip, ring slots static inside the body
 #pragma unroll 1
     for (int it = 0; it < NFULL + (REM ? 1 : 0); ++it) {
         const int qb = 6 + it * S;
@@ -381,7 +400,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
 // ------------------------------------------------------------------------------------------------
 // backward walk of one segment: recomputes u from x, forms ds from gy, du = ds*(1 + a*ib*sin(2 a u)),
 // scatters du into dx (written in place over x), and accumulates the segment's share of
-// d/dalpha_eff, d/dbeta_eff.
+// d/dalpha_eff, d/dbeta_eff.  Same packed-pair arithmetic and step numbering as the forward.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restrict__ grow0, int t0, int Tlen, float a,
@@ -392,9 +411,14 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
     constexpr int NFULL = L / S, REM = L % S;
+    // the last step whose pair still holds an s-value of this segment is q = L+3 (its odd member);
+    // in loop coordinates q = 6 + it*S + k:
+    constexpr int IT_LAST = (L - 3) / S, K_LAST = (L - 3) % S;
     T* seg = row0 + t0;
     const T* gseg = grow0 + t0;
-    float xr[S], gr[S], ac[S], hold[8];
+    float xr[S], gr[S];
+    float2 ac[S];
+    float hold[8], yb[VEC];
     float d_lo = 0.f, d_hi = 0.f, x_last = 0.f;
 
     if (MODE != 2) {
@@ -413,12 +437,12 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     }
     if (MODE != 0) {
 #pragma unroll
-        for (int i = 0; i < S; ++i) ac[i] = 0.f;   // accumulators left of the row start only ever see FMAs
+        for (int i = 0; i < S; ++i) ac[i] = make_float2(0.f, 0.f);   // accumulators left of the row start only see FMAs
         if (t0 == 0) {
             if (MODE == 1) {
                 const float x0 = io::load1(row0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { xr[j] = x0; gr[j] = 0.f; }   // replicate x, gy does not extend
+                for (int j = 0; j < 8; ++j) { xr[j] = x0; gr[j] = 0.f; }   // replicate x; gy does not extend
             }
             // adjoint of the left replicate pad of s: taps that fell on the pad fold onto s[0]
             const float g0 = io::load1(grow0);
@@ -440,132 +464,132 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
 
     const float a2 = 2.0f * a;
     const float iba = ib * a;
-    float ga = 0.f, gb = 0.f;
+    float2 ga2 = make_float2(0.f, 0.f), gb2 = make_float2(0.f, 0.f);
 
-    auto step = [&](const int Q, const int q, const bool first_iter) {
+    auto step = [&](const int Q, const int q, const bool first_iter, const bool tail) {
         if (MODE != 2) {
-            if ((Q + 8) % VEC == 0) {
-                float* dx = &xr[(Q + 8) % S];
-                float* dg = &gr[(Q + 8) % S];
-                io::load_chunk(seg + q, dx);
-                io::load_chunk(gseg + q, dg);
+            if ((Q + 7) % VEC == 0) {
+                float* dx = &xr[(Q + 7) % S];
+                float* dg = &gr[(Q + 7) % S];
+                io::load_chunk(seg + q - 1, dx);
+                io::load_chunk(gseg + q - 1, dg);
                 if (MODE == 1) {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
-                        const bool past = t0 + q + e > Tlen - 1;
+                        const bool past = t0 + q - 1 + e > Tlen - 1;
                         dx[e] = past ? x_last : dx[e];
                         dg[e] = past ? 0.f : dg[e];
                     }
                 }
             }
         } else {
-            const int t = t0 + q;
-            xr[(Q + 8) % S] = io::load1(row0 + min(t, Tlen - 1));
+            const int t = t0 + q - 1;
+            xr[(Q + 7) % S] = io::load1(row0 + min(t, Tlen - 1));
             const float g = io::load1(grow0 + min(t, Tlen - 1));
-            gr[(Q + 8) % S] = (t < Tlen) ? g : 0.f;
+            gr[(Q + 7) % S] = (t < Tlen) ? g : 0.f;
         }
-        float ue = tp.ue[0] * xr[(Q + 7) % S];
-        float uo = tp.uo[0] * xr[(Q + 8) % S];
-        float de = tp.de[0] * gr[(Q + 7) % S];
-        float dd = tp.dod[0] * gr[(Q + 8) % S];
+        float2 u2 = __fmul2_rn(tp.p.cu[0], bcast2(xr[(Q + 7) % S]));
+        float2 d2 = __fmul2_rn(tp.p.cd[0], bcast2(gr[(Q + 7) % S]));
 #pragma unroll
         for (int j = 1; j < 6; ++j) {
-            ue = fmaf(tp.ue[j], xr[(Q + 7 - j + S) % S], ue);
-            uo = fmaf(tp.uo[j], xr[(Q + 8 - j + S) % S], uo);
-            de = fmaf(tp.de[j], gr[(Q + 7 - j + S) % S], de);
-            dd = fmaf(tp.dod[j], gr[(Q + 8 - j + S) % S], dd);
+            u2 = __ffma2_rn(tp.p.cu[j], bcast2(xr[(Q + 7 - j + S) % S]), u2);
+            d2 = __ffma2_rn(tp.p.cd[j], bcast2(gr[(Q + 7 - j + S) % S]), d2);
         }
         const int m = t0 - 3 + q;
         if (MODE != 0) {
-            if (Q < 3 && first_iter) {
-                if (m < 0) { de = 0.f; dd = 0.f; }
+            // ds does not exist outside [0, 2T): what fell on the replicate pads was folded into d_lo / d_hi
+            if (Q <= 3 && first_iter) {
+                if (m <= 0) d2.x = 0.f;
+                if (m < 0) d2.y = 0.f;
             }
-            if (m >= Tlen) { de = 0.f; dd = 0.f; }
+            if (m > Tlen) d2.x = 0.f;
+            if (m >= Tlen) d2.y = 0.f;
             if (Q == 3 && first_iter) {
-                if (t0 == 0) de += d_lo;
+                if (t0 == 0) d2.y += d_lo;      // ds[0]
             }
-            if (m == Tlen - 1) dd += d_hi;
+            if (m == Tlen) d2.x += d_hi;         // ds[2T-1]
         }
-        // s[2m], s[2m+1] belong to this segment for q in [3, L+3)
-        const bool own = first_iter ? (Q >= 3) : (q < L + 3);
-        float due, duo;
-        {
-            const float ph = a2 * ue;
-            const float sn = __sinf(ph), cs = __cosf(ph);
-            const float p = de * sn;
-            due = fmaf(p, iba, de);
-            if (own) {
-                ga = fmaf(p, ue, ga);
-                gb += fmaf(-de, cs, de);
+        const float2 ph = __fmul2_rn(bcast2(a2), u2);
+        const float2 sn = make_float2(__sinf(ph.x), __sinf(ph.y));
+        const float2 cs = make_float2(__cosf(ph.x), __cosf(ph.y));
+        const float2 p2 = __fmul2_rn(d2, sn);
+        const float2 du2 = __ffma2_rn(p2, bcast2(iba), d2);
+        // parameter-gradient partials: s[2m-1] belongs to this segment for q in [4, L+3], s[2m] for q in [3, L+2]
+        if (first_iter) {
+            if (Q == 3) {
+                ga2.y = fmaf(p2.y, u2.y, ga2.y);
+                gb2.y += fmaf(-d2.y, cs.y, d2.y);
+            } else if (Q > 3) {
+                ga2 = __ffma2_rn(p2, u2, ga2);
+                gb2 = __fadd2_rn(gb2, __ffma2_rn(make_float2(-d2.x, -d2.y), cs, d2));
             }
-        }
-        {
-            const float ph = a2 * uo;
-            const float sn = __sinf(ph), cs = __cosf(ph);
-            const float p = dd * sn;
-            duo = fmaf(p, iba, dd);
-            if (own) {
-                ga = fmaf(p, uo, ga);
-                gb += fmaf(-dd, cs, dd);
-            }
+        } else if (!tail) {
+            ga2 = __ffma2_rn(p2, u2, ga2);
+            gb2 = __fadd2_rn(gb2, __ffma2_rn(make_float2(-d2.x, -d2.y), cs, d2));
+        } else if (Q == 6 + K_LAST) {
+            ga2.x = fmaf(p2.x, u2.x, ga2.x);
+            gb2.x += fmaf(-d2.x, cs.x, d2.x);
         }
         constexpr int LOW = (MODE == 0) ? 0 : -3;   // edge modes also keep dx_ext[-3..-1] (folded below)
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            if (!(first_iter && Q - j < LOW)) {
-                float& acc = ac[(Q - j + 2 * S) % S];
-                acc = (j == 0) ? tp.uo[0] * duo : fmaf(tp.uo[j], duo, acc);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
             if (!(first_iter && Q - 1 - j < LOW)) {
-                float& acc = ac[(Q - 1 - j + 2 * S) % S];
-                acc = fmaf(tp.ue[j], due, acc);
+                float2& acc = ac[(Q - 1 - j + 2 * S) % S];
+                acc = (j == 0) ? __fmul2_rn(tp.p.cu[0], du2) : __ffma2_rn(tp.p.cu[j], du2, acc);
             }
         }
         if (!(first_iter && Q < 6)) {
             const int o = q - 6;
-            float& done = ac[(Q - 6 + 2 * S) % S];
+            const float2 done = ac[(Q - 6 + 2 * S) % S];
+            float yv = done.x + done.y;
             if (MODE != 0) {
                 // adjoint of the x replicate pad: fold dx_ext beyond the row onto its first / last sample
                 if (Q == 6 && o == 0) {
-                    if (t0 == 0) done += ac[(2 * S - 3) % S] + ac[(2 * S - 2) % S] + ac[(2 * S - 1) % S];
+                    if (t0 == 0) {
+                        const float2 e1 = ac[(2 * S - 1) % S], e2 = ac[(2 * S - 2) % S], e3 = ac[(2 * S - 3) % S];
+                        yv += (e3.x + e3.y) + (e2.x + e2.y) + (e1.x + e1.y);
+                    }
                 }
-                if (t0 + o == Tlen - 1)
-                    done += ac[(Q - 5 + 2 * S) % S] + ac[(Q - 4 + 2 * S) % S] + ac[(Q - 3 + 2 * S) % S];
+                if (t0 + o == Tlen - 1) {
+                    const float2 e1 = ac[(Q - 5 + 2 * S) % S], e2 = ac[(Q - 4 + 2 * S) % S], e3 = ac[(Q - 3 + 2 * S) % S];
+                    yv += (e1.x + e1.y) + (e2.x + e2.y) + (e3.x + e3.y);
+                }
             }
             if (MODE != 2) {
+                yb[(Q - 6 + 2 * S) % VEC] = yv;
                 if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
                     const int c0 = o - (VEC - 1);
-                    float v[VEC];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) v[e] = ac[(Q - 6 - (VEC - 1) + e + 2 * S) % S];
                     if (c0 < 8) {
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = v[e];
+                        for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = yb[e];
                     } else if (MODE == 0 || t0 + c0 < Tlen) {
-                        io::store_chunk(seg + c0, v);
+                        io::store_chunk(seg + c0, yb);
                     }
                 }
             } else {
-                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = done;
-                else if (t0 + o < Tlen) io::store1(seg + o, done);
+                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = yv;
+                else if (t0 + o < Tlen) io::store1(seg + o, yv);
             }
         }
     };
 
 #pragma unroll
-    for (int q = 0; q < 6; ++q) step(q, q, true);
+    for (int q = 1; q < 6; ++q) step(q, q, true, false);
 #pragma unroll 1
     for (int it = 0; it < NFULL + (REM ? 1 : 0); ++it) {
         const int qb = 6 + it * S;
+        if (it < IT_LAST) {
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
-            if (REM != 0 && k == REM) {
-                if (it == NFULL) break;
+            for (int k = 0; k < S; ++k) step(6 + k, qb + k, false, false);
+        } else {
+            // final trip(s): the parameter-gradient partials stop after q = L+3
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                if (REM != 0 && k == REM) {
+                    if (it == NFULL) break;
+                }
+                step(6 + k, qb + k, false, (it > IT_LAST) || (k >= K_LAST));
             }
-            step(6 + k, qb + k, false);
         }
         if (it == 0 && lane == 0) issue_prefetch(pf);
     }
@@ -579,8 +603,8 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
         for (int o = 0; o < 8; ++o)
             if (t0 + o < Tlen) io::store1(seg + o, hold[o]);
     }
-    ga_out = ga * ib;               // sum ds * ib * u * sin(2 a u)
-    gb_out = -0.5f * ib * ib * gb;  // -sum ds * sin^2(a u) * ib^2,  sin^2 = (1 - cos 2au)/2
+    ga_out = (ga2.x + ga2.y) * ib;               // sum ds * ib * u * sin(2 a u)
+    gb_out = -0.5f * ib * ib * (gb2.x + gb2.y);  // -sum ds * sin^2(a u) * ib^2,  sin^2 = (1 - cos 2au)/2
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,7 +654,7 @@ struct WarpTile {
 // forward kernel: persistent, one autonomous pipeline per warp
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int NW, bool ALIGNED>
-__global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? 6 : 5) : 1) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
+__global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_MINB_F32 : AFA_FWD_MINB_BF16) : 1) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
     using WT = WarpTile<T, CH>;
     constexpr int L = WT::L;
     static_assert(NW * 2 * sizeof(uint64_t) <= 128, "barrier block");
@@ -732,7 +756,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? 6 : 5) : 
 // backward kernel: same frame, two staged tensors (x, gy), gx written in place over x
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int NW, bool ALIGNED>
-__global__ void __launch_bounds__(NW * 32, ALIGNED ? 4 : 1) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
+__global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
     using WT = WarpTile<T, CH>;
     constexpr int L = WT::L;
     static_assert(NW * 2 * sizeof(uint64_t) <= 128, "barrier block");
