@@ -273,6 +273,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
     _lib.load_library()
+    if args.chunks:
+        _lib.set_tuning(0, args.chunks, 0)
     dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     esize = 4 if args.dtype == "fp32" else 2
 
@@ -490,6 +492,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-repeats", type=int, default=3)
+    ap.add_argument("--chunks", type=int, default=0, help="tuning: 16-byte chunks per thread segment for the forward (0 = library default)")
     ap.add_argument("--table", action="store_true")
     ap.add_argument("--torch-baseline", action="store_true", help="with --table: also time the torch-op path on the GPU")
     args = ap.parse_args()

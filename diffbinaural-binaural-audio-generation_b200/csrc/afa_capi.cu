@@ -11,7 +11,7 @@
 #include "afa_kernels.cuh"
 
 #ifndef AFA_CHUNK_LIST
-#define AFA_CHUNK_LIST(X) X(5) X(9)
+#define AFA_CHUNK_LIST(X) X(5) X(9) X(13)
 #endif
 
 namespace {
@@ -98,10 +98,13 @@ int grid_for(const void* kernel, size_t smem, uint32_t n_wtiles, uint32_t* grid)
 }
 
 
-int default_chunks(int which, int dtype) {
-    (void)which;
-    (void)dtype;
-    return 9;
+// Segment length heuristic (measured, profiles/): long segments amortise the 5 warm-up steps and the
+// per-tile bookkeeping, but need enough warp tiles to keep every resident warp busy for >= 2 tiles.
+int default_chunks(int which, int dtype, int64_t elements) {
+    if (which == 1) return 9;
+    const int vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
+    const int64_t wtiles13 = elements / (32 * 13 * vec);
+    return wtiles13 >= 2 * 148 * 16 ? 13 : 9;
 }
 
 int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t batch, int64_t channels, int64_t T,
@@ -111,7 +114,7 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     if (T >= (1ll << 30)) return fail(AFA_ERR_TOO_LARGE, "T=%lld exceeds 2^30", (long long)T);
     pl->dtype = dtype;
     pl->vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
-    int ch = g_tune_chunks[which] ? g_tune_chunks[which] : default_chunks(which, dtype);
+    int ch = g_tune_chunks[which] ? g_tune_chunks[which] : default_chunks(which, dtype, batch * channels * T);
     pl->chunks = ch;
     pl->L = ch * pl->vec;
     const int64_t rows = batch * channels;

@@ -34,6 +34,7 @@
 namespace afa {
 
 constexpr int kHalo = 8;  // elements staged either side of a warp tile's flat range (>= 5 needed)
+constexpr int kBarBytes = 64;  // mbarrier block at the start of dynamic shared memory (2 per warp)
 
 // Resident CTAs per SM the aligned kernels are compiled for (register cap = 65536 / (128 * n)).
 #ifndef AFA_FWD_MINB_F32
@@ -216,13 +217,23 @@ __device__ __forceinline__ void effective_params(float a_raw, float b_raw, int f
 }
 
 // What a walk needs to know to prefetch the warp's NEXT tile once its previous bulk store has
-// drained (issued by lane 0 after the first loop iteration of the walk).
+// drained (issued by lane 0 after the first S loop steps of the walk), and to prepare that tile's
+// channel parameters (all lanes, same place: the global-load and exp/rcp latencies hide under the walk).
 struct Prefetch {
     const void* src0;
     const void* src1;    // second tensor (backward: gy), or nullptr
     uint32_t dst0, dst1; // shared-memory addresses of the stage being refilled
     uint32_t bar;        // shared-memory address of that stage's mbarrier
     uint32_t bytes;      // per tensor; 0 = nothing to prefetch
+};
+struct ChanParams {
+    float a_eff, b_eff, ib;
+};
+struct NextChan {
+    const float* alpha;
+    const float* beta;
+    int32_t c;           // channel of this lane's segment in the next tile, or -1
+    int32_t flags;
 };
 __device__ __forceinline__ void issue_prefetch(const Prefetch& pf) {
     if (pf.bytes) {
@@ -240,6 +251,18 @@ __device__ __forceinline__ void issue_prefetch(const Prefetch& pf) {
                 "l"(pf.src1), "r"(pf.bytes), "r"(pf.bar)
                 : "memory");
     }
+}
+__device__ __forceinline__ ChanParams load_chan_params(const float* alpha, const float* beta, int c, int flags) {
+    ChanParams p;
+    const float a_raw = __ldg(alpha + c);
+    const float b_raw = (flags & 2) ? a_raw : __ldg(beta + c);
+    effective_params(a_raw, b_raw, flags, p.a_eff, p.b_eff, p.ib);
+    return p;
+}
+// the mid-walk hook: lane 0 refills the other stage, every lane prepares its next channel parameters
+__device__ __forceinline__ void mid_walk_hook(const Prefetch& pf, const NextChan& nc, ChanParams& next, int lane) {
+    if (lane == 0) issue_prefetch(pf);
+    if (nc.c >= 0) next = load_chan_params(nc.alpha, nc.beta, nc.c, nc.flags);
 }
 
 template <int VEC>
@@ -260,7 +283,8 @@ __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen, float a, float ib, const FwdTaps& tp,
-                                         const Prefetch& pf, int lane, uint32_t mask) {
+                                         const Prefetch& pf, const NextChan& nc, ChanParams& next, int lane,
+                                         uint32_t mask) {
     using io = IO<T>;
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
@@ -355,26 +379,28 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
                 yb[(Q - 6 + 2 * S) % VEC] = yv;
                 if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
                     const int c0 = o - (VEC - 1);                     // first sample of the finished chunk
-                    if (c0 < 8) {                                      // a neighbour may still need these x
+                    if (first_iter && Q - 6 - (VEC - 1) < 8) {         // (static) a neighbour may still need these x
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = yb[e];
+                        for (int e = 0; e < VEC; ++e) hold[Q - 6 - (VEC - 1) + e] = yb[e];
                     } else if (MODE == 0 || t0 + c0 < Tlen) {
                         io::store_chunk(seg + c0, yb);
                     }
                 }
             } else {
-                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = yv;
+                if (first_iter && Q - 6 < 8) hold[Q - 6] = yv;
                 else if (t0 + o < Tlen) io::store1(seg + o, yv);
             }
         }
     };
 
-    // prologue: q = 1..5 (static; dead work is eliminated)
+    static_assert(L >= S, "segment shorter than the ring");
+    // the first 5 + S steps are fully static (q = 1 .. S+5): warm-up, and the outputs that must wait in hold[]
 #pragma unroll
-    for (int q = 1; q < 6; ++q) step(q, q, true);
-    // main loop: q = 6 .. L+5, S steps per trip, ring slots static inside the body
+    for (int q = 1; q < 6 + S; ++q) step(q, q, true);
+    mid_walk_hook(pf, nc, next, lane);
+    // main loop: q = S+6 .. L+5, S steps per trip, ring slots static inside the body
 #pragma unroll 1
-    for (int it = 0; it < NFULL + (REM ? 1 : 0); ++it) {
+    for (int it = 1; it < NFULL + (REM ? 1 : 0); ++it) {
         const int qb = 6 + it * S;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
@@ -383,7 +409,6 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             }
             step(6 + k, qb + k, false);
         }
-        if (it == 0 && lane == 0) issue_prefetch(pf);
     }
     __syncwarp(mask);  // every lane has finished reading its right halo: now the first 8 outputs may land
     if (MODE != 2) {
@@ -404,8 +429,8 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restrict__ grow0, int t0, int Tlen, float a,
-                                         float ib, const BwdTaps& tp, const Prefetch& pf, int lane, uint32_t mask,
-                                         float& ga_out, float& gb_out) {
+                                         float ib, const BwdTaps& tp, const Prefetch& pf, const NextChan& nc,
+                                         ChanParams& next, int lane, uint32_t mask, float& ga_out, float& gb_out) {
     using io = IO<T>;
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
@@ -559,24 +584,26 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                 yb[(Q - 6 + 2 * S) % VEC] = yv;
                 if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
                     const int c0 = o - (VEC - 1);
-                    if (c0 < 8) {
+                    if (first_iter && Q - 6 - (VEC - 1) < 8) {
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) hold[(Q - 6 - (VEC - 1) + e + 2 * S) % 8] = yb[e];
+                        for (int e = 0; e < VEC; ++e) hold[Q - 6 - (VEC - 1) + e] = yb[e];
                     } else if (MODE == 0 || t0 + c0 < Tlen) {
                         io::store_chunk(seg + c0, yb);
                     }
                 }
             } else {
-                if (o < 8) hold[(Q - 6 + 2 * S) % 8] = yv;
+                if (first_iter && Q - 6 < 8) hold[Q - 6] = yv;
                 else if (t0 + o < Tlen) io::store1(seg + o, yv);
             }
         }
     };
 
+    static_assert(L >= S + 3, "segment shorter than the ring");
 #pragma unroll
-    for (int q = 1; q < 6; ++q) step(q, q, true, false);
+    for (int q = 1; q < 6 + S; ++q) step(q, q, true, false);
+    mid_walk_hook(pf, nc, next, lane);
 #pragma unroll 1
-    for (int it = 0; it < NFULL + (REM ? 1 : 0); ++it) {
+    for (int it = 1; it < NFULL + (REM ? 1 : 0); ++it) {
         const int qb = 6 + it * S;
         if (it < IT_LAST) {
 #pragma unroll
@@ -591,7 +618,6 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                 step(6 + k, qb + k, false, (it > IT_LAST) || (k >= K_LAST));
             }
         }
-        if (it == 0 && lane == 0) issue_prefetch(pf);
     }
     __syncwarp(mask);
     if (MODE != 2) {
@@ -646,8 +672,8 @@ struct WarpTile {
     static constexpr int L = CH * VEC;
     static constexpr int kStageElems = 32 * L + 2 * kHalo;               // one tensor, one stage
     static constexpr size_t kStageBytes = sizeof(T) * (size_t)kStageElems;  // multiple of 16
-    static constexpr size_t fwd_smem(int nw) { return 128 + (size_t)nw * 2 * kStageBytes; }
-    static constexpr size_t bwd_smem(int nw) { return 128 + (size_t)nw * 2 * 2 * kStageBytes; }
+    static constexpr size_t fwd_smem(int nw) { return kBarBytes + (size_t)nw * 2 * kStageBytes; }
+    static constexpr size_t bwd_smem(int nw) { return kBarBytes + (size_t)nw * 2 * 2 * kStageBytes; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -657,11 +683,11 @@ template <typename T, int CH, int NW, bool ALIGNED>
 __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_MINB_F32 : AFA_FWD_MINB_BF16) : 1) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
     using WT = WarpTile<T, CH>;
     constexpr int L = WT::L;
-    static_assert(NW * 2 * sizeof(uint64_t) <= 128, "barrier block");
+    static_assert(NW * 2 * sizeof(uint64_t) <= kBarBytes, "barrier block");
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * 2;
-    T* stages = reinterpret_cast<T*>(smem + 128) + (size_t)warp * 2 * WT::kStageElems;
+    T* stages = reinterpret_cast<T*>(smem + kBarBytes) + (size_t)warp * 2 * WT::kStageElems;
     const Geometry& g = args.g;
     const T* gx = static_cast<const T*>(args.x);
     T* gy = static_cast<T*>(args.y);
@@ -678,7 +704,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
         }
         __syncwarp();
     }
-    float a_raw = 0.f, b_raw = 0.f;
+    ChanParams cp;
     {
         const TileDesc d0 = describe_tile<L>(wt, lane, g);
         if (ALIGNED && lane == 0) {
@@ -686,22 +712,19 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
             mbar_expect_tx(&bars[0], bytes);
             tma_load_1d(stages, gx + d0.ld_lo, bytes, &bars[0]);
         }
-        const uint32_t c = d0.row - g.chan.div(d0.row) * g.chan.d;
-        a_raw = __ldg(args.alpha + c);
-        b_raw = (g.flags & 2) ? a_raw : __ldg(args.beta + c);
+        cp = load_chan_params(args.alpha, args.beta, (int)(d0.row - g.chan.div(d0.row) * g.chan.d), g.flags);
     }
     uint32_t phase = 0;  // bit s = parity to wait for on stage s
     int st = 0;
     for (;;) {
         const uint32_t nwt = wt + GW;
         const bool has_next = nwt < g.n_wtiles;
-        float a_nraw = 0.f, b_nraw = 0.f;
         Prefetch pf{nullptr, nullptr, 0u, 0u, 0u, 0u};
+        NextChan nc{args.alpha, args.beta, -1, g.flags};
+        ChanParams cp_next = cp;
         if (has_next) {
             const TileDesc nxt = describe_tile<L>(nwt, lane, g);
-            const uint32_t c = nxt.row - g.chan.div(nxt.row) * g.chan.d;
-            a_nraw = __ldg(args.alpha + c);
-            b_nraw = (g.flags & 2) ? a_nraw : __ldg(args.beta + c);
+            nc.c = (int32_t)(nxt.row - g.chan.div(nxt.row) * g.chan.d);
             if (ALIGNED) {
                 pf.src0 = gx + nxt.ld_lo;
                 pf.dst0 = smem_u32(stages + (size_t)(st ^ 1) * WT::kStageElems);
@@ -711,8 +734,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
         }
         const TileDesc cur = describe_tile<L>(wt, lane, g);
         T* tile = stages + (size_t)st * WT::kStageElems;
-        float a_eff, b_eff, ib;
-        effective_params(a_raw, b_raw, g.flags, a_eff, b_eff, ib);
+        const float a_eff = cp.a_eff, b_eff = cp.b_eff, ib = cp.ib;
         T* row0 = tile + (cur.row_base - cur.ld_lo);
         const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
 
@@ -721,9 +743,9 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
             phase ^= (1u << st);
             const bool fast = cur.active && cur.t0 >= 5 && (cur.t0 + L + 5 < g.T);
             if (__all_sync(0xffffffffu, fast)) {
-                walk_fwd<T, CH, 0>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, 0xffffffffu);
+                walk_fwd<T, CH, 0>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, 0xffffffffu);
             } else if (cur.active) {
-                walk_fwd<T, CH, 1>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask);
+                walk_fwd<T, CH, 1>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -736,7 +758,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
             const int n_in = (int)(cur.ld_hi - cur.ld_lo);
             for (int i = lane; i < n_in; i += 32) tile[i] = gx[cur.ld_lo + i];
             __syncwarp();
-            if (cur.active) walk_fwd<T, CH, 2>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask);
+            if (cur.active) walk_fwd<T, CH, 2>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask);
             __syncwarp();
             const int n_out = (int)(cur.flat_hi - cur.flat_lo);
             const T* src = tile + (cur.flat_lo - cur.ld_lo);
@@ -745,8 +767,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
         }
         if (!has_next) break;
         wt = nwt;
-        a_raw = a_nraw;
-        b_raw = b_nraw;
+        cp = cp_next;
         st ^= 1;
     }
     if (ALIGNED && lane == 0) tma_store_wait_read();  // shared memory must outlive the last bulk store's reads
@@ -759,12 +780,12 @@ template <typename T, int CH, int NW, bool ALIGNED>
 __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
     using WT = WarpTile<T, CH>;
     constexpr int L = WT::L;
-    static_assert(NW * 2 * sizeof(uint64_t) <= 128, "barrier block");
+    static_assert(NW * 2 * sizeof(uint64_t) <= kBarBytes, "barrier block");
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * 2;
     // per warp: [stage 0: x | gy][stage 1: x | gy]
-    T* stages = reinterpret_cast<T*>(smem + 128) + (size_t)warp * 4 * WT::kStageElems;
+    T* stages = reinterpret_cast<T*>(smem + kBarBytes) + (size_t)warp * 4 * WT::kStageElems;
     const Geometry& g = args.g;
     const T* px = static_cast<const T*>(args.x);
     const T* pg = static_cast<const T*>(args.gy);
@@ -782,7 +803,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         }
         __syncwarp();
     }
-    float a_raw = 0.f, b_raw = 0.f;
+    ChanParams cp;
     {
         const TileDesc d0 = describe_tile<L>(wt, lane, g);
         if (ALIGNED && lane == 0) {
@@ -791,22 +812,19 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
             tma_load_1d(stages, px + d0.ld_lo, bytes, &bars[0]);
             tma_load_1d(stages + WT::kStageElems, pg + d0.ld_lo, bytes, &bars[0]);
         }
-        const uint32_t c = d0.row - g.chan.div(d0.row) * g.chan.d;
-        a_raw = __ldg(args.alpha + c);
-        b_raw = (g.flags & 2) ? a_raw : __ldg(args.beta + c);
+        cp = load_chan_params(args.alpha, args.beta, (int)(d0.row - g.chan.div(d0.row) * g.chan.d), g.flags);
     }
     uint32_t phase = 0;
     int st = 0;
     for (;;) {
         const uint32_t nwt = wt + GW;
         const bool has_next = nwt < g.n_wtiles;
-        float a_nraw = 0.f, b_nraw = 0.f;
         Prefetch pf{nullptr, nullptr, 0u, 0u, 0u, 0u};
+        NextChan nc{args.alpha, args.beta, -1, g.flags};
+        ChanParams cp_next = cp;
         if (has_next) {
             const TileDesc nxt = describe_tile<L>(nwt, lane, g);
-            const uint32_t c = nxt.row - g.chan.div(nxt.row) * g.chan.d;
-            a_nraw = __ldg(args.alpha + c);
-            b_nraw = (g.flags & 2) ? a_nraw : __ldg(args.beta + c);
+            nc.c = (int32_t)(nxt.row - g.chan.div(nxt.row) * g.chan.d);
             if (ALIGNED) {
                 pf.src0 = px + nxt.ld_lo;
                 pf.src1 = pg + nxt.ld_lo;
@@ -819,8 +837,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         const TileDesc cur = describe_tile<L>(wt, lane, g);
         T* tile_x = stages + (size_t)st * 2 * WT::kStageElems;
         T* tile_g = tile_x + WT::kStageElems;
-        float a_eff, b_eff, ib;
-        effective_params(a_raw, b_raw, g.flags, a_eff, b_eff, ib);
+        const float a_eff = cp.a_eff, b_eff = cp.b_eff, ib = cp.ib;
         T* row0 = tile_x + (cur.row_base - cur.ld_lo);
         const T* grow0 = tile_g + (cur.row_base - cur.ld_lo);
         float ga = 0.f, gb = 0.f;
@@ -831,9 +848,9 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
             phase ^= (1u << st);
             const bool fast = cur.active && cur.t0 >= 5 && (cur.t0 + L + 5 < g.T);
             if (__all_sync(0xffffffffu, fast)) {
-                walk_bwd<T, CH, 0>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, 0xffffffffu, ga, gb);
+                walk_bwd<T, CH, 0>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, 0xffffffffu, ga, gb);
             } else if (cur.active) {
-                walk_bwd<T, CH, 1>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask, ga, gb);
+                walk_bwd<T, CH, 1>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, ga, gb);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -849,7 +866,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
                 tile_g[i] = pg[cur.ld_lo + i];
             }
             __syncwarp();
-            if (cur.active) walk_bwd<T, CH, 2>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, lane, amask, ga, gb);
+            if (cur.active) walk_bwd<T, CH, 2>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, ga, gb);
             __syncwarp();
             const int n_out = (int)(cur.flat_hi - cur.flat_lo);
             const T* src = tile_x + (cur.flat_lo - cur.ld_lo);
@@ -867,8 +884,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         }
         if (!has_next) break;
         wt = nwt;
-        a_raw = a_nraw;
-        b_raw = b_nraw;
+        cp = cp_next;
         st ^= 1;
     }
     if (ALIGNED && lane == 0) tma_store_wait_read();
