@@ -277,9 +277,9 @@ __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 // (16B-aligned rows); 2: rows not 16B-aligned (scalar smem I/O).  `row0` points at this row's sample 0
 // inside the staged tile (may lie outside the tile; only in-range positions are touched).
 // Step q (1 <= q <= L+5) handles the 2x-rate pair (s[2m-1], s[2m]), m = t0 - 3 + q, and completes
-// y[t0 + q - 6].  X ring: x[t0 - 8 + j] lives in xr[j % S]; accumulator ring: the two partial sums of
-// y[t0 + o] (odd-phase taps, even-phase taps: two fixed 6-term FMA chains, then one add) live in
-// ac[o % S] -- so results do not depend on how rows are cut into segments.
+// y[t0 + q - 6].  Register rings with compile-time slots hold the pending upsampler pairs and the two partial
+// sums of each pending y (odd-phase taps, even-phase taps: two fixed 6-term FMA chains, then one add), so
+// results do not depend on how rows are cut into segments.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen, float a, float ib, const FwdTaps& tp,
@@ -291,19 +291,24 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     constexpr int S = RingCfg<VEC>::S;
     constexpr int NFULL = L / S, REM = L % S;
     T* seg = row0 + t0;
-    float xr[S];
-    float2 ac[S];
+    // Both FIRs run in TRANSPOSED (scatter) form: a new input updates the six pending outputs it feeds, so
+    // the 12 FFMA2 of a step are independent of each other (dependences only reach back >= 1 step).
+    //   up[(m) % S]   : pending (u[2m-1], u[2m]);   x[m+2] is its last contribution
+    //   ac[(o) % S]   : pending (yo, ye) of y[t0+o]
+    float2 up[S], ac[S];
+    float xb[VEC];            // the current 16-byte chunk of x
     float hold[8], yb[VEC];
     float s_first = 0.f, s_last = 0.f, x_last = 0.f;
 
     // ---- preload x[t0-8 .. t0-1] and the edge constants; nothing below reads a neighbour's first 8
     //      samples again before the final __syncwarp, and nobody overwrites them before it (hold[]).
+    float xpre[8];
     if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < 8 / VEC; ++c) io::load_chunk(seg - 8 + c * VEC, &xr[c * VEC]);
+        for (int c = 0; c < 8 / VEC; ++c) io::load_chunk(seg - 8 + c * VEC, &xpre[c * VEC]);
     } else {
 #pragma unroll
-        for (int j = 2; j < 8; ++j) xr[j] = io::load1(row0 + min(max(t0 - 8 + j, 0), Tlen - 1));
+        for (int j = 3; j < 8; ++j) xpre[j] = io::load1(row0 + min(max(t0 - 8 + j, 0), Tlen - 1));
     }
     if (MODE != 0) {
         if (t0 == 0) {  // left replicate pad of x, and s[0] which the left pad of s repeats      filter.py:98
@@ -312,7 +317,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             const float x2 = io::load1(row0 + min(2, Tlen - 1));
             if (MODE == 1) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xr[j] = x0;
+                for (int j = 0; j < 8; ++j) xpre[j] = x0;
             }
             float u = tp.ue[0] * x2;
             u = fmaf(tp.ue[1], x1, u);
@@ -330,26 +335,37 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     }
     __syncwarp(mask);
 
-    // one step; Q is the static part of the step index (ring slots), q the dynamic step number
+    // one step; Q is the static part of the step index (ring slots), q the dynamic step number.
+    // Steps q <= 0 only feed x[t0-5 .. t0-1] into the pending upsampler outputs (warm-up).
     auto step = [&](const int Q, const int q, const bool first_iter) {
-        // --- bring in X[q+7 ..] = x[t0 + q - 1 ..]
-        if (MODE != 2) {
+        // --- the new input x[m+2] = x[t0 + q - 1]
+        float xv;
+        if (first_iter && Q <= 0) {
+            xv = xpre[Q + 7];
+        } else if (MODE != 2) {
             if ((Q + 7) % VEC == 0) {
-                float* dst = &xr[(Q + 7) % S];
-                io::load_chunk(seg + q - 1, dst);
+                io::load_chunk(seg + q - 1, xb);
                 if (MODE == 1) {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) dst[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : dst[e];
+                    for (int e = 0; e < VEC; ++e) xb[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : xb[e];
                 }
             }
+            xv = xb[(Q + 7) % VEC];
         } else {
-            xr[(Q + 7) % S] = io::load1(row0 + min(t0 + q - 1, Tlen - 1));
+            xv = io::load1(row0 + min(t0 + q - 1, Tlen - 1));
         }
-        // --- polyphase upsample: (u[2m-1], u[2m]) from x[m-3 .. m+2]                  resample.py:32-36
-        float2 u2 = __fmul2_rn(tp.p.cu[0], bcast2(xr[(Q + 7) % S]));
+        // --- upsampler, transposed form: (u[2(m+j)-1], u[2(m+j)]) += cu[j] * x[m+2]     resample.py:32-36
+        const float2 xx = bcast2(xv);
 #pragma unroll
-        for (int j = 1; j < 6; ++j) u2 = __ffma2_rn(tp.p.cu[j], bcast2(xr[(Q + 7 - j + S) % S]), u2);
-        // --- Snake / SnakeBeta on the pair                                          activations.py:124
+        for (int j = 0; j < 6; ++j) {
+            if (!(first_iter && Q + j < 1)) {
+                float2& pend = up[(Q + j + 4 * S) % S];
+                pend = (j == 5) ? __fmul2_rn(tp.p.cu[5], xx) : __ffma2_rn(tp.p.cu[j], xx, pend);
+            }
+        }
+        if (first_iter && Q < 1) return;
+        // --- (u[2m-1], u[2m]) is complete: Snake / SnakeBeta on the pair             activations.py:124
+        const float2 u2 = up[(Q + 4 * S) % S];
         const float2 th = __fmul2_rn(u2, bcast2(a));
         const float2 sn = make_float2(__sinf(th.x), __sinf(th.y));
         float2 s2 = __ffma2_rn(bcast2(ib), __fmul2_rn(sn, sn), u2);
@@ -362,22 +378,22 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             if (m > Tlen) s2.x = s_last;   // s[n] for n >= 2T repeats s[2T-1]
             if (m >= Tlen) s2.y = s_last;
         }
-        // --- scatter: (yo, ye)[m+2-j] += cd[j] * (s[2m-1], s[2m])                       filter.py:98-99
+        // --- low-pass, transposed form: (yo, ye)[m+2-j] += cd[j] * (s[2m-1], s[2m])     filter.py:98-99
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             if (!(first_iter && Q - 1 - j < 0)) {
-                float2& acc = ac[(Q - 1 - j + 2 * S) % S];
+                float2& acc = ac[(Q - 1 - j + 4 * S) % S];
                 acc = (j == 0) ? __fmul2_rn(tp.p.cd[0], s2) : __ffma2_rn(tp.p.cd[j], s2, acc);
             }
         }
         // --- y[t0 + q - 6] is complete
         if (!(first_iter && Q < 6)) {
             const int o = q - 6;
-            const float2 done = ac[(Q - 6 + 2 * S) % S];
+            const float2 done = ac[(Q - 6 + 4 * S) % S];
             const float yv = done.x + done.y;
             if (MODE != 2) {
-                yb[(Q - 6 + 2 * S) % VEC] = yv;
-                if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
+                yb[(Q - 6 + 4 * S) % VEC] = yv;
+                if ((Q - 6 + 4 * S) % VEC == VEC - 1) {
                     const int c0 = o - (VEC - 1);                     // first sample of the finished chunk
                     if (first_iter && Q - 6 - (VEC - 1) < 8) {         // (static) a neighbour may still need these x
 #pragma unroll
@@ -394,9 +410,9 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     };
 
     static_assert(L >= S, "segment shorter than the ring");
-    // the first 5 + S steps are fully static (q = 1 .. S+5): warm-up, and the outputs that must wait in hold[]
+    // the first 10 + S steps are fully static (q = -4 .. S+5): warm-up, and the outputs that must wait in hold[]
 #pragma unroll
-    for (int q = 1; q < 6 + S; ++q) step(q, q, true);
+    for (int q = -4; q < 6 + S; ++q) step(q, q, true);
     mid_walk_hook(pf, nc, next, lane);
     // main loop: q = S+6 .. L+5, S steps per trip, ring slots static inside the body
 #pragma unroll 1
@@ -441,23 +457,26 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     constexpr int IT_LAST = (L - 3) / S, K_LAST = (L - 3) % S;
     T* seg = row0 + t0;
     const T* gseg = grow0 + t0;
-    float xr[S], gr[S];
-    float2 ac[S];
+    // transposed-form FIRs, as in the forward: pending (u[2m-1], u[2m]), pending (ds[2m-1], ds[2m]),
+    // pending (dxo, dxe) of dx[t0+o]
+    float2 up[S], dp[S], ac[S];
+    float xb[VEC], gb_[VEC];
     float hold[8], yb[VEC];
     float d_lo = 0.f, d_hi = 0.f, x_last = 0.f;
 
+    float xpre[8], gpre[8];
     if (MODE != 2) {
 #pragma unroll
         for (int c = 0; c < 8 / VEC; ++c) {
-            io::load_chunk(seg - 8 + c * VEC, &xr[c * VEC]);
-            io::load_chunk(gseg - 8 + c * VEC, &gr[c * VEC]);
+            io::load_chunk(seg - 8 + c * VEC, &xpre[c * VEC]);
+            io::load_chunk(gseg - 8 + c * VEC, &gpre[c * VEC]);
         }
     } else {
 #pragma unroll
-        for (int j = 2; j < 8; ++j) {
+        for (int j = 3; j < 8; ++j) {
             const int t = t0 - 8 + j;
-            xr[j] = io::load1(row0 + min(max(t, 0), Tlen - 1));
-            gr[j] = (t >= 0) ? io::load1(grow0 + max(t, 0)) : 0.f;
+            xpre[j] = io::load1(row0 + min(max(t, 0), Tlen - 1));
+            gpre[j] = (t >= 0) ? io::load1(grow0 + max(t, 0)) : 0.f;
         }
     }
     if (MODE != 0) {
@@ -467,7 +486,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
             if (MODE == 1) {
                 const float x0 = io::load1(row0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { xr[j] = x0; gr[j] = 0.f; }   // replicate x; gy does not extend
+                for (int j = 0; j < 8; ++j) { xpre[j] = x0; gpre[j] = 0.f; }   // replicate x; gy does not extend
             }
             // adjoint of the left replicate pad of s: taps that fell on the pad fold onto s[0]
             const float g0 = io::load1(grow0);
@@ -492,34 +511,45 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     float2 ga2 = make_float2(0.f, 0.f), gb2 = make_float2(0.f, 0.f);
 
     auto step = [&](const int Q, const int q, const bool first_iter, const bool tail) {
-        if (MODE != 2) {
+        // --- the new inputs x[m+2], gy[m+2]  (index t0 + q - 1)
+        float xv, gv;
+        if (first_iter && Q <= 0) {
+            xv = xpre[Q + 7];
+            gv = gpre[Q + 7];
+        } else if (MODE != 2) {
             if ((Q + 7) % VEC == 0) {
-                float* dx = &xr[(Q + 7) % S];
-                float* dg = &gr[(Q + 7) % S];
-                io::load_chunk(seg + q - 1, dx);
-                io::load_chunk(gseg + q - 1, dg);
+                io::load_chunk(seg + q - 1, xb);
+                io::load_chunk(gseg + q - 1, gb_);
                 if (MODE == 1) {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
                         const bool past = t0 + q - 1 + e > Tlen - 1;
-                        dx[e] = past ? x_last : dx[e];
-                        dg[e] = past ? 0.f : dg[e];
+                        xb[e] = past ? x_last : xb[e];
+                        gb_[e] = past ? 0.f : gb_[e];
                     }
                 }
             }
+            xv = xb[(Q + 7) % VEC];
+            gv = gb_[(Q + 7) % VEC];
         } else {
             const int t = t0 + q - 1;
-            xr[(Q + 7) % S] = io::load1(row0 + min(t, Tlen - 1));
+            xv = io::load1(row0 + min(t, Tlen - 1));
             const float g = io::load1(grow0 + min(t, Tlen - 1));
-            gr[(Q + 7) % S] = (t < Tlen) ? g : 0.f;
+            gv = (t < Tlen) ? g : 0.f;
         }
-        float2 u2 = __fmul2_rn(tp.p.cu[0], bcast2(xr[(Q + 7) % S]));
-        float2 d2 = __fmul2_rn(tp.p.cd[0], bcast2(gr[(Q + 7) % S]));
+        const float2 xx = bcast2(xv), gg = bcast2(gv);
 #pragma unroll
-        for (int j = 1; j < 6; ++j) {
-            u2 = __ffma2_rn(tp.p.cu[j], bcast2(xr[(Q + 7 - j + S) % S]), u2);
-            d2 = __ffma2_rn(tp.p.cd[j], bcast2(gr[(Q + 7 - j + S) % S]), d2);
+        for (int j = 0; j < 6; ++j) {
+            if (!(first_iter && Q + j < 1)) {
+                float2& pu = up[(Q + j + 4 * S) % S];
+                float2& pd = dp[(Q + j + 4 * S) % S];
+                pu = (j == 5) ? __fmul2_rn(tp.p.cu[5], xx) : __ffma2_rn(tp.p.cu[j], xx, pu);
+                pd = (j == 5) ? __fmul2_rn(tp.p.cd[5], gg) : __ffma2_rn(tp.p.cd[j], gg, pd);
+            }
         }
+        if (first_iter && Q < 1) return;
+        const float2 u2 = up[(Q + 4 * S) % S];
+        float2 d2 = dp[(Q + 4 * S) % S];
         const int m = t0 - 3 + q;
         if (MODE != 0) {
             // ds does not exist outside [0, 2T): what fell on the replicate pads was folded into d_lo / d_hi
@@ -559,30 +589,30 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             if (!(first_iter && Q - 1 - j < LOW)) {
-                float2& acc = ac[(Q - 1 - j + 2 * S) % S];
+                float2& acc = ac[(Q - 1 - j + 4 * S) % S];
                 acc = (j == 0) ? __fmul2_rn(tp.p.cu[0], du2) : __ffma2_rn(tp.p.cu[j], du2, acc);
             }
         }
         if (!(first_iter && Q < 6)) {
             const int o = q - 6;
-            const float2 done = ac[(Q - 6 + 2 * S) % S];
+            const float2 done = ac[(Q - 6 + 4 * S) % S];
             float yv = done.x + done.y;
             if (MODE != 0) {
                 // adjoint of the x replicate pad: fold dx_ext beyond the row onto its first / last sample
-                if (Q == 6 && o == 0) {
+                if (first_iter && Q == 6) {
                     if (t0 == 0) {
-                        const float2 e1 = ac[(2 * S - 1) % S], e2 = ac[(2 * S - 2) % S], e3 = ac[(2 * S - 3) % S];
+                        const float2 e1 = ac[(4 * S - 1) % S], e2 = ac[(4 * S - 2) % S], e3 = ac[(4 * S - 3) % S];
                         yv += (e3.x + e3.y) + (e2.x + e2.y) + (e1.x + e1.y);
                     }
                 }
                 if (t0 + o == Tlen - 1) {
-                    const float2 e1 = ac[(Q - 5 + 2 * S) % S], e2 = ac[(Q - 4 + 2 * S) % S], e3 = ac[(Q - 3 + 2 * S) % S];
+                    const float2 e1 = ac[(Q - 5 + 4 * S) % S], e2 = ac[(Q - 4 + 4 * S) % S], e3 = ac[(Q - 3 + 4 * S) % S];
                     yv += (e1.x + e1.y) + (e2.x + e2.y) + (e3.x + e3.y);
                 }
             }
             if (MODE != 2) {
-                yb[(Q - 6 + 2 * S) % VEC] = yv;
-                if ((Q - 6 + 2 * S) % VEC == VEC - 1) {
+                yb[(Q - 6 + 4 * S) % VEC] = yv;
+                if ((Q - 6 + 4 * S) % VEC == VEC - 1) {
                     const int c0 = o - (VEC - 1);
                     if (first_iter && Q - 6 - (VEC - 1) < 8) {
 #pragma unroll
@@ -600,7 +630,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
 
     static_assert(L >= S + 3, "segment shorter than the ring");
 #pragma unroll
-    for (int q = 1; q < 6 + S; ++q) step(q, q, true, false);
+    for (int q = -4; q < 6 + S; ++q) step(q, q, true, false);
     mid_walk_hook(pf, nc, next, lane);
 #pragma unroll 1
     for (int it = 1; it < NFULL + (REM ? 1 : 0); ++it) {
