@@ -43,6 +43,7 @@ struct Plan {
     int vec;
     int L;
     bool aligned;
+    bool half;           // bf16 rows 8-byte but not 16-byte aligned (T % 8 == 4): TMA path with 8-byte smem chunks
     uint32_t nseg;
     uint32_t total_segs;
     uint32_t n_wtiles;
@@ -127,7 +128,8 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
     const uintptr_t ptr_or = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
     if (ptr_or & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
-    pl->aligned = (T % pl->vec == 0) && ((ptr_or & 15) == 0);
+    pl->half = dtype == AFA_DTYPE_BF16 && (T % 8 == 4);
+    pl->aligned = ((T % pl->vec == 0) || pl->half) && ((ptr_or & 15) == 0);
     return 0;
 }
 
@@ -164,6 +166,7 @@ afa::Geometry make_geometry(const Plan& pl, int64_t batch, int64_t channels, int
     g.chan = make_fastdiv((uint32_t)channels);
     g.T = (int32_t)T;
     g.flags = flags;
+    g.half = pl.half ? 1 : 0;
     return g;
 }
 

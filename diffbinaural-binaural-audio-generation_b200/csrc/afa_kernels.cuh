@@ -84,6 +84,7 @@ struct Geometry {
     FastDiv chan;         // channels
     int32_t T;
     int32_t flags;
+    int32_t half;         // rows are only 8-byte aligned (bf16, T % 8 == 4): 8-byte shared-memory chunk I/O, split stores
 };
 
 struct FwdArgs {
@@ -168,6 +169,9 @@ struct IO<float> {
     static __device__ __forceinline__ void store_chunk(float* p, const float* v) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    static __device__ __forceinline__ void load_chunk(const float* p, float* o, bool) { load_chunk(p, o); }   // fp32 rows: 16B or nothing
+    static __device__ __forceinline__ void store_chunk(float* p, const float* v, bool) { store_chunk(p, v); }
+    static __device__ __forceinline__ void store_half_chunk(float*, const float*) {}
     static __device__ __forceinline__ float load1(const float* p) { return *p; }
     static __device__ __forceinline__ void store1(float* p, float v) { *p = v; }
 };
@@ -191,6 +195,41 @@ struct IO<__nv_bfloat16> {
             w[i] = *reinterpret_cast<const uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // `half`: the chunk is only 8-byte aligned -> two 8-byte accesses
+    static __device__ __forceinline__ void load_chunk(const __nv_bfloat16* p, float* o, bool half) {
+        if (!half) {
+            load_chunk(p, o);
+        } else {
+            const uint2 a = *reinterpret_cast<const uint2*>(p);
+            const uint2 b = *reinterpret_cast<const uint2*>(p + 4);
+            const uint32_t w[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                o[2 * i] = __uint_as_float(w[i] << 16);
+                o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+        }
+    }
+    static __device__ __forceinline__ void store_chunk(__nv_bfloat16* p, const float* v, bool half) {
+        if (!half) {
+            store_chunk(p, v);
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+            *reinterpret_cast<uint2*>(p + 4) = make_uint2(w[2], w[3]);
+        }
+    }
+    // rows that are 8-byte aligned end in the middle of a chunk: store only its first 4 samples
+    static __device__ __forceinline__ void store_half_chunk(__nv_bfloat16* p, const float* v) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     }
     static __device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -284,7 +323,7 @@ __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen, float a, float ib, const FwdTaps& tp,
                                          const Prefetch& pf, const NextChan& nc, ChanParams& next, int lane,
-                                         uint32_t mask) {
+                                         uint32_t mask, bool half) {
     using io = IO<T>;
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
@@ -305,7 +344,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     float xpre[8];
     if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < 8 / VEC; ++c) io::load_chunk(seg - 8 + c * VEC, &xpre[c * VEC]);
+        for (int c = 0; c < 8 / VEC; ++c) io::load_chunk(seg - 8 + c * VEC, &xpre[c * VEC], half);
     } else {
 #pragma unroll
         for (int j = 3; j < 8; ++j) xpre[j] = io::load1(row0 + min(max(t0 - 8 + j, 0), Tlen - 1));
@@ -344,7 +383,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             xv = xpre[Q + 7];
         } else if (MODE != 2) {
             if ((Q + 7) % VEC == 0) {
-                io::load_chunk(seg + q - 1, xb);
+                io::load_chunk(seg + q - 1, xb, half);
                 if (MODE == 1) {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) xb[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : xb[e];
@@ -398,8 +437,10 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
                     if (first_iter && Q - 6 - (VEC - 1) < 8) {         // (static) a neighbour may still need these x
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) hold[Q - 6 - (VEC - 1) + e] = yb[e];
-                    } else if (MODE == 0 || t0 + c0 < Tlen) {
-                        io::store_chunk(seg + c0, yb);
+                    } else if (MODE == 0 || t0 + c0 + VEC <= Tlen) {
+                        io::store_chunk(seg + c0, yb, half);
+                    } else if (t0 + c0 < Tlen) {
+                        io::store_half_chunk(seg + c0, yb);      // half-aligned rows end mid-chunk
                     }
                 }
             } else {
@@ -429,8 +470,10 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     __syncwarp(mask);  // every lane has finished reading its right halo: now the first 8 outputs may land
     if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < 8 / VEC; ++c)
-            if (MODE == 0 || t0 + c * VEC < Tlen) io::store_chunk(seg + c * VEC, &hold[c * VEC]);
+        for (int c = 0; c < 8 / VEC; ++c) {
+            if (MODE == 0 || t0 + c * VEC + VEC <= Tlen) io::store_chunk(seg + c * VEC, &hold[c * VEC], half);
+            else if (t0 + c * VEC < Tlen) io::store_half_chunk(seg + c * VEC, &hold[c * VEC]);
+        }
     } else {
 #pragma unroll
         for (int o = 0; o < 8; ++o)
@@ -446,7 +489,8 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
 template <typename T, int CH, int MODE>
 __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restrict__ grow0, int t0, int Tlen, float a,
                                          float ib, const BwdTaps& tp, const Prefetch& pf, const NextChan& nc,
-                                         ChanParams& next, int lane, uint32_t mask, float& ga_out, float& gb_out) {
+                                         ChanParams& next, int lane, uint32_t mask, bool half, float& ga_out,
+                                         float& gb_out) {
     using io = IO<T>;
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
@@ -468,8 +512,8 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     if (MODE != 2) {
 #pragma unroll
         for (int c = 0; c < 8 / VEC; ++c) {
-            io::load_chunk(seg - 8 + c * VEC, &xpre[c * VEC]);
-            io::load_chunk(gseg - 8 + c * VEC, &gpre[c * VEC]);
+            io::load_chunk(seg - 8 + c * VEC, &xpre[c * VEC], half);
+            io::load_chunk(gseg - 8 + c * VEC, &gpre[c * VEC], half);
         }
     } else {
 #pragma unroll
@@ -518,8 +562,8 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
             gv = gpre[Q + 7];
         } else if (MODE != 2) {
             if ((Q + 7) % VEC == 0) {
-                io::load_chunk(seg + q - 1, xb);
-                io::load_chunk(gseg + q - 1, gb_);
+                io::load_chunk(seg + q - 1, xb, half);
+                io::load_chunk(gseg + q - 1, gb_, half);
                 if (MODE == 1) {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
@@ -617,8 +661,10 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                     if (first_iter && Q - 6 - (VEC - 1) < 8) {
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) hold[Q - 6 - (VEC - 1) + e] = yb[e];
-                    } else if (MODE == 0 || t0 + c0 < Tlen) {
-                        io::store_chunk(seg + c0, yb);
+                    } else if (MODE == 0 || t0 + c0 + VEC <= Tlen) {
+                        io::store_chunk(seg + c0, yb, half);
+                    } else if (t0 + c0 < Tlen) {
+                        io::store_half_chunk(seg + c0, yb);      // half-aligned rows end mid-chunk
                     }
                 }
             } else {
@@ -652,8 +698,10 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     __syncwarp(mask);
     if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < 8 / VEC; ++c)
-            if (MODE == 0 || t0 + c * VEC < Tlen) io::store_chunk(seg + c * VEC, &hold[c * VEC]);
+        for (int c = 0; c < 8 / VEC; ++c) {
+            if (MODE == 0 || t0 + c * VEC + VEC <= Tlen) io::store_chunk(seg + c * VEC, &hold[c * VEC], half);
+            else if (t0 + c * VEC < Tlen) io::store_half_chunk(seg + c * VEC, &hold[c * VEC]);
+        }
     } else {
 #pragma unroll
         for (int o = 0; o < 8; ++o)
@@ -668,7 +716,8 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
 // ------------------------------------------------------------------------------------------------
 struct TileDesc {
     int64_t flat_lo, flat_hi;  // this warp tile's output range in the flat [rows*T] array
-    int64_t ld_lo, ld_hi;      // staged range (flat range + halo, clipped to the array)
+    int64_t ld_lo, ld_hi;      // staged range (flat range + halo, clipped to the array; 16-byte aligned for the TMA)
+    int64_t ld_extra;          // half-aligned rows: 4 trailing elements of the array the TMA cannot fetch, or -1
     int64_t row_base;          // row * T of this lane's row
     uint32_t gid, row;
     int32_t t0;
@@ -693,6 +742,17 @@ __device__ __forceinline__ TileDesc describe_tile(uint32_t wt, int lane, const G
     d.flat_hi = __shfl_sync(0xffffffffu, hi, (int)last_lane);
     d.ld_lo = max((int64_t)0, d.flat_lo - kHalo);
     d.ld_hi = min(g.total, d.flat_hi + kHalo);
+    d.ld_extra = -1;
+    if (g.half) {   // element offsets are multiples of 4 (8 bytes); the bulk copy needs multiples of 8 (16 bytes)
+        d.ld_lo &= ~(int64_t)7;
+        const int64_t up = (d.ld_hi + 7) & ~(int64_t)7;
+        if (up <= g.total) {
+            d.ld_hi = up;
+        } else {                  // array ends 8 bytes past a 16-byte boundary: fetch those 8 bytes by hand
+            d.ld_extra = g.total - 4;
+            d.ld_hi = g.total - 4;
+        }
+    }
     return d;
 }
 
@@ -700,11 +760,41 @@ template <typename T, int CH>
 struct WarpTile {
     static constexpr int VEC = IO<T>::VEC;
     static constexpr int L = CH * VEC;
-    static constexpr int kStageElems = 32 * L + 2 * kHalo;               // one tensor, one stage
+    static constexpr int kStageElems = 32 * L + 2 * kHalo + 8;           // one tensor, one stage (+8: 16-byte rounding of half-aligned tiles)
     static constexpr size_t kStageBytes = sizeof(T) * (size_t)kStageElems;  // multiple of 16
     static constexpr size_t fwd_smem(int nw) { return kBarBytes + (size_t)nw * 2 * kStageBytes; }
     static constexpr size_t bwd_smem(int nw) { return kBarBytes + (size_t)nw * 2 * 2 * kStageBytes; }
 };
+
+// Bulk-store a finished tile.  16-byte-aligned rows: one bulk TMA store.  Half-aligned rows (bf16, T % 8 == 4):
+// the 16-byte-aligned body goes by bulk store, up to 4 leading / trailing elements by 8-byte stores.
+template <typename T>
+__device__ __forceinline__ void store_tile(T* gdst, const T* tile, const TileDesc& d, bool half, int lane) {
+    if (!half) {
+        if (lane == 0) {
+            tma_store_1d(gdst + d.flat_lo, tile + (d.flat_lo - d.ld_lo), (uint32_t)((d.flat_hi - d.flat_lo) * (int64_t)sizeof(T)));
+            tma_store_commit();
+        }
+        return;
+    }
+    const int64_t blo = (d.flat_lo + 7) & ~(int64_t)7, bhi = d.flat_hi & ~(int64_t)7;
+    if (lane == 0) {
+        if (bhi > blo) tma_store_1d(gdst + blo, tile + (blo - d.ld_lo), (uint32_t)((bhi - blo) * (int64_t)sizeof(T)));
+        tma_store_commit();
+    } else if (lane == 1) {
+        if (blo > d.flat_lo && blo <= d.flat_hi)
+            *reinterpret_cast<uint2*>(gdst + d.flat_lo) = *reinterpret_cast<const uint2*>(tile + (d.flat_lo - d.ld_lo));
+    } else if (lane == 2) {
+        if (bhi < d.flat_hi && bhi >= blo)
+            *reinterpret_cast<uint2*>(gdst + bhi) = *reinterpret_cast<const uint2*>(tile + (bhi - d.ld_lo));
+    }
+}
+// The 8 trailing bytes of the array that a 16-byte bulk copy cannot reach (half-aligned rows, last tile only).
+template <typename T>
+__device__ __forceinline__ void fetch_extra(T* tile, const T* gsrc, const TileDesc& d, int lane) {
+    if (d.ld_extra >= 0 && lane == 0)
+        *reinterpret_cast<uint2*>(tile + (d.ld_extra - d.ld_lo)) = *reinterpret_cast<const uint2*>(gsrc + d.ld_extra);
+}
 
 // ------------------------------------------------------------------------------------------------
 // forward kernel: persistent, one autonomous pipeline per warp
@@ -769,26 +859,27 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
         const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
 
         if (ALIGNED) {
+            const bool half = g.half != 0;
             mbar_wait(&bars[st], (phase >> st) & 1u);
             phase ^= (1u << st);
+            if (half) {
+                fetch_extra(tile, gx, cur, lane);
+                __syncwarp();
+            }
             const bool fast = cur.active && cur.t0 >= 5 && (cur.t0 + L + 5 < g.T);
             if (__all_sync(0xffffffffu, fast)) {
-                walk_fwd<T, CH, 0>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, 0xffffffffu);
+                walk_fwd<T, CH, 0>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, 0xffffffffu, half);
             } else if (cur.active) {
-                walk_fwd<T, CH, 1>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask);
+                walk_fwd<T, CH, 1>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, half);
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                tma_store_1d(gy + cur.flat_lo, tile + (cur.flat_lo - cur.ld_lo),
-                             (uint32_t)((cur.flat_hi - cur.flat_lo) * (int64_t)sizeof(T)));
-                tma_store_commit();
-            }
+            store_tile(gy, tile, cur, half, lane);
         } else {
             const int n_in = (int)(cur.ld_hi - cur.ld_lo);
             for (int i = lane; i < n_in; i += 32) tile[i] = gx[cur.ld_lo + i];
             __syncwarp();
-            if (cur.active) walk_fwd<T, CH, 2>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask);
+            if (cur.active) walk_fwd<T, CH, 2>(row0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, false);
             __syncwarp();
             const int n_out = (int)(cur.flat_hi - cur.flat_lo);
             const T* src = tile + (cur.flat_lo - cur.ld_lo);
@@ -874,21 +965,23 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
 
         if (ALIGNED) {
+            const bool half = g.half != 0;
             mbar_wait(&bars[st], (phase >> st) & 1u);
             phase ^= (1u << st);
+            if (half) {
+                fetch_extra(tile_x, px, cur, lane);
+                fetch_extra(tile_g, pg, cur, lane);
+                __syncwarp();
+            }
             const bool fast = cur.active && cur.t0 >= 5 && (cur.t0 + L + 5 < g.T);
             if (__all_sync(0xffffffffu, fast)) {
-                walk_bwd<T, CH, 0>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, 0xffffffffu, ga, gb);
+                walk_bwd<T, CH, 0>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, 0xffffffffu, half, ga, gb);
             } else if (cur.active) {
-                walk_bwd<T, CH, 1>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, ga, gb);
+                walk_bwd<T, CH, 1>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, half, ga, gb);
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                tma_store_1d(po + cur.flat_lo, tile_x + (cur.flat_lo - cur.ld_lo),
-                             (uint32_t)((cur.flat_hi - cur.flat_lo) * (int64_t)sizeof(T)));
-                tma_store_commit();
-            }
+            store_tile(po, tile_x, cur, half, lane);
         } else {
             const int n_in = (int)(cur.ld_hi - cur.ld_lo);
             for (int i = lane; i < n_in; i += 32) {
@@ -896,7 +989,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
                 tile_g[i] = pg[cur.ld_lo + i];
             }
             __syncwarp();
-            if (cur.active) walk_bwd<T, CH, 2>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, ga, gb);
+            if (cur.active) walk_bwd<T, CH, 2>(row0, grow0, cur.t0, g.T, a_eff, ib, args.taps, pf, nc, cp_next, lane, amask, false, ga, gb);
             __syncwarp();
             const int n_out = (int)(cur.flat_hi - cur.flat_lo);
             const T* src = tile_x + (cur.flat_lo - cur.ld_lo);
