@@ -101,10 +101,11 @@ int grid_for(const void* kernel, size_t smem, uint32_t n_wtiles, uint32_t* grid)
 
 // Segment length heuristic (measured, profiles/): long segments amortise the 5 warm-up steps and the
 // per-tile bookkeeping, but need enough warp tiles to keep every resident warp busy for >= 2 tiles.
-int default_chunks(int which, int dtype, int64_t elements) {
-    if (which == 1) return 9;
+int default_chunks(int which, int dtype, int64_t elements, int64_t T) {
     const int vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
     const int64_t wtiles13 = elements / (32 * 13 * vec);
+    if (which == 1)   // backward: two staged tensors -> fewer resident warps; long segments only pay on long rows
+        return (wtiles13 >= 2 * 148 * 8 && T >= 32768) ? 13 : 5;
     return wtiles13 >= 2 * 148 * 16 ? 13 : 9;
 }
 
@@ -115,7 +116,7 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     if (T >= (1ll << 30)) return fail(AFA_ERR_TOO_LARGE, "T=%lld exceeds 2^30", (long long)T);
     pl->dtype = dtype;
     pl->vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
-    int ch = g_tune_chunks[which] ? g_tune_chunks[which] : default_chunks(which, dtype, batch * channels * T);
+    int ch = g_tune_chunks[which] ? g_tune_chunks[which] : default_chunks(which, dtype, batch * channels * T, T);
     pl->chunks = ch;
     pl->L = ch * pl->vec;
     const int64_t rows = batch * channels;
