@@ -45,6 +45,13 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def stage_shapes(clips: int, t_mel: int):
     return [(2 * clips, c, mult * t_mel, calls) for (c, mult, calls) in AMP_STAGES]
 
@@ -116,8 +123,8 @@ def cpu_reference_pass(t_mel: int, clips: int = 1, repeats: int = 1, threads: in
 
     from oracle import torch_path as TP
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    torch.set_num_threads(threads or host_cores())
     torch.manual_seed(1234)
     taps = TP.make_taps()
     work = []
@@ -140,7 +147,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = torch.get_num_threads()
+    cores = host_cores()
     t_mel = args.t_mel
     sample = (f"one Activation1d call per AMP stage shape (6 calls, B=2 i.e. one binaural clip, T_mel={t_mel}, fp32) "
               f"per step, torch CPU ops, {cores} threads")
@@ -353,7 +360,7 @@ def run_gpu(args):
 
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
+        cores = host_cores()
         cpu_reference_pass(args.t_mel, 1, repeats=1)
         elems, times = cpu_reference_pass(args.t_mel, 1, repeats=args.cpu_repeats)
         cpu_base = {"value": round(elems * 8 / min(times) / 1e9, 4), "unit": UNIT, "cores": cores, "kind": "port",
