@@ -264,6 +264,58 @@ def run_e2e(wl: Workload, steps: int, warmup: int):
     return dt / steps, h2d, h2d
 
 
+def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: int, t_mel: int, reps: int = 1):
+    """audio-seconds per second of the whole generator (BASELINE configs 3/4): `total_clips` 10-second binaural
+    clips dealt round-robin over ranks; per batch: pinned H2D of the mels -> CUDA-graph replay of the bf16 generator
+    (fused Activation1d + cuDNN convolutions) on L and R -> D2H of the waveforms.  Random-init weights."""
+    import torch
+    import torch.distributed as dist
+
+    from afa_b200 import shard_indices
+    from afa_b200.vocoder import BigVGANGenerator, GraphedVocoder
+
+    torch.manual_seed(1234)
+    gen = BigVGANGenerator().to(dev)
+    with torch.no_grad():
+        for n, p in gen.named_parameters():
+            if n.endswith("alpha") or n.endswith("beta"):
+                p.normal_(0, 0.5)
+    gen = gen.bfloat16().eval()
+    B = 2 * clips_per_batch
+    gv = GraphedVocoder(gen, B, t_mel, dtype=torch.bfloat16, device=dev)
+    mine = shard_indices(total_clips, rank, world)
+    n_batches = (len(mine) + clips_per_batch - 1) // clips_per_batch
+    mel_host = (torch.rand(B, 80, t_mel) * 14.5 - 12.0).pin_memory()          # U(-12, 2.5): DiffBinaural's mel clamp range
+    wav_host = torch.empty(B, 1, t_mel * gen.hop, dtype=torch.bfloat16).pin_memory()
+    for _ in range(2):
+        wav_host.copy_(gv(mel_host.to(dev, non_blocking=True)), non_blocking=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for _b in range(n_batches):
+            y = gv(mel_host.to(dev, non_blocking=True))
+            wav_host.copy_(y, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the only collective of the inference path: gather finished waveforms (one per rank here)
+        outs = [torch.empty_like(gv.static_out) for _ in range(world)]
+        dist.all_gather(outs, gv.static_out)
+    ms = float(t.item())
+    return {
+        "audio_sec_per_sec": round(total_clips * 10.0 / (ms * 1e-3), 1), "unit": "binaural audio-s per wall-s",
+        "total_clips": total_clips, "clips_per_batch": clips_per_batch, "ms_total": round(ms, 2),
+        "ms_per_clip_per_gpu": round(ms / max(1, len(mine)), 3), "dtype": "bf16 generator, fp32 math inside Activation1d",
+        "includes": "pinned H2D of mels, CUDA-graph replay (fused Activation1d + cuDNN convs), D2H of waveforms",
+        "params": sum(p.numel() for p in gen.parameters()),
+    }
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -287,6 +339,9 @@ def run_gpu(args):
 
     wl = Workload(dev, args.clips, args.t_mel, dtype)
     bytes_per_step = wl.elements * 2 * esize
+    shapes_calls = [list(s["shape"]) + [s["calls"]] for s in wl.stages]
+    n_elements, n_launches = wl.elements, wl.launches
+    min_call_mb = min(s["shape"][0] * s["shape"][1] * s["shape"][2] for s in wl.stages) * esize * 2 / 1e6
 
     # warm-up (also fills the host tap caches), then capture the step in a CUDA graph
     for _ in range(max(1, args.warmup if not args.graph else 1)):
@@ -367,7 +422,19 @@ def run_gpu(args):
                     "sample": (f"one Activation1d call per AMP stage shape (6 calls, B=2, T_mel={args.t_mel}, fp32, "
                                f"{elems} elements), torch CPU ops (oracle/torch_path.py), best of {args.cpu_repeats}")}
 
-    if world > 1:
+    used_graph = graph is not None
+    vocoder = None
+    if not args.no_vocoder:
+        del wl, graph
+        torch.cuda.empty_cache()
+        try:
+            # weak-scaling companion number: `--clips` clips per GPU through the whole generator
+            vocoder = run_vocoder(dev, world, rank, args.clips * world, min(4, args.clips), args.t_mel)
+        except Exception as exc:  # noqa: BLE001  (the headline metric must still print)
+            vocoder = {"error": repr(exc)[:200]}
+        wl = None
+
+    if world > 1 and wl is not None:
         # the only collective: gather one checksum per rank (stands in for gathering finished waveforms)
         chk = torch.stack([s["ys"][0].float().abs().mean() for s in wl.stages]).sum().reshape(1)
         outs = [torch.empty_like(chk) for _ in range(world)]
@@ -381,11 +448,10 @@ def run_gpu(args):
             "config": {
                 "workload": (f"bigvgan_binaural_22khz_80band_256x: all 109 AMP Activation1d forwards of one generator pass, "
                              f"{args.clips} x 10 s binaural clips per GPU (B={2 * args.clips}, T_mel={args.t_mel}), SnakeBeta logscale"),
-                "shapes_BCT_calls": [list(s["shape"]) + [s["calls"]] for s in wl.stages],
-                "elements_per_step": wl.elements, "algorithmic_bytes_per_step": bytes_per_step,
-                "l2": "every call's tensors exceed L2 (>=%.0f MB in + out per call) and rotate over 2 buffer sets" % (
-                    min(s["shape"][0] * s["shape"][1] * s["shape"][2] for s in wl.stages) * esize * 2 / 1e6),
-                "cuda_graph": bool(graph is not None), "parallelism": f"clip-sharded dp{world}, no collective in the path",
+                "shapes_BCT_calls": shapes_calls,
+                "elements_per_step": n_elements, "algorithmic_bytes_per_step": bytes_per_step,
+                "l2": "every call's tensors exceed L2 (>=%.0f MB in + out per call) and rotate over 2 buffer sets" % min_call_mb,
+                "cuda_graph": used_graph, "parallelism": f"clip-sharded dp{world}, no collective in the path",
             },
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
@@ -396,8 +462,38 @@ def run_gpu(args):
             "gpu_launches": int(gpu_launches),
             "clocks": clocks.summary(),
             "audio_sec_per_sec_activation_only": round(world * args.clips * 10.0 / (ms_per_step * 1e-3), 2),
+            "vocoder": vocoder,
         }
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_vocoder_mode(args):
+    """`--mode vocoder`: BASELINE config 3/4 as the main line -- `--total-clips` clips, strong scaling over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    with ClockSampler(local_rank) as clocks:
+        v = run_vocoder(dev, world, rank, args.total_clips, min(4, args.total_clips), args.t_mel, reps=max(1, args.steps))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "vocoded_audio_sec_per_sec", "value": v["audio_sec_per_sec"], "unit": "audio-s/s", "n_gpus": world,
+            "steps": max(1, args.steps), "warmup": 2, "ms_per_step": v["ms_total"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"full BigVGAN generator (bigvgan_binaural_22khz_80band_256x, random init), "
+                                   f"{args.total_clips} x 10 s binaural clips sharded by clip over {world} GPU(s)",
+                       "parallelism": f"clip-sharded dp{world}, NCCL only to gather waveforms"},
+            "vocoder": v, "clocks": clocks.summary(),
+        }))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -498,6 +594,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the whole-generator audio-s/s companion number")
+    ap.add_argument("--mode", choices=["activation", "vocoder"], default="activation",
+                    help="vocoder: BASELINE config 4 (--total-clips clips sharded over the ranks, strong scaling)")
+    ap.add_argument("--total-clips", type=int, default=64)
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=0, help="tuning: 16-byte chunks per thread segment for the forward (0 = library default)")
     ap.add_argument("--table", action="store_true")
@@ -509,6 +609,8 @@ def main():
         return run_table(args)
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "vocoder":
+        return run_vocoder_mode(args)
     return run_gpu(args)
 
 
