@@ -298,3 +298,58 @@ def test_module_semantics_on_device():
     xs = x.clone().requires_grad_(True)
     ms(xs).sum().backward()
     assert ms.act.alpha.grad is not None and xs.grad is not None
+
+
+def test_ddp_wrapped_module_gets_all_gradients():
+    """train_binaural_mel.py:540-543 wraps the generator in DDP with find_unused_parameters=False: the fused op
+    must hand autograd a gradient for act.alpha and act.beta (single-process NCCL group here)."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    afa_b200, _, _, _, SnakeBeta = _mods()
+    dev = torch.device("cuda:0")
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1, device_id=dev)
+        created = True
+    try:
+        C = 16
+        m = afa_b200.Activation1d(activation=SnakeBeta(C, alpha_logscale=True)).to(dev)
+        ddp = DDP(m, device_ids=[0], find_unused_parameters=False)
+        x = torch.randn(4, C, 512, device=dev, requires_grad=True)
+        ddp(x).square().mean().backward()
+        assert m.act.alpha.grad is not None and m.act.beta.grad is not None and x.grad is not None
+        assert torch.isfinite(m.act.alpha.grad).all() and m.act.alpha.grad.abs().sum() > 0
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 500)              # train_binaural_mel.py:788-790
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_no_out_of_bounds_writes(dtype):
+    """compute-sanitizer is closed on this pool, so guard bands do its job for writes: outputs live inside a
+    larger sentinel-filled allocation (16-byte aligned, 8-byte aligned and unaligned placements) and the
+    sentinels must survive forward and backward."""
+    _, _lib, Fn, _, _ = _mods()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(21)
+    taps = Fn.host_taps(TP.make_taps())
+    guard = 64
+    es = 4 if dtype == torch.float32 else 2
+    for (B, C, T) in [(1, 1, 1), (2, 3, 4), (3, 5, 12), (2, 3, 37), (1, 7, 100), (2, 24, 3444), (5, 3, 2300)]:
+        n = B * C * T
+        a = torch.randn(C, device=dev) * 0.5
+        b = torch.randn(C, device=dev) * 0.5
+        x = torch.randn(B, C, T, device=dev).to(dtype)
+        gy = torch.randn(B, C, T, device=dev).to(dtype)
+        for shift in (0, 8 // es, 1):                       # 16-byte aligned, 8-byte aligned, element aligned
+            big = torch.full((n + 2 * guard + 8,), 12345.0, device=dev, dtype=dtype)
+            off = guard + shift
+            y = big[off : off + n].view(B, C, T)
+            Fn.activation1d_forward_raw(x, a, b, taps, taps, True, out=y)
+            torch.cuda.synchronize()
+            assert torch.all(big[:off] == 12345.0) and torch.all(big[off + n :] == 12345.0), (B, C, T, shift, "fwd")
+            assert torch.isfinite(y.float()).all()
+        gx, ga, gb = Fn.activation1d_backward_raw(x, gy, a, b, taps, taps, True)
+        assert torch.isfinite(gx.float()).all() and torch.isfinite(ga).all() and torch.isfinite(gb).all()
