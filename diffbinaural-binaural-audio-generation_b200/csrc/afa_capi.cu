@@ -11,7 +11,7 @@
 #include "afa_kernels.cuh"
 
 #ifndef AFA_CHUNK_LIST
-#define AFA_CHUNK_LIST(X) X(5) X(9) X(13)
+#define AFA_CHUNK_LIST(X) X(5) X(9) X(13) X(17)
 #endif
 
 namespace {
@@ -99,14 +99,26 @@ int grid_for(const void* kernel, size_t smem, uint32_t n_wtiles, uint32_t* grid)
 }
 
 
-// Segment length heuristic (measured, profiles/): long segments amortise the 5 warm-up steps and the
-// per-tile bookkeeping, but need enough warp tiles to keep every resident warp busy for >= 2 tiles.
+// Segment length heuristic, fitted to same-box sweeps on the model's shapes (profiles/r01_fwd_sweep_segment_length.log):
+// long segments amortise the warm-up steps and the per-tile bookkeeping, but every row end costs a slower
+// edge-mode warp, so short rows want short segments; small launches want many small tiles.
 int default_chunks(int which, int dtype, int64_t elements, int64_t T) {
     const int vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
-    const int64_t wtiles13 = elements / (32 * 13 * vec);
-    if (which == 1)   // backward: two staged tensors -> fewer resident warps; long segments only pay on long rows
+    if (which == 1) {   // backward: two staged tensors -> fewer resident warps; long segments only pay on long rows
+        const int64_t wtiles13 = elements / (32 * 13 * vec);
         return (wtiles13 >= 2 * 148 * 8 && T >= 32768) ? 13 : 5;
-    return wtiles13 >= 2 * 148 * 16 ? 13 : 9;
+    }
+    if (elements < (16ll << 20)) return 9;
+    if (dtype == AFA_DTYPE_F32) {
+        if (T < 8192) return 5;
+        if (T < 24576) return 9;
+        if (T < 49152) return 13;
+        return 17;
+    }
+    if (T < 8192) return 9;
+    if (T < 49152) return 5;
+    if (T < 131072) return 13;
+    return 17;
 }
 
 int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t batch, int64_t channels, int64_t T,

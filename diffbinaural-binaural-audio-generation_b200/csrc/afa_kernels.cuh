@@ -328,7 +328,6 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
-    constexpr int NFULL = L / S, REM = L % S;
     T* seg = row0 + t0;
     // Both FIRs run in TRANSPOSED (scatter) form: a new input updates the six pending outputs it feeds, so
     // the 12 FFMA2 of a step are independent of each other (dependences only reach back >= 1 step).
@@ -376,7 +375,8 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
 
     // one step; Q is the static part of the step index (ring slots), q the dynamic step number.
     // Steps q <= 0 only feed x[t0-5 .. t0-1] into the pending upsampler outputs (warm-up).
-    auto step = [&](const int Q, const int q, const bool first_iter) {
+    // `epi`: one of the last five steps (static): work that only feeds outputs of the NEXT segment is skipped
+    auto step = [&](const int Q, const int q, const bool first_iter, const bool epi) {
         // --- the new input x[m+2] = x[t0 + q - 1]
         float xv;
         if (first_iter && Q <= 0) {
@@ -385,8 +385,10 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             if ((Q + 7) % VEC == 0) {
                 io::load_chunk(seg + q - 1, xb, half);
                 if (MODE == 1) {
+                    if (__any_sync(mask, t0 + q - 1 + VEC - 1 > Tlen - 1)) {   // some lane's chunk crosses its row end
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) xb[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : xb[e];
+                        for (int e = 0; e < VEC; ++e) xb[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : xb[e];
+                    }
                 }
             }
             xv = xb[(Q + 7) % VEC];
@@ -397,7 +399,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
         const float2 xx = bcast2(xv);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            if (!(first_iter && Q + j < 1)) {
+            if (!(first_iter && Q + j < 1) && !(epi && Q + j > L + 5)) {
                 float2& pend = up[(Q + j + 4 * S) % S];
                 pend = (j == 5) ? __fmul2_rn(tp.p.cu[5], xx) : __ffma2_rn(tp.p.cu[j], xx, pend);
             }
@@ -420,7 +422,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
         // --- low-pass, transposed form: (yo, ye)[m+2-j] += cd[j] * (s[2m-1], s[2m])     filter.py:98-99
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            if (!(first_iter && Q - 1 - j < 0)) {
+            if (!(first_iter && Q - 1 - j < 0) && !(epi && Q - 1 - j >= L)) {
                 float2& acc = ac[(Q - 1 - j + 4 * S) % S];
                 acc = (j == 0) ? __fmul2_rn(tp.p.cd[0], s2) : __ffma2_rn(tp.p.cd[j], s2, acc);
             }
@@ -450,23 +452,26 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
         }
     };
 
-    static_assert(L >= S, "segment shorter than the ring");
-    // the first 10 + S steps are fully static (q = -4 .. S+5): warm-up, and the outputs that must wait in hold[]
+    // q = -4 .. S+5 static (warm-up + the outputs that wait in hold[]), q = S+6 .. L rolled (S steps per trip, ring
+    // slots static inside the body), q = L+1 .. L+5 static again (dead work towards the next segment removed)
+    constexpr int NR = L - S - 5, NF = NR / S, RM = NR % S;
+    static_assert(NR >= 0, "segment shorter than the ring");
 #pragma unroll
-    for (int q = -4; q < 6 + S; ++q) step(q, q, true);
+    for (int q = -4; q < 6 + S; ++q) step(q, q, true, false);
     mid_walk_hook(pf, nc, next, lane);
-    // main loop: q = S+6 .. L+5, S steps per trip, ring slots static inside the body
 #pragma unroll 1
-    for (int it = 1; it < NFULL + (REM ? 1 : 0); ++it) {
-        const int qb = 6 + it * S;
+    for (int it = 0; it < NF + (RM ? 1 : 0); ++it) {
+        const int qb = 6 + S + it * S;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
-            if (REM != 0 && k == REM) {
-                if (it == NFULL) break;
+            if (RM != 0 && k == RM) {
+                if (it == NF) break;
             }
-            step(6 + k, qb + k, false);
+            step(6 + k, qb + k, false, false);
         }
     }
+#pragma unroll
+    for (int q = L + 1; q < L + 6; ++q) step(q, q, false, true);
     __syncwarp(mask);  // every lane has finished reading its right halo: now the first 8 outputs may land
     if (MODE != 2) {
 #pragma unroll
@@ -495,10 +500,6 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
-    constexpr int NFULL = L / S, REM = L % S;
-    // the last step whose pair still holds an s-value of this segment is q = L+3 (its odd member);
-    // in loop coordinates q = 6 + it*S + k:
-    constexpr int IT_LAST = (L - 3) / S, K_LAST = (L - 3) % S;
     T* seg = row0 + t0;
     const T* gseg = grow0 + t0;
     // transposed-form FIRs, as in the forward: pending (u[2m-1], u[2m]), pending (ds[2m-1], ds[2m]),
@@ -554,7 +555,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     const float iba = ib * a;
     float2 ga2 = make_float2(0.f, 0.f), gb2 = make_float2(0.f, 0.f);
 
-    auto step = [&](const int Q, const int q, const bool first_iter, const bool tail) {
+    auto step = [&](const int Q, const int q, const bool first_iter, const bool epi) {
         // --- the new inputs x[m+2], gy[m+2]  (index t0 + q - 1)
         float xv, gv;
         if (first_iter && Q <= 0) {
@@ -565,11 +566,13 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                 io::load_chunk(seg + q - 1, xb, half);
                 io::load_chunk(gseg + q - 1, gb_, half);
                 if (MODE == 1) {
+                    if (__any_sync(mask, t0 + q - 1 + VEC - 1 > Tlen - 1)) {   // some lane's chunk crosses its row end
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const bool past = t0 + q - 1 + e > Tlen - 1;
-                        xb[e] = past ? x_last : xb[e];
-                        gb_[e] = past ? 0.f : gb_[e];
+                        for (int e = 0; e < VEC; ++e) {
+                            const bool past = t0 + q - 1 + e > Tlen - 1;
+                            xb[e] = past ? x_last : xb[e];
+                            gb_[e] = past ? 0.f : gb_[e];
+                        }
                     }
                 }
             }
@@ -584,7 +587,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
         const float2 xx = bcast2(xv), gg = bcast2(gv);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            if (!(first_iter && Q + j < 1)) {
+            if (!(first_iter && Q + j < 1) && !(epi && Q + j > L + 5)) {
                 float2& pu = up[(Q + j + 4 * S) % S];
                 float2& pd = dp[(Q + j + 4 * S) % S];
                 pu = (j == 5) ? __fmul2_rn(tp.p.cu[5], xx) : __ffma2_rn(tp.p.cu[j], xx, pu);
@@ -614,25 +617,24 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
         const float2 p2 = __fmul2_rn(d2, sn);
         const float2 du2 = __ffma2_rn(p2, bcast2(iba), d2);
         // parameter-gradient partials: s[2m-1] belongs to this segment for q in [4, L+3], s[2m] for q in [3, L+2]
-        if (first_iter) {
-            if (Q == 3) {
-                ga2.y = fmaf(p2.y, u2.y, ga2.y);
-                gb2.y += fmaf(-d2.y, cs.y, d2.y);
-            } else if (Q > 3) {
-                ga2 = __ffma2_rn(p2, u2, ga2);
-                gb2 = __fadd2_rn(gb2, __ffma2_rn(make_float2(-d2.x, -d2.y), cs, d2));
-            }
-        } else if (!tail) {
+        // (q <= S+5 and q > L are static steps, so the boundary cases cost nothing in the rolled loop)
+        const bool own_x = first_iter ? (Q >= 4) : (epi ? (Q <= L + 3) : true);
+        const bool own_y = first_iter ? (Q >= 3) : (epi ? (Q <= L + 2) : true);
+        if (own_x && own_y) {
             ga2 = __ffma2_rn(p2, u2, ga2);
             gb2 = __fadd2_rn(gb2, __ffma2_rn(make_float2(-d2.x, -d2.y), cs, d2));
-        } else if (Q == 6 + K_LAST) {
+        } else if (own_y) {
+            ga2.y = fmaf(p2.y, u2.y, ga2.y);
+            gb2.y += fmaf(-d2.y, cs.y, d2.y);
+        } else if (own_x) {
             ga2.x = fmaf(p2.x, u2.x, ga2.x);
             gb2.x += fmaf(-d2.x, cs.x, d2.x);
         }
         constexpr int LOW = (MODE == 0) ? 0 : -3;   // edge modes also keep dx_ext[-3..-1] (folded below)
+        constexpr int HIGH = (MODE == 0) ? L : L + 3;   // ... and dx_ext[T..T+2] when the row ends in this segment
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            if (!(first_iter && Q - 1 - j < LOW)) {
+            if (!(first_iter && Q - 1 - j < LOW) && !(epi && Q - 1 - j >= HIGH)) {
                 float2& acc = ac[(Q - 1 - j + 4 * S) % S];
                 acc = (j == 0) ? __fmul2_rn(tp.p.cu[0], du2) : __ffma2_rn(tp.p.cu[j], du2, acc);
             }
@@ -649,9 +651,11 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                         yv += (e3.x + e3.y) + (e2.x + e2.y) + (e1.x + e1.y);
                     }
                 }
-                if (t0 + o == Tlen - 1) {
-                    const float2 e1 = ac[(Q - 5 + 4 * S) % S], e2 = ac[(Q - 4 + 4 * S) % S], e3 = ac[(Q - 3 + 4 * S) % S];
-                    yv += (e1.x + e1.y) + (e2.x + e2.y) + (e3.x + e3.y);
+                if (__any_sync(mask, t0 + o == Tlen - 1)) {   // (warp-uniform guard keeps the fold off the common path)
+                    if (t0 + o == Tlen - 1) {
+                        const float2 e1 = ac[(Q - 5 + 4 * S) % S], e2 = ac[(Q - 4 + 4 * S) % S], e3 = ac[(Q - 3 + 4 * S) % S];
+                        yv += (e1.x + e1.y) + (e2.x + e2.y) + (e3.x + e3.y);
+                    }
                 }
             }
             if (MODE != 2) {
@@ -674,27 +678,24 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
         }
     };
 
-    static_assert(L >= S + 3, "segment shorter than the ring");
+    constexpr int NR = L - S - 5, NF = NR / S, RM = NR % S;
+    static_assert(NR >= 0, "segment shorter than the ring");
 #pragma unroll
     for (int q = -4; q < 6 + S; ++q) step(q, q, true, false);
     mid_walk_hook(pf, nc, next, lane);
 #pragma unroll 1
-    for (int it = 1; it < NFULL + (REM ? 1 : 0); ++it) {
-        const int qb = 6 + it * S;
-        if (it < IT_LAST) {
+    for (int it = 0; it < NF + (RM ? 1 : 0); ++it) {
+        const int qb = 6 + S + it * S;
 #pragma unroll
-            for (int k = 0; k < S; ++k) step(6 + k, qb + k, false, false);
-        } else {
-            // final trip(s): the parameter-gradient partials stop after q = L+3
-#pragma unroll
-            for (int k = 0; k < S; ++k) {
-                if (REM != 0 && k == REM) {
-                    if (it == NFULL) break;
-                }
-                step(6 + k, qb + k, false, (it > IT_LAST) || (k >= K_LAST));
+        for (int k = 0; k < S; ++k) {
+            if (RM != 0 && k == RM) {
+                if (it == NF) break;
             }
+            step(6 + k, qb + k, false, false);
         }
     }
+#pragma unroll
+    for (int q = L + 1; q < L + 6; ++q) step(q, q, false, true);
     __syncwarp(mask);
     if (MODE != 2) {
 #pragma unroll
