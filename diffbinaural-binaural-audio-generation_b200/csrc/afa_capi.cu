@@ -129,6 +129,10 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     pl->dtype = dtype;
     pl->vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
     int ch = g_tune_chunks[which] ? g_tune_chunks[which] : default_chunks(which, dtype, batch * channels * T, T);
+    const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
+    const uintptr_t ptr_or = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
+    pl->half = dtype == AFA_DTYPE_BF16 && (T % 8 == 4) && ((ptr_or & 15) == 0);
+    if (pl->half) ch = 9;   // kHalfChunks
     pl->chunks = ch;
     pl->L = ch * pl->vec;
     const int64_t rows = batch * channels;
@@ -138,10 +142,7 @@ int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t
     pl->nseg = (uint32_t)nseg;
     pl->total_segs = (uint32_t)total_segs;
     pl->n_wtiles = (uint32_t)((total_segs + 31) / 32);
-    const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
-    const uintptr_t ptr_or = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
     if (ptr_or & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
-    pl->half = dtype == AFA_DTYPE_BF16 && (T % 8 == 4);
     pl->aligned = ((T % pl->vec == 0) || pl->half) && ((ptr_or & 15) == 0);
     return 0;
 }
@@ -183,9 +184,9 @@ afa::Geometry make_geometry(const Plan& pl, int64_t batch, int64_t channels, int
     return g;
 }
 
-template <typename T, int CH, bool AL>
+template <typename T, int CH, bool AL, bool HALF = false>
 int launch_fwd_t(const afa::FwdArgs& a, cudaStream_t st) {
-    auto k = afa::afa_fwd_kernel<T, CH, kNW, AL>;
+    auto k = afa::afa_fwd_kernel<T, CH, kNW, AL, HALF>;
     const size_t smem = afa::WarpTile<T, CH>::fwd_smem(kNW);
     uint32_t grid = 0;
     if (int rc = grid_for((const void*)k, smem, a.g.n_wtiles, &grid)) return rc;
@@ -194,9 +195,9 @@ int launch_fwd_t(const afa::FwdArgs& a, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_fwd_kernel launch");
 }
-template <typename T, int CH, bool AL>
+template <typename T, int CH, bool AL, bool HALF = false>
 int launch_bwd_t(const afa::BwdArgs& a, cudaStream_t st) {
-    auto k = afa::afa_bwd_kernel<T, CH, kNW, AL>;
+    auto k = afa::afa_bwd_kernel<T, CH, kNW, AL, HALF>;
     const size_t smem = afa::WarpTile<T, CH>::bwd_smem(kNW);
     uint32_t grid = 0;
     if (int rc = grid_for((const void*)k, smem, a.g.n_wtiles, &grid)) return rc;
@@ -206,8 +207,13 @@ int launch_bwd_t(const afa::BwdArgs& a, cudaStream_t st) {
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_bwd_kernel launch");
 }
 
+constexpr int kHalfChunks = 9;   // the half-aligned (bf16, T % 8 == 4) kernels are compiled for this segment size only
+
 template <typename T>
 int launch_fwd(const Plan& pl, const afa::FwdArgs& a, cudaStream_t st) {
+    if constexpr (sizeof(T) == 2) {
+        if (pl.half && pl.aligned) return launch_fwd_t<T, kHalfChunks, true, true>(a, st);
+    }
 #define X(CH)                                                                                   \
     if (pl.chunks == CH)                                                                        \
         return pl.aligned ? launch_fwd_t<T, CH, true>(a, st) : launch_fwd_t<T, CH, false>(a, st);
@@ -217,6 +223,9 @@ int launch_fwd(const Plan& pl, const afa::FwdArgs& a, cudaStream_t st) {
 }
 template <typename T>
 int launch_bwd(const Plan& pl, const afa::BwdArgs& a, cudaStream_t st) {
+    if constexpr (sizeof(T) == 2) {
+        if (pl.half && pl.aligned) return launch_bwd_t<T, kHalfChunks, true, true>(a, st);
+    }
 #define X(CH)                                                                                   \
     if (pl.chunks == CH)                                                                        \
         return pl.aligned ? launch_bwd_t<T, CH, true>(a, st) : launch_bwd_t<T, CH, false>(a, st);
@@ -332,6 +341,11 @@ int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]) {
     }
     AFA_CHUNK_LIST(X)
 #undef X
+    if (pl.half && pl.aligned) {
+        k = which == 0 ? (const void*)afa::afa_fwd_kernel<__nv_bfloat16, kHalfChunks, kNW, true, true>
+                       : (const void*)afa::afa_bwd_kernel<__nv_bfloat16, kHalfChunks, kNW, true, true>;
+        smem = kernel_smem<__nv_bfloat16, kHalfChunks>(which);
+    }
     if (!k) return fail(AFA_ERR_BAD_ARG, "no kernel for %d chunks", pl.chunks);
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, k);

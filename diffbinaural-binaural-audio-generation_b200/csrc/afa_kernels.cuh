@@ -328,6 +328,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
+    constexpr bool kStaticTail = (VEC == 4);   // last five steps straight-line (fp32 only, see below)
     T* seg = row0 + t0;
     // Both FIRs run in TRANSPOSED (scatter) form: a new input updates the six pending outputs it feeds, so
     // the 12 FFMA2 of a step are independent of each other (dependences only reach back >= 1 step).
@@ -385,10 +386,8 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             if ((Q + 7) % VEC == 0) {
                 io::load_chunk(seg + q - 1, xb, half);
                 if (MODE == 1) {
-                    if (__any_sync(mask, t0 + q - 1 + VEC - 1 > Tlen - 1)) {   // some lane's chunk crosses its row end
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) xb[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : xb[e];
-                    }
+                    for (int e = 0; e < VEC; ++e) xb[e] = (t0 + q - 1 + e > Tlen - 1) ? x_last : xb[e];
                 }
             }
             xv = xb[(Q + 7) % VEC];
@@ -454,7 +453,9 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
 
     // q = -4 .. S+5 static (warm-up + the outputs that wait in hold[]), q = S+6 .. L rolled (S steps per trip, ring
     // slots static inside the body), q = L+1 .. L+5 static again (dead work towards the next segment removed)
-    constexpr int NR = L - S - 5, NF = NR / S, RM = NR % S;
+    // (the static tail pays for fp32; for bf16 its 16-step ring makes the extra straight-line code cost more in
+    //  instruction-cache misses than the removed dead work saves -- measured, profiles/r01_ab_epilogue.log)
+    constexpr int NR = kStaticTail ? L - S - 5 : L - S, NF = NR / S, RM = NR % S;
     static_assert(NR >= 0, "segment shorter than the ring");
 #pragma unroll
     for (int q = -4; q < 6 + S; ++q) step(q, q, true, false);
@@ -470,8 +471,10 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
             step(6 + k, qb + k, false, false);
         }
     }
+    if (kStaticTail) {
 #pragma unroll
-    for (int q = L + 1; q < L + 6; ++q) step(q, q, false, true);
+        for (int q = L + 1; q < L + 6; ++q) step(q, q, false, true);
+    }
     __syncwarp(mask);  // every lane has finished reading its right halo: now the first 8 outputs may land
     if (MODE != 2) {
 #pragma unroll
@@ -500,6 +503,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
+    constexpr bool kStaticTail = (VEC == 4);
     T* seg = row0 + t0;
     const T* gseg = grow0 + t0;
     // transposed-form FIRs, as in the forward: pending (u[2m-1], u[2m]), pending (ds[2m-1], ds[2m]),
@@ -566,13 +570,11 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                 io::load_chunk(seg + q - 1, xb, half);
                 io::load_chunk(gseg + q - 1, gb_, half);
                 if (MODE == 1) {
-                    if (__any_sync(mask, t0 + q - 1 + VEC - 1 > Tlen - 1)) {   // some lane's chunk crosses its row end
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) {
-                            const bool past = t0 + q - 1 + e > Tlen - 1;
-                            xb[e] = past ? x_last : xb[e];
-                            gb_[e] = past ? 0.f : gb_[e];
-                        }
+                    for (int e = 0; e < VEC; ++e) {
+                        const bool past = t0 + q - 1 + e > Tlen - 1;
+                        xb[e] = past ? x_last : xb[e];
+                        gb_[e] = past ? 0.f : gb_[e];
                     }
                 }
             }
@@ -618,8 +620,8 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
         const float2 du2 = __ffma2_rn(p2, bcast2(iba), d2);
         // parameter-gradient partials: s[2m-1] belongs to this segment for q in [4, L+3], s[2m] for q in [3, L+2]
         // (q <= S+5 and q > L are static steps, so the boundary cases cost nothing in the rolled loop)
-        const bool own_x = first_iter ? (Q >= 4) : (epi ? (Q <= L + 3) : true);
-        const bool own_y = first_iter ? (Q >= 3) : (epi ? (Q <= L + 2) : true);
+        const bool own_x = first_iter ? (Q >= 4) : (epi ? (Q <= L + 3) : (kStaticTail || q <= L + 3));
+        const bool own_y = first_iter ? (Q >= 3) : (epi ? (Q <= L + 2) : (kStaticTail || q <= L + 2));
         if (own_x && own_y) {
             ga2 = __ffma2_rn(p2, u2, ga2);
             gb2 = __fadd2_rn(gb2, __ffma2_rn(make_float2(-d2.x, -d2.y), cs, d2));
@@ -651,11 +653,9 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
                         yv += (e3.x + e3.y) + (e2.x + e2.y) + (e1.x + e1.y);
                     }
                 }
-                if (__any_sync(mask, t0 + o == Tlen - 1)) {   // (warp-uniform guard keeps the fold off the common path)
-                    if (t0 + o == Tlen - 1) {
-                        const float2 e1 = ac[(Q - 5 + 4 * S) % S], e2 = ac[(Q - 4 + 4 * S) % S], e3 = ac[(Q - 3 + 4 * S) % S];
-                        yv += (e1.x + e1.y) + (e2.x + e2.y) + (e3.x + e3.y);
-                    }
+                if (t0 + o == Tlen - 1) {
+                    const float2 e1 = ac[(Q - 5 + 4 * S) % S], e2 = ac[(Q - 4 + 4 * S) % S], e3 = ac[(Q - 3 + 4 * S) % S];
+                    yv += (e1.x + e1.y) + (e2.x + e2.y) + (e3.x + e3.y);
                 }
             }
             if (MODE != 2) {
@@ -678,7 +678,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
         }
     };
 
-    constexpr int NR = L - S - 5, NF = NR / S, RM = NR % S;
+    constexpr int NR = kStaticTail ? L - S - 5 : L - S, NF = NR / S, RM = NR % S;
     static_assert(NR >= 0, "segment shorter than the ring");
 #pragma unroll
     for (int q = -4; q < 6 + S; ++q) step(q, q, true, false);
@@ -694,8 +694,10 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
             step(6 + k, qb + k, false, false);
         }
     }
+    if (kStaticTail) {
 #pragma unroll
-    for (int q = L + 1; q < L + 6; ++q) step(q, q, false, true);
+        for (int q = L + 1; q < L + 6; ++q) step(q, q, false, true);
+    }
     __syncwarp(mask);
     if (MODE != 2) {
 #pragma unroll
@@ -725,7 +727,7 @@ struct TileDesc {
     bool active;               // this lane owns a segment
 };
 
-template <int L>
+template <int L, bool HALF>
 __device__ __forceinline__ TileDesc describe_tile(uint32_t wt, int lane, const Geometry& g) {
     TileDesc d;
     const uint32_t gid_first = wt * 32u;
@@ -744,7 +746,7 @@ __device__ __forceinline__ TileDesc describe_tile(uint32_t wt, int lane, const G
     d.ld_lo = max((int64_t)0, d.flat_lo - kHalo);
     d.ld_hi = min(g.total, d.flat_hi + kHalo);
     d.ld_extra = -1;
-    if (g.half) {   // element offsets are multiples of 4 (8 bytes); the bulk copy needs multiples of 8 (16 bytes)
+    if (HALF) {   // element offsets are multiples of 4 (8 bytes); the bulk copy needs multiples of 8 (16 bytes)
         d.ld_lo &= ~(int64_t)7;
         const int64_t up = (d.ld_hi + 7) & ~(int64_t)7;
         if (up <= g.total) {
@@ -800,7 +802,7 @@ __device__ __forceinline__ void fetch_extra(T* tile, const T* gsrc, const TileDe
 // ------------------------------------------------------------------------------------------------
 // forward kernel: persistent, one autonomous pipeline per warp
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CH, int NW, bool ALIGNED>
+template <typename T, int CH, int NW, bool ALIGNED, bool HALF = false>
 __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_MINB_F32 : AFA_FWD_MINB_BF16) : 1) afa_fwd_kernel(const __grid_constant__ FwdArgs args) {
     using WT = WarpTile<T, CH>;
     constexpr int L = WT::L;
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
     }
     ChanParams cp;
     {
-        const TileDesc d0 = describe_tile<L>(wt, lane, g);
+        const TileDesc d0 = describe_tile<L, HALF>(wt, lane, g);
         if (ALIGNED && lane == 0) {
             const uint32_t bytes = (uint32_t)((d0.ld_hi - d0.ld_lo) * (int64_t)sizeof(T));
             mbar_expect_tx(&bars[0], bytes);
@@ -844,7 +846,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
         NextChan nc{args.alpha, args.beta, -1, g.flags};
         ChanParams cp_next = cp;
         if (has_next) {
-            const TileDesc nxt = describe_tile<L>(nwt, lane, g);
+            const TileDesc nxt = describe_tile<L, HALF>(nwt, lane, g);
             nc.c = (int32_t)(nxt.row - g.chan.div(nxt.row) * g.chan.d);
             if (ALIGNED) {
                 pf.src0 = gx + nxt.ld_lo;
@@ -853,14 +855,14 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
                 pf.bytes = (uint32_t)((nxt.ld_hi - nxt.ld_lo) * (int64_t)sizeof(T));
             }
         }
-        const TileDesc cur = describe_tile<L>(wt, lane, g);
+        const TileDesc cur = describe_tile<L, HALF>(wt, lane, g);
         T* tile = stages + (size_t)st * WT::kStageElems;
         const float a_eff = cp.a_eff, b_eff = cp.b_eff, ib = cp.ib;
         T* row0 = tile + (cur.row_base - cur.ld_lo);
         const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
 
         if (ALIGNED) {
-            const bool half = g.half != 0;
+            constexpr bool half = HALF;   // compile-time: 16-byte-aligned launches pay nothing for the 8-byte path
             mbar_wait(&bars[st], (phase >> st) & 1u);
             phase ^= (1u << st);
             if (half) {
@@ -898,7 +900,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
 // ------------------------------------------------------------------------------------------------
 // backward kernel: same frame, two staged tensors (x, gy), gx written in place over x
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CH, int NW, bool ALIGNED>
+template <typename T, int CH, int NW, bool ALIGNED, bool HALF = false>
 __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_kernel(const __grid_constant__ BwdArgs args) {
     using WT = WarpTile<T, CH>;
     constexpr int L = WT::L;
@@ -927,7 +929,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
     }
     ChanParams cp;
     {
-        const TileDesc d0 = describe_tile<L>(wt, lane, g);
+        const TileDesc d0 = describe_tile<L, HALF>(wt, lane, g);
         if (ALIGNED && lane == 0) {
             const uint32_t bytes = (uint32_t)((d0.ld_hi - d0.ld_lo) * (int64_t)sizeof(T));
             mbar_expect_tx(&bars[0], 2 * bytes);
@@ -945,7 +947,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         NextChan nc{args.alpha, args.beta, -1, g.flags};
         ChanParams cp_next = cp;
         if (has_next) {
-            const TileDesc nxt = describe_tile<L>(nwt, lane, g);
+            const TileDesc nxt = describe_tile<L, HALF>(nwt, lane, g);
             nc.c = (int32_t)(nxt.row - g.chan.div(nxt.row) * g.chan.d);
             if (ALIGNED) {
                 pf.src0 = px + nxt.ld_lo;
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
                 pf.bytes = (uint32_t)((nxt.ld_hi - nxt.ld_lo) * (int64_t)sizeof(T));
             }
         }
-        const TileDesc cur = describe_tile<L>(wt, lane, g);
+        const TileDesc cur = describe_tile<L, HALF>(wt, lane, g);
         T* tile_x = stages + (size_t)st * 2 * WT::kStageElems;
         T* tile_g = tile_x + WT::kStageElems;
         const float a_eff = cp.a_eff, b_eff = cp.b_eff, ib = cp.ib;
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         const uint32_t amask = __ballot_sync(0xffffffffu, cur.active);
 
         if (ALIGNED) {
-            const bool half = g.half != 0;
+            constexpr bool half = HALF;   // compile-time: 16-byte-aligned launches pay nothing for the 8-byte path
             mbar_wait(&bars[st], (phase >> st) & 1u);
             phase ^= (1u << st);
             if (half) {
