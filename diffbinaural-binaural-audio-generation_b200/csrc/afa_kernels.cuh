@@ -328,7 +328,7 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
-    constexpr bool kStaticTail = (VEC == 4);   // last five steps straight-line (fp32 only, see below)
+    constexpr bool kStaticTail = (VEC == 4 && MODE == 0);   // last five steps straight-line (fp32 interior walk only, see below)
     T* seg = row0 + t0;
     // Both FIRs run in TRANSPOSED (scatter) form: a new input updates the six pending outputs it feeds, so
     // the 12 FFMA2 of a step are independent of each other (dependences only reach back >= 1 step).
@@ -453,8 +453,9 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
 
     // q = -4 .. S+5 static (warm-up + the outputs that wait in hold[]), q = S+6 .. L rolled (S steps per trip, ring
     // slots static inside the body), q = L+1 .. L+5 static again (dead work towards the next segment removed)
-    // (the static tail pays for fp32; for bf16 its 16-step ring makes the extra straight-line code cost more in
-    //  instruction-cache misses than the removed dead work saves -- measured, profiles/r01_ab_epilogue.log)
+    // (the static tail pays for the fp32 interior walk only; for bf16 (16-step ring) and for edge-mode warps the extra
+    //  straight-line code costs more in instruction-cache misses than the removed dead work saves -- measured,
+    //  profiles/r01_ab_epilogue.log)
     constexpr int NR = kStaticTail ? L - S - 5 : L - S, NF = NR / S, RM = NR % S;
     static_assert(NR >= 0, "segment shorter than the ring");
 #pragma unroll
@@ -503,7 +504,7 @@ __device__ __forceinline__ void walk_bwd(T* __restrict__ row0, const T* __restri
     constexpr int VEC = io::VEC;
     constexpr int L = CH * VEC;
     constexpr int S = RingCfg<VEC>::S;
-    constexpr bool kStaticTail = (VEC == 4);
+    constexpr bool kStaticTail = (VEC == 4 && MODE == 0);
     T* seg = row0 + t0;
     const T* gseg = grow0 + t0;
     // transposed-form FIRs, as in the forward: pending (u[2m-1], u[2m]), pending (ds[2m-1], ds[2m]),
