@@ -109,16 +109,9 @@ int default_chunks(int which, int dtype, int64_t elements, int64_t T) {
         return (wtiles13 >= 2 * 148 * 8 && T >= 32768) ? 13 : 5;
     }
     if (elements < (16ll << 20)) return 9;
-    if (dtype == AFA_DTYPE_F32) {
-        if (T < 8192) return 5;
-        if (T < 24576) return 9;
-        if (T < 49152) return 13;
-        return 17;
-    }
+    if (dtype == AFA_DTYPE_F32) return T < 8192 ? 13 : 17;
     if (T < 8192) return 9;
-    if (T < 49152) return 5;
-    if (T < 131072) return 13;
-    return 17;
+    return T < 131072 ? 13 : 17;
 }
 
 int make_plan(int which, const void* p0, const void* p1, const void* p2, int64_t batch, int64_t channels, int64_t T,
