@@ -106,7 +106,8 @@ int default_chunks(int which, int dtype, int64_t elements, int64_t T) {
     const int vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
     if (which == 1) {   // backward: two staged tensors -> fewer resident warps; long segments only pay on long rows
         const int64_t wtiles13 = elements / (32 * 13 * vec);
-        return (wtiles13 >= 2 * 148 * 8 && T >= 32768) ? 13 : 5;
+        if (wtiles13 >= 2 * 148 * 8 && T >= 32768) return 13;
+        return (dtype == AFA_DTYPE_F32 && T >= 8192 && elements >= (16ll << 20)) ? 9 : 5;
     }
     if (elements < (16ll << 20)) return 9;
     if (dtype == AFA_DTYPE_F32) return T < 8192 ? 13 : 17;

@@ -46,6 +46,14 @@ constexpr int kBarBytes = 64;  // mbarrier block at the start of dynamic shared 
 #ifndef AFA_BWD_MINB
 #define AFA_BWD_MINB 4
 #endif
+// Shared-memory stages per warp in the forward kernel: 2 = prefetch tile i+1 while walking tile i;
+// 1 = no intra-warp prefetch (half the shared memory per warp -> more resident warps hide the reload).
+#ifndef AFA_FWD_STAGES
+#define AFA_FWD_STAGES 2
+#endif
+#ifndef AFA_BWD_STAGES
+#define AFA_BWD_STAGES 2
+#endif
 
 // Filter taps as kernel parameters, pre-paired for packed f32x2 math (they become uniform-register
 // operands of FFMA2).  The 2x-rate signal is handled as pairs (s[2m-1], s[2m]): both members read the
@@ -766,8 +774,8 @@ struct WarpTile {
     static constexpr int L = CH * VEC;
     static constexpr int kStageElems = 32 * L + 2 * kHalo + 8;           // one tensor, one stage (+8: 16-byte rounding of half-aligned tiles)
     static constexpr size_t kStageBytes = sizeof(T) * (size_t)kStageElems;  // multiple of 16
-    static constexpr size_t fwd_smem(int nw) { return kBarBytes + (size_t)nw * 2 * kStageBytes; }
-    static constexpr size_t bwd_smem(int nw) { return kBarBytes + (size_t)nw * 2 * 2 * kStageBytes; }
+    static constexpr size_t fwd_smem(int nw) { return kBarBytes + (size_t)nw * AFA_FWD_STAGES * kStageBytes; }
+    static constexpr size_t bwd_smem(int nw) { return kBarBytes + (size_t)nw * AFA_BWD_STAGES * 2 * kStageBytes; }
 };
 
 // Bulk-store a finished tile.  16-byte-aligned rows: one bulk TMA store.  Half-aligned rows (bf16, T % 8 == 4):
@@ -811,7 +819,8 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * 2;
-    T* stages = reinterpret_cast<T*>(smem + kBarBytes) + (size_t)warp * 2 * WT::kStageElems;
+    constexpr int kStages = AFA_FWD_STAGES;
+    T* stages = reinterpret_cast<T*>(smem + kBarBytes) + (size_t)warp * kStages * WT::kStageElems;
     const Geometry& g = args.g;
     const T* gx = static_cast<const T*>(args.x);
     T* gy = static_cast<T*>(args.y);
@@ -851,11 +860,14 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
             nc.c = (int32_t)(nxt.row - g.chan.div(nxt.row) * g.chan.d);
             if (ALIGNED) {
                 pf.src0 = gx + nxt.ld_lo;
-                pf.dst0 = smem_u32(stages + (size_t)(st ^ 1) * WT::kStageElems);
-                pf.bar = smem_u32(&bars[st ^ 1]);
+                pf.dst0 = smem_u32(stages + (size_t)((st ^ 1) % kStages) * WT::kStageElems);
+                pf.bar = smem_u32(&bars[(st ^ 1) % kStages]);
                 pf.bytes = (uint32_t)((nxt.ld_hi - nxt.ld_lo) * (int64_t)sizeof(T));
             }
         }
+        // one stage: the refill of this same stage can only be issued after this tile's store has drained
+        Prefetch late = pf;
+        if (kStages == 1) pf.bytes = 0;
         const TileDesc cur = describe_tile<L, HALF>(wt, lane, g);
         T* tile = stages + (size_t)st * WT::kStageElems;
         const float a_eff = cp.a_eff, b_eff = cp.b_eff, ib = cp.ib;
@@ -879,6 +891,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
             fence_proxy_async_smem();
             __syncwarp();
             store_tile(gy, tile, cur, half, lane);
+            if (kStages == 1 && lane == 0) issue_prefetch(late);
         } else {
             const int n_in = (int)(cur.ld_hi - cur.ld_lo);
             for (int i = lane; i < n_in; i += 32) tile[i] = gx[cur.ld_lo + i];
@@ -893,7 +906,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? (sizeof(T) == 4 ? AFA_FWD_M
         if (!has_next) break;
         wt = nwt;
         cp = cp_next;
-        st ^= 1;
+        if (kStages == 2) st ^= 1;
     }
     if (ALIGNED && lane == 0) tma_store_wait_read();  // shared memory must outlive the last bulk store's reads
 }
@@ -910,7 +923,8 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * 2;
     // per warp: [stage 0: x | gy][stage 1: x | gy]
-    T* stages = reinterpret_cast<T*>(smem + kBarBytes) + (size_t)warp * 4 * WT::kStageElems;
+    constexpr int kStages = AFA_BWD_STAGES;
+    T* stages = reinterpret_cast<T*>(smem + kBarBytes) + (size_t)warp * kStages * 2 * WT::kStageElems;
     const Geometry& g = args.g;
     const T* px = static_cast<const T*>(args.x);
     const T* pg = static_cast<const T*>(args.gy);
@@ -953,12 +967,14 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
             if (ALIGNED) {
                 pf.src0 = px + nxt.ld_lo;
                 pf.src1 = pg + nxt.ld_lo;
-                pf.dst0 = smem_u32(stages + (size_t)(st ^ 1) * 2 * WT::kStageElems);
+                pf.dst0 = smem_u32(stages + (size_t)((st ^ 1) % kStages) * 2 * WT::kStageElems);
                 pf.dst1 = pf.dst0 + (uint32_t)WT::kStageBytes;
-                pf.bar = smem_u32(&bars[st ^ 1]);
+                pf.bar = smem_u32(&bars[(st ^ 1) % kStages]);
                 pf.bytes = (uint32_t)((nxt.ld_hi - nxt.ld_lo) * (int64_t)sizeof(T));
             }
         }
+        Prefetch late = pf;                      // one stage: refill only after this tile's store has drained
+        if (kStages == 1) pf.bytes = 0;
         const TileDesc cur = describe_tile<L, HALF>(wt, lane, g);
         T* tile_x = stages + (size_t)st * 2 * WT::kStageElems;
         T* tile_g = tile_x + WT::kStageElems;
@@ -986,6 +1002,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
             fence_proxy_async_smem();
             __syncwarp();
             store_tile(po, tile_x, cur, half, lane);
+            if (kStages == 1 && lane == 0) issue_prefetch(late);
         } else {
             const int n_in = (int)(cur.ld_hi - cur.ld_lo);
             for (int i = lane; i < n_in; i += 32) {
@@ -1012,7 +1029,7 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
         if (!has_next) break;
         wt = nwt;
         cp = cp_next;
-        st ^= 1;
+        if (kStages == 2) st ^= 1;
     }
     if (ALIGNED && lane == 0) tma_store_wait_read();
 }

@@ -9,7 +9,7 @@ from afa_b200.activations import SnakeBeta
 dev = torch.device("cuda:0")
 shapes = [(16, 768, 3444), (16, 192, 27552), (16, 24, 220416), (2, 96, 55104), (32, 96, 2048)]
 for dtype in (torch.float32, torch.bfloat16):
-    for ch in (5, 9, 13):
+    for ch in (5, 9, 13, 17):
         _lib.set_tuning(1, ch, 0)
         for (b, c, t) in shapes:
             m = Activation1d(activation=SnakeBeta(c, alpha_logscale=True)).to(dev)
