@@ -398,7 +398,8 @@ def run_gpu(args):
             traffic = tj[key]
     except Exception:
         pass
-    kinfo = _lib.kernel_info(0, 0 if args.dtype == "fp32" else 1, 4 * args.t_mel * 16)
+    kb, kc, kt = max((s["shape"] for s in wl.stages), key=lambda sh: sh[2])          # the long-row (dominant) variant
+    kinfo = _lib.kernel_info(0, 0 if args.dtype == "fp32" else 1, kt, kb, kc)
 
     # e2e through the module with host buffers
     e2e = None

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "afa_activation1d_bwd",
     "afa_set_tuning",
     "afa_kernel_info",
+    "afa_kernel_info_shape",
     "afa_launch_count",
 )
 
@@ -59,6 +60,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32
         lib.afa_kernel_info.argtypes = [i32, i32, i64, ctypes.POINTER(ctypes.c_int32)]
+        lib.afa_kernel_info_shape.restype = i32
+        lib.afa_kernel_info_shape.argtypes = [i32, i32, i64, i64, i64, ctypes.POINTER(ctypes.c_int32)]
         lib.afa_launch_count.restype = i64
         if path is None:
             _lib = lib
@@ -75,9 +78,10 @@ def launch_count() -> int:
     return int(load_library().afa_launch_count())
 
 
-def kernel_info(which: int, dtype_code: int, T: int) -> dict:
+def kernel_info(which: int, dtype_code: int, T: int, batch: int = 1, channels: int = 1) -> dict:
+    """Resource usage of the kernel variant a [batch, channels, T] launch selects."""
     out = (ctypes.c_int32 * 6)()
-    check(load_library().afa_kernel_info(which, dtype_code, T, out), "afa_kernel_info")
+    check(load_library().afa_kernel_info_shape(which, dtype_code, batch, channels, T, out), "afa_kernel_info_shape")
     keys = ("registers", "smem_bytes", "threads", "segment_elems", "ctas_per_sm", "launches")
     return dict(zip(keys, [int(v) for v in out]))
 

@@ -323,9 +323,13 @@ int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha,
 }
 
 int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]) {
+    return afa_kernel_info_shape(which, dtype, 1, 1, T, out);
+}
+
+int afa_kernel_info_shape(int which, int dtype, int64_t batch, int64_t channels, int64_t T, int32_t out[6]) {
     if (!out || which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "bad argument");
     Plan pl;
-    if (int rc = make_plan(which, nullptr, nullptr, nullptr, 1, 1, T, dtype, &pl)) return rc;
+    if (int rc = make_plan(which, nullptr, nullptr, nullptr, batch, channels, T, dtype, &pl)) return rc;
     const void* k = nullptr;
     size_t smem = 0;
 #define X(CH)                                                                                                 \

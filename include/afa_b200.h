@@ -92,6 +92,8 @@ int afa_activation1d_bwd(const void *x, const void *gy, void *gx,
  */
 int afa_set_tuning(int which, int chunks, int threads);
 int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]);
+/* Same, for the kernel variant a launch of shape [batch, channels, T] selects (segment length depends on size). */
+int afa_kernel_info_shape(int which, int dtype, int64_t batch, int64_t channels, int64_t T, int32_t out[6]);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t afa_launch_count(void);
 
