@@ -1,4 +1,4 @@
-"""Quick manual GPU probe (not a pytest file): parity + first timings. Usage: python tests/quick_gpu.py"""
+"""Quick manual GPU probe (not a pytest file): parity + first timings. Usage: python tools/quick_gpu.py"""
 import os
 import sys
 import time
