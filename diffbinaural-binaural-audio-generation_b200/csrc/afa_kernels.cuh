@@ -161,7 +161,6 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-
 // ------------------------------------------------------------------------------------------------
 // element I/O on shared memory
 // ------------------------------------------------------------------------------------------------
@@ -464,16 +463,20 @@ __device__ __forceinline__ void walk_fwd(T* __restrict__ row0, int t0, int Tlen,
     // (the static tail pays for the fp32 interior walk only; for bf16 (16-step ring) and for edge-mode warps the extra
     //  straight-line code costs more in instruction-cache misses than the removed dead work saves -- measured,
     //  profiles/r01_ab_epilogue.log)
-    constexpr int NR = kStaticTail ? L - S - 5 : L - S, NF = NR / S, RM = NR % S;
+#ifndef AFA_FWD_BODY_TRIPS
+#define AFA_FWD_BODY_TRIPS 1
+#endif
+    constexpr int BODY = S * ((VEC == 4 && MODE == 0) ? AFA_FWD_BODY_TRIPS : 1);   // steps per rolled-loop trip
+    constexpr int NR = kStaticTail ? L - S - 5 : L - S, NF = NR / BODY, RM = NR % BODY;
     static_assert(NR >= 0, "segment shorter than the ring");
 #pragma unroll
     for (int q = -4; q < 6 + S; ++q) step(q, q, true, false);
     mid_walk_hook(pf, nc, next, lane);
 #pragma unroll 1
     for (int it = 0; it < NF + (RM ? 1 : 0); ++it) {
-        const int qb = 6 + S + it * S;
+        const int qb = 6 + S + it * BODY;
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
+        for (int k = 0; k < BODY; ++k) {
             if (RM != 0 && k == RM) {
                 if (it == NF) break;
             }
