@@ -353,3 +353,22 @@ def test_no_out_of_bounds_writes(dtype):
             assert torch.isfinite(y.float()).all()
         gx, ga, gb = Fn.activation1d_backward_raw(x, gy, a, b, taps, taps, True)
         assert torch.isfinite(gx.float()).all() and torch.isfinite(ga).all() and torch.isfinite(gb).all()
+
+
+def test_backward_is_run_to_run_deterministic():
+    """Two-stage reduction, no atomics: the parameter gradients (and gx) are bit-identical across runs, which
+    DDP-averaged training (train_binaural_mel.py:540-543) can rely on."""
+    _, _, Fn, _, _ = _mods()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(9)
+    taps = Fn.host_taps(TP.make_taps())
+    for dtype in (torch.float32, torch.bfloat16):
+        for (B, C, T) in [(4, 24, 8192), (32, 96, 2048), (2, 768, 3444)]:
+            x = torch.randn(B, C, T, device=dev).to(dtype)
+            gy = torch.randn(B, C, T, device=dev).to(dtype)
+            a = torch.randn(C, device=dev) * 0.5
+            b = torch.randn(C, device=dev) * 0.5
+            first = Fn.activation1d_backward_raw(x, gy, a, b, taps, taps, True)
+            for _ in range(3):
+                again = Fn.activation1d_backward_raw(x, gy, a, b, taps, taps, True)
+                assert all(torch.equal(p, q) for p, q in zip(first, again))
