@@ -18,6 +18,9 @@ EXPORTED_SYMBOLS = (
     "afa_activation1d_fwd",
     "afa_bwd_workspace_bytes",
     "afa_activation1d_bwd",
+    "afa_amp_activation1d_fwd_cl",
+    "afa_resblock_mean",
+    "afa_tail_fwd_cl",
     "afa_set_tuning",
     "afa_kernel_info",
     "afa_kernel_info_shape",
@@ -56,6 +59,15 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_activation1d_bwd.restype = i32
         lib.afa_activation1d_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, fp, fp, i64, i64, i64, i32, i32, vp,
                                              ctypes.c_size_t, vp]
+        f32 = ctypes.c_float
+        lib.afa_amp_activation1d_fwd_cl.restype = i32
+        lib.afa_amp_activation1d_fwd_cl.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, vp, vp, fp, fp,
+                                                    i64, i64, i64, i32, i32, vp]
+        lib.afa_resblock_mean.restype = i32
+        lib.afa_resblock_mean.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i32, vp, f32, vp, i64, i64, i32, vp]
+        lib.afa_tail_fwd_cl.restype = i32
+        lib.afa_tail_fwd_cl.argtypes = [vp, i64, vp, vp, fp, fp, vp, vp, i32, vp, vp, i32, f32, i64, i64, i64,
+                                        i32, i32, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32

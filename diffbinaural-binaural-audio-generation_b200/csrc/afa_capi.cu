@@ -9,6 +9,7 @@
 
 #include "afa_b200.h"
 #include "afa_kernels.cuh"
+#include "afa_cl_kernels.cuh"
 
 #ifndef AFA_CHUNK_LIST
 #define AFA_CHUNK_LIST(X) X(5) X(9) X(13) X(17)
@@ -18,8 +19,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-int g_tune_chunks[2] = {0, 0};
-int g_tune_threads[2] = {0, 0};
+int g_tune_chunks[3] = {0, 0, 0};   // [2]: channels-last walk, segment length in units of 12 samples
+int g_tune_threads[3] = {0, 0, 0};
 
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 int fail(int code, const char* fmt, ...) {
@@ -247,7 +248,12 @@ const char* afa_last_error(void) { return g_err; }
 int64_t afa_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int afa_set_tuning(int which, int chunks, int threads) {
-    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd) or 1 (bwd)");
+    if (which == 2) {   // channels-last walk: segment length = 12 * chunks samples
+        if (chunks < 0 || chunks > 4096) return fail(AFA_ERR_BAD_ARG, "channels-last segment length must be 12 * [1, 4096]");
+        g_tune_chunks[2] = chunks;
+        return 0;
+    }
+    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd) or 2 (channels-last fwd)");
     bool ok = chunks == 0;
 #define X(CH) ok = ok || chunks == CH;
     AFA_CHUNK_LIST(X)
@@ -360,6 +366,155 @@ int afa_kernel_info_shape(int which, int dtype, int64_t batch, int64_t channels,
     out[4] = occ;
     out[5] = (int32_t)g_launches.load();
     return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// AMP-block entry points on channels-last activations (afa_cl_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Segment length of the channels-last walk: long segments amortise the 10 extra steps (halo warm-up and
+// drain) per segment; small launches want enough threads to fill 148 SMs a few times over.
+int cl_segment(int64_t batch, int64_t channels, int64_t T) {
+    if (g_tune_chunks[2]) return 12 * g_tune_chunks[2];
+    const int64_t want_threads = 148ll * 5 * afa::kClThreads * 3;
+    int L = 96;
+    while (L > 24 && batch * channels * ((T + L - 1) / L) < want_threads) L -= 24;
+    return L;
+}
+
+template <typename T>
+int launch_cl(const afa::ClArgs& a, bool res, cudaStream_t st) {
+    const uint32_t grid = (a.total + afa::kClThreads - 1) / afa::kClThreads;
+    if (res) afa::afa_cl_fwd_kernel<T, true><<<grid, afa::kClThreads, 0, st>>>(a);
+    else afa::afa_cl_fwd_kernel<T, false><<<grid, afa::kClThreads, 0, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_fwd_kernel launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int afa_amp_activation1d_fwd_cl(const void* x, int64_t x_bstride, const void* res, int64_t res_bstride,
+                                const float* bias, void* xsum, int64_t xsum_bstride, void* y, int64_t y_bstride,
+                                int64_t y_tpad, const float* alpha, const float* beta, const float* taps_up12,
+                                const float* taps_down12, int64_t batch, int64_t channels, int64_t T, int dtype,
+                                int flags, void* stream) {
+    if (!x || !y || !alpha || !taps_up12 || !taps_down12) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
+    if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
+    if (dtype != AFA_DTYPE_F32 && dtype != AFA_DTYPE_BF16) return fail(AFA_ERR_BAD_DTYPE, "dtype %d is not AFA_DTYPE_F32/BF16", dtype);
+    if (batch < 0 || channels <= 0 || T < 0) return fail(AFA_ERR_BAD_ARG, "bad shape batch=%lld channels=%lld T=%lld", (long long)batch, (long long)channels, (long long)T);
+    if (xsum && !res) return fail(AFA_ERR_BAD_ARG, "xsum is only produced together with res");
+    if (y == x || y == res || (xsum && (xsum == x || xsum == y || xsum == res)))
+        return fail(AFA_ERR_BAD_ARG, "outputs must not alias inputs or each other (segments re-read their neighbours' halo)");
+    if (y_tpad == 0) y_tpad = T;
+    const int64_t row = T * channels, yrow = y_tpad * channels;
+    if (y_tpad < T || x_bstride < row || (res && res_bstride < row) || (xsum && xsum_bstride < row) || y_bstride < yrow)
+        return fail(AFA_ERR_BAD_ARG, "batch strides must cover T*channels elements (y: y_tpad*channels)");
+    if (yrow >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "T*channels=%lld exceeds 2^31", (long long)yrow);
+    const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
+    if (((uintptr_t)x | (uintptr_t)res | (uintptr_t)xsum | (uintptr_t)y) & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
+    if (batch == 0 || T == 0) return 0;
+    const int L = cl_segment(batch, channels, T);
+    const int64_t nseg = (T + L - 1) / L;
+    const int64_t total = batch * nseg * channels;
+    if (total >= (1ll << 31) - afa::kClThreads) return fail(AFA_ERR_TOO_LARGE, "batch*channels*ceil(T/%d)=%lld exceeds 2^31", L, (long long)total);
+    afa::ClArgs a;
+    a.x = x; a.res = res; a.xsum = xsum; a.y = y;
+    a.bias = bias; a.alpha = alpha; a.beta = beta;
+    fold_fwd_taps(taps_up12, taps_down12, &a.taps);
+    a.x_bs = x_bstride; a.res_bs = res_bstride; a.xsum_bs = xsum_bstride; a.y_bs = y_bstride;
+    a.total = (uint32_t)total;
+    a.chan = make_fastdiv((uint32_t)channels);
+    a.nseg = make_fastdiv((uint32_t)nseg);
+    a.T = (int32_t)T; a.L = L; a.y_tpad = (int32_t)y_tpad; a.flags = flags;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == AFA_DTYPE_F32 ? launch_cl<float>(a, res != nullptr, st) : launch_cl<__nv_bfloat16>(a, res != nullptr, st);
+}
+
+int afa_tail_fwd_cl(const void* x, int64_t x_bstride, const float* alpha, const float* beta, const float* taps_up12,
+                    const float* taps_down12, const float* w_post, const float* bias_post, int use_tanh, float* wave,
+                    int16_t* pcm, int pcm_interleave, float pcm_scale, int64_t batch, int64_t channels, int64_t T,
+                    int dtype, int flags, void* stream) {
+    if (!x || !alpha || !taps_up12 || !taps_down12 || !w_post) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
+    if (!wave && !pcm) return fail(AFA_ERR_BAD_ARG, "at least one of wave / pcm is required");
+    if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
+    if (dtype != AFA_DTYPE_F32 && dtype != AFA_DTYPE_BF16) return fail(AFA_ERR_BAD_DTYPE, "dtype %d is not AFA_DTYPE_F32/BF16", dtype);
+    if (batch < 0 || channels <= 0 || T < 0) return fail(AFA_ERR_BAD_ARG, "bad shape batch=%lld channels=%lld T=%lld", (long long)batch, (long long)channels, (long long)T);
+    if (channels > 32) return fail(AFA_ERR_BAD_ARG, "the tail kernel maps channels to the lanes of a warp: channels=%lld > 32", (long long)channels);
+    if (pcm && (pcm_interleave < 1 || batch % pcm_interleave)) return fail(AFA_ERR_BAD_ARG, "batch=%lld is not a multiple of pcm_interleave=%d", (long long)batch, pcm_interleave);
+    if (x_bstride < T * channels) return fail(AFA_ERR_BAD_ARG, "batch stride must cover T*channels elements");
+    if (T * channels >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "T*channels exceeds 2^31");
+    if (batch == 0 || T == 0) return 0;
+    const int L = 96;                                  // walk length; 90 outputs per segment
+    const int64_t nseg = (T + (L - 6) - 1) / (L - 6);
+    const int64_t warps = batch * nseg;
+    if (warps >= (1ll << 31) / 32) return fail(AFA_ERR_TOO_LARGE, "too many segments");
+    afa::TailArgs a;
+    a.x = x; a.alpha = alpha; a.beta = beta; a.w = w_post; a.bias = bias_post; a.wave = wave; a.pcm = pcm;
+    fold_fwd_taps(taps_up12, taps_down12, &a.taps);
+    a.x_bs = x_bstride;
+    a.total_warps = (uint32_t)warps;
+    a.nseg = make_fastdiv((uint32_t)nseg);
+    a.T = (int32_t)T; a.C = (int32_t)channels; a.L = L; a.flags = flags; a.use_tanh = use_tanh;
+    a.il = pcm ? pcm_interleave : 1;
+    a.pcm_scale = pcm_scale;
+    const uint32_t wpb = afa::kClThreads / 32;
+    const uint32_t grid = (uint32_t)((warps + wpb - 1) / wpb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AFA_DTYPE_F32) afa::afa_cl_tail_kernel<float><<<grid, afa::kClThreads, 0, st>>>(a);
+    else afa::afa_cl_tail_kernel<__nv_bfloat16><<<grid, afa::kClThreads, 0, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_tail_kernel launch");
+}
+
+int afa_resblock_mean(const void* const* xt, const void* const* xres, int num_kernels, const float* bias_sum,
+                      float scale, void* out, int64_t rows, int64_t channels, int dtype, void* stream) {
+    if (!xt || !xres || !out) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
+    if (num_kernels < 1 || num_kernels > afa::kMeanMaxK) return fail(AFA_ERR_BAD_ARG, "num_kernels must be in [1, %d]", afa::kMeanMaxK);
+    if (dtype != AFA_DTYPE_F32 && dtype != AFA_DTYPE_BF16) return fail(AFA_ERR_BAD_DTYPE, "dtype %d is not AFA_DTYPE_F32/BF16", dtype);
+    if (rows < 0 || channels <= 0) return fail(AFA_ERR_BAD_ARG, "bad shape rows=%lld channels=%lld", (long long)rows, (long long)channels);
+    const int64_t n = rows * channels;
+    if (n >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "rows*channels=%lld exceeds 2^31", (long long)n);
+    if (n == 0) return 0;
+    const int vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
+    uintptr_t ptr_or = (uintptr_t)out;
+    afa::MeanArgs a;
+    for (int j = 0; j < afa::kMeanMaxK; ++j) { a.y[j] = nullptr; a.r[j] = nullptr; }
+    for (int j = 0; j < num_kernels; ++j) {
+        if (!xt[j] || !xres[j]) return fail(AFA_ERR_BAD_ARG, "null tensor pointer at index %d", j);
+        a.y[j] = xt[j];
+        a.r[j] = xres[j];
+        ptr_or |= (uintptr_t)xt[j] | (uintptr_t)xres[j];
+    }
+    const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
+    if (ptr_or & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
+    const bool vector = (channels % vec == 0) && ((ptr_or & 15) == 0);
+    a.bias_sum = bias_sum;
+    a.out = out;
+    a.n = n;
+    a.cvec = make_fastdiv((uint32_t)(vector ? channels / vec : channels));
+    a.K = num_kernels;
+    a.scale = scale;
+    const int64_t nv = vector ? n / vec : n;
+    const uint32_t grid = (uint32_t)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AFA_DTYPE_F32) {
+        if (vector) afa::afa_mean_kernel<float, 4><<<grid, 256, 0, st>>>(a);
+        else afa::afa_mean_kernel<float, 1><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (vector) afa::afa_mean_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(a);
+        else afa::afa_mean_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(a);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "afa_mean_kernel launch");
 }
 
 }  // extern "C"

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 100            /* 0.1.0 */
+#define AFA_VERSION 110            /* 0.1.1: + AMP-block entry points on channels-last activations */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
@@ -83,10 +83,68 @@ int afa_activation1d_bwd(const void *x, const void *gy, void *gx,
                          int dtype, int flags,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * AMP-block entry points on CHANNELS-LAST activations: dense [batch, T, channels] arrays, channels
+ * contiguous, with a per-tensor batch stride in elements (>= T*channels; rows may be padded in time).
+ * They are what an inference engine needs to keep the generator channels-last between cuDNN's NHWC
+ * tensor-core convolutions (no layout conversion kernels) and to drop the separate bias / residual /
+ * mean kernels of the reference's AMPBlock.  Forward only.
+ *
+ *   afa_amp_activation1d_fwd_cl  <->  `xt = c(xt)` bias add + `x = xt + x` + the next `a(x)`
+ *                                      BigVGAN/bigvgan.py:132-141 (AMPBlock1.forward), :233-236 (AMPBlock2)
+ *   afa_resblock_mean            <->  `xs += resblocks[...](x)` ... `x = xs / self.num_kernels`
+ *                                      BigVGAN/bigvgan.py:368-376
+ *   afa_tail_fwd_cl              <->  activation_post -> conv_post -> clamp | tanh   BigVGAN/bigvgan.py:379-385
+ *                                      (+ `* MAX_WAV_VALUE`, astype("int16"), stereo interleave
+ *                                       BigVGAN/inference_e2e.py:193-201)
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * x' = x + bias[c] + res ;  xsum = x' (optional, needs res) ;  y = down2x(snake(up2x(x'))).
+ * bias: float32 [channels] device or NULL; res / xsum: NULL or arrays shaped like x.  y_tpad >= T (0 = T):
+ * rows [T, y_tpad) of every batch entry of y are written as zeros (the zero padding a dilated convolution
+ * run as a (k x 1) convolution over the [y_tpad/d, d] polyphase view reads).  Outputs must not alias inputs.
+ */
+int afa_amp_activation1d_fwd_cl(const void *x, int64_t x_bstride,
+                                const void *res, int64_t res_bstride,
+                                const float *bias,
+                                void *xsum, int64_t xsum_bstride,
+                                void *y, int64_t y_bstride, int64_t y_tpad,
+                                const float *alpha, const float *beta,
+                                const float *taps_up12, const float *taps_down12,
+                                int64_t batch, int64_t channels, int64_t T,
+                                int dtype, int flags, void *stream);
+
+/*
+ * out = scale * (sum_{j < num_kernels} (xt[j] + xres[j]) + bias_sum[c]) over dense [rows, channels] arrays
+ * (rows = batch*T).  xt[j]: output of the last convolution of resblock j WITHOUT its bias; xres[j]: that
+ * resblock's residual stream; bias_sum: float32 [channels] = sum of those biases (or NULL); scale = 1/num_kernels.
+ * xt / xres are HOST arrays of device pointers.
+ */
+int afa_resblock_mean(const void *const *xt, const void *const *xres, int num_kernels,
+                      const float *bias_sum, float scale, void *out,
+                      int64_t rows, int64_t channels, int dtype, void *stream);
+
+/*
+ * wave[b][t] = final(conv_post(activation_post(x)))  with conv_post: channels -> 1, kernel 7, zero padding 3,
+ * weight w_post float32 [channels][7] (device), optional bias_post (1 float, device), final = clamp(-1, 1)
+ * (use_tanh = 0) or tanh.  channels <= 32.  Outputs (at least one): wave float32 [batch][T]; pcm int16 with
+ * element (b, t) at ((b / pcm_interleave) * T + t) * pcm_interleave + b % pcm_interleave, value
+ * (int16)(wave * pcm_scale) truncated toward zero like numpy's astype("int16") (pcm_scale = 32767).
+ */
+int afa_tail_fwd_cl(const void *x, int64_t x_bstride,
+                    const float *alpha, const float *beta,
+                    const float *taps_up12, const float *taps_down12,
+                    const float *w_post, const float *bias_post, int use_tanh,
+                    float *wave, int16_t *pcm, int pcm_interleave, float pcm_scale,
+                    int64_t batch, int64_t channels, int64_t T,
+                    int dtype, int flags, void *stream);
+
 /*
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).
  * afa_set_tuning: which=0 forward, 1 backward; chunks = 16-byte chunks per thread segment
  * (odd, one of the compiled values), threads = CTA size.  0 keeps the built-in choice.
+ * which=2: channels-last forward, segment length = 12 * chunks samples.
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
  * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects.
  */

@@ -1,0 +1,342 @@
+"""GPU parity of the channels-last AMP-block kernels (through the C ABI) against the oracle and the vectors the
+unmodified reference produced (tests/golden/amp_golden.npz).
+
+Tolerances, E = max|y - ref| / max|ref|: fp32 <= 1e-5; bf16 I/O (fp32 math) <= 1e-2;
+int16 PCM: |diff| <= 1 LSB and >= 99 % of the samples exact (the reference truncates a float that our fp32
+result reproduces to ~1e-7 relative, so a value within that distance of an integer may truncate differently).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import afa_oracle as O
+from oracle import amp_oracle as A
+from oracle import torch_path as TP
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-2
+DEV = "cuda:0"
+
+
+def _fc():
+    from afa_b200 import functional as F_afa
+    from afa_b200 import functional_cl as FC
+
+    return F_afa, FC
+
+
+@pytest.fixture(scope="module")
+def amp_golden():
+    g = dict(np.load(os.path.join(REPO, "tests", "golden", "amp_golden.npz")))
+    cases = {}
+    for k, v in g.items():
+        name, rest = k.split("/", 1)
+        c = cases.setdefault(name, {"sd": {}})
+        if rest.startswith("sd/"):
+            c["sd"][rest[3:]] = v
+        else:
+            c[rest] = v
+    return cases
+
+
+@pytest.fixture
+def true_fp32_convs():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _taps():
+    F_afa, _ = _fc()
+    t = TP.make_taps()
+    h = F_afa.host_taps(t)
+    return t, (h, h), t.reshape(-1).double().numpy()
+
+
+def _padded(x: torch.Tensor, rows: int, fill=float("nan")) -> torch.Tensor:
+    """[B, T, C] -> a [B, T, C] view into a [B, rows, C] buffer (batch stride rows*C), padding poisoned."""
+    B, T, C = x.shape
+    buf = torch.full((B, rows, C), fill, dtype=x.dtype, device=x.device)
+    buf[:, :T] = x
+    return buf[:, :T]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cl_activation_grid(dtype):
+    """Edge grid: T around the segment / ring boundaries, odd channel counts, Snake / SnakeBeta, log-scale on/off,
+    with and without bias / residual / xsum, padded batch strides, zero-filled tail rows."""
+    _, FC = _fc()
+    t32, taps, taps64 = _taps()
+    rng = np.random.default_rng(5)
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    Ts = [1, 2, 3, 5, 6, 11, 12, 13, 23, 24, 25, 29, 47, 48, 49, 95, 96, 97, 101, 191, 192, 193, 300, 1000]
+    Cs = [1, 3, 8, 24, 32, 33, 48]
+    n = 0
+    for T in Ts:
+        for C in Cs:
+            if (T * C) % 3 == 1 and T > 100:
+                continue
+            B = 1 + (n % 3)
+            kind = ("snakebeta", "snake")[n % 2]
+            logscale = (n % 4) < 3
+            with_bias, with_res = (n % 3) != 0, (n % 5) in (1, 2, 3)
+            with_xsum = with_res and (n % 5) != 3
+            n += 1
+            x = torch.tensor(rng.standard_normal((B, T, C)), dtype=dtype, device=DEV)
+            res = torch.tensor(rng.standard_normal((B, T, C)), dtype=dtype, device=DEV) if with_res else None
+            bias = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV) if with_bias else None
+            if logscale:
+                alpha = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+                beta = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+            else:
+                alpha = torch.tensor(rng.random(C) * 2 + 0.25, dtype=torch.float32, device=DEV)
+                beta = torch.tensor(rng.random(C) * 2 + 0.25, dtype=torch.float32, device=DEV)
+            if kind == "snake":
+                beta = None
+            tpad = T + (n % 4) * 2
+            xin = _padded(x, T + 3) if n % 2 else x
+            rin = _padded(res, T + 1) if (with_res and n % 3 == 0) else res
+            out = torch.full((B, tpad + 2, C), 7.0, dtype=dtype, device=DEV)
+            xsum = torch.full((B, T, C), 9.0, dtype=dtype, device=DEV) if with_xsum else None
+            y = FC.amp_activation1d_cl(xin, T, alpha, beta, taps[0], taps[1], logscale, bias=bias, res=rin, xsum=xsum,
+                                       out=out, out_tpad=tpad)
+            torch.cuda.synchronize()
+            xs_ref, y_ref = A.amp_activation1d_cl(
+                x.double().cpu().numpy(), alpha.double().cpu().numpy(), None if beta is None else beta.double().cpu().numpy(),
+                logscale, None if bias is None else bias.double().cpu().numpy(), None if res is None else res.double().cpu().numpy(),
+                taps64, taps64)
+            tag = f"T={T} C={C} B={B} {kind} log={logscale} bias={with_bias} res={with_res} xsum={with_xsum}"
+            got = y[:, :T].double().cpu().numpy()
+            assert O.max_normalised_error(got, y_ref) <= tol, (tag, O.max_normalised_error(got, y_ref))
+            if tpad > T:
+                assert torch.all(out[:, T:tpad] == 0), tag             # zero padding for the polyphase convolution
+            assert torch.all(out[:, tpad:] == 7.0), tag                # nothing written beyond it
+            if with_xsum:
+                assert O.max_normalised_error(xsum.double().cpu().numpy(), xs_ref) <= (1e-6 if dtype == torch.float32 else 4e-3), tag
+
+
+def test_cl_activation_matches_reference_golden(golden_cases):
+    """The reference's own Activation1d outputs (tests/golden/activation1d_golden.npz), fed channels-last."""
+    _, FC = _fc()
+    for name, c in golden_cases.items():
+        B, C, T, is_beta, logscale = [int(v) for v in c["meta"]]
+        F_afa, _ = _fc()
+        h = F_afa.host_taps(TP.make_taps())
+        taps = (h, h)
+        x = torch.tensor(c["x"], device=DEV).transpose(1, 2).contiguous()
+        alpha = torch.tensor(c["alpha"], device=DEV)
+        beta = torch.tensor(c["beta"], device=DEV) if is_beta else None
+        y = FC.amp_activation1d_cl(x, T, alpha, beta, taps[0], taps[1], bool(logscale))
+        got = y.transpose(1, 2).double().cpu().numpy()
+        assert O.max_normalised_error(got, c["y_f64"]) <= TOL_F32, name
+        assert O.max_normalised_error(got, c["y_f32"]) <= TOL_F32, name
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cl_activation_full_size_vs_torch_oracle(dtype):
+    """BASELINE shapes (8 clips: B=16) against the torch-op oracle on the device; segment-length invariance (bitwise)."""
+    from afa_b200 import _lib
+
+    _, FC = _fc()
+    t32, taps, _ = _taps()
+    torch.manual_seed(3)
+    for C, T in ((768, 3444), (96, 55104), (24, 220416)):
+        B = 16 if dtype == torch.bfloat16 else 4
+        x = torch.randn(B, T, C, device=DEV, dtype=dtype)
+        res = torch.randn(B, T, C, device=DEV, dtype=dtype)
+        bias = torch.randn(C, device=DEV) * 0.3
+        alpha = torch.randn(C, device=DEV) * 0.5
+        beta = torch.randn(C, device=DEV) * 0.5
+        xsum = torch.empty_like(x)
+        y = FC.amp_activation1d_cl(x, T, alpha, beta, taps[0], taps[1], True, bias=bias, res=res, xsum=xsum)
+        xs = x.float() + bias + res.float()
+        ref = TP.activation1d_torch(xs.transpose(1, 2).contiguous(), alpha, beta, True, t32.to(DEV), t32.to(DEV)).transpose(1, 2)
+        scale = ref.abs().max().item()
+        tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+        assert (y.float() - ref).abs().max().item() / scale <= tol, (C, T)
+        assert (xsum.float() - xs).abs().max().item() / xs.abs().max().item() <= (1e-6 if dtype == torch.float32 else 4e-3)
+        # plain variant (bias folded into the pending pairs), and bitwise invariance against the segment length
+        y0 = FC.amp_activation1d_cl(x, T, alpha, beta, taps[0], taps[1], True, bias=bias)
+        ref0 = TP.activation1d_torch((x.float() + bias).transpose(1, 2).contiguous(), alpha, beta, True, t32.to(DEV), t32.to(DEV)).transpose(1, 2)
+        assert (y0.float() - ref0).abs().max().item() / ref0.abs().max().item() <= tol, (C, T)
+        try:
+            _lib.set_tuning(2, 2)
+            y1 = FC.amp_activation1d_cl(x, T, alpha, beta, taps[0], taps[1], True, bias=bias)
+            _lib.set_tuning(2, 11)
+            y2 = FC.amp_activation1d_cl(x, T, alpha, beta, taps[0], taps[1], True, bias=bias)
+        finally:
+            _lib.set_tuning(2, 0)
+        assert torch.equal(y0, y1) and torch.equal(y0, y2), (C, T)
+        del x, res, xsum, y, ref, xs, y0, y1, y2, ref0
+        torch.cuda.empty_cache()
+
+
+def test_resblock_mean():
+    _, FC = _fc()
+    rng = np.random.default_rng(9)
+    for dtype, tol in ((torch.float32, 1e-6), (torch.bfloat16, 4e-3)):
+        for (B, T, C, K) in ((2, 37, 24, 3), (1, 5, 7, 3), (3, 16, 48, 1), (2, 33, 8, 4), (1, 1, 1, 2)):
+            xts = [torch.tensor(rng.standard_normal((B, T, C)), dtype=dtype, device=DEV) for _ in range(K)]
+            xrs = [torch.tensor(rng.standard_normal((B, T, C)), dtype=dtype, device=DEV) for _ in range(K)]
+            bs = torch.tensor(rng.standard_normal(C), dtype=torch.float32, device=DEV)
+            out = FC.resblock_mean(xts, xrs, bs)
+            ref = A.resblock_mean([t.double().cpu().numpy() for t in xts], [t.double().cpu().numpy() for t in xrs], bs.double().cpu().numpy())
+            assert O.max_normalised_error(out.double().cpu().numpy(), ref) <= tol, (dtype, B, T, C, K)
+            out2 = FC.resblock_mean(xts, xrs, None, 0.5)
+            ref2 = A.resblock_mean([t.double().cpu().numpy() for t in xts], [t.double().cpu().numpy() for t in xrs], None, 0.5)
+            assert O.max_normalised_error(out2.double().cpu().numpy(), ref2) <= tol
+
+
+def _tail_from_golden(c, dtype):
+    F_afa, FC = _fc()
+    B, C, T, use_tanh, has_bias = [int(v) for v in c["meta"]]
+    sd = c["sd"]
+    up = F_afa.host_taps(torch.tensor(sd["activation_post.upsample.filter"]))
+    dn = F_afa.host_taps(torch.tensor(sd["activation_post.downsample.lowpass.filter"]))
+    x = torch.tensor(c["x"], device=DEV).transpose(1, 2).contiguous().to(dtype)
+    alpha = torch.tensor(sd["activation_post.act.alpha"], device=DEV)
+    beta = torch.tensor(sd["activation_post.act.beta"], device=DEV)
+    w = torch.tensor(sd["conv_post.weight"], device=DEV).reshape(C, 7).contiguous()
+    b = torch.tensor(sd["conv_post.bias"], device=DEV) if has_bias else None
+    return FC.tail_cl(x, T, alpha, beta, up, dn, True, w, b, use_tanh=bool(use_tanh), want_wave=True, want_pcm=True)
+
+
+def test_tail_matches_reference_golden(amp_golden):
+    """activation_post -> conv_post -> clamp | tanh -> int16 stereo, against the reference's own outputs."""
+    for name in ("tail_clamp", "tail_tanh_bias"):
+        c = amp_golden[name]
+        wave, pcm = _tail_from_golden(c, torch.float32)
+        got = wave.double().cpu().numpy()
+        assert O.max_normalised_error(got, c["wave_f64"][:, 0, :]) <= TOL_F32, name
+        assert O.max_normalised_error(got, c["wave_f32"][:, 0, :]) <= TOL_F32, name
+        p = pcm.cpu().numpy()
+        assert p.shape == (1,) + c["pcm_i16"].shape and p.dtype == np.int16
+        diff = np.abs(p[0].astype(np.int32) - c["pcm_i16"].astype(np.int32))
+        assert diff.max() <= 1 and (diff == 0).mean() >= 0.99, (name, diff.max(), (diff == 0).mean())
+        # the PCM is exactly the truncation of the float wave the same launch wrote
+        assert np.array_equal(p, A.pcm_interleave(wave.cpu().numpy(), 2)), name
+        wave_b, _ = _tail_from_golden(c, torch.bfloat16)
+        assert O.max_normalised_error(wave_b.double().cpu().numpy(), c["wave_f64"][:, 0, :]) <= TOL_BF16, name
+
+
+def test_tail_edge_grid():
+    _, FC = _fc()
+    t32, taps, taps64 = _taps()
+    rng = np.random.default_rng(21)
+    for T in (1, 2, 3, 4, 7, 89, 90, 91, 93, 94, 180, 181, 500):
+        for C in (1, 8, 24, 32):
+            B = 2
+            x = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.float32, device=DEV)
+            alpha = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+            beta = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+            w = torch.tensor(rng.standard_normal((C, 7)) * 0.5 / np.sqrt(7 * C), dtype=torch.float32, device=DEV)
+            wave, pcm = FC.tail_cl(x, T, alpha, beta, taps[0], taps[1], True, w, None, use_tanh=False, want_pcm=True)
+            ref = A.tail_cl(x.double().cpu().numpy(), alpha.double().cpu().numpy(), beta.double().cpu().numpy(), True,
+                            w.double().cpu().numpy(), None, False, taps64, taps64)
+            err = np.abs(wave.double().cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-3)
+            assert err <= TOL_F32, (T, C, err)
+            assert np.array_equal(pcm.cpu().numpy(), A.pcm_interleave(wave.cpu().numpy(), 2)), (T, C)
+
+
+def _engine_from_sd(sd, h, dtype):
+    from afa_b200.engine import ChannelsLastVocoder
+    from afa_b200.vocoder import BINAURAL_22KHZ_80BAND_256X, BigVGANGenerator
+
+    hh = dict(BINAURAL_22KHZ_80BAND_256X)
+    hh.update(h)
+    gen = BigVGANGenerator(hh)
+    gen.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    gen = gen.to(DEV).eval()
+    return gen, ChannelsLastVocoder(gen.to(dtype) if dtype != torch.float32 else gen, dtype=dtype)
+
+
+def test_engine_matches_reference_generator_golden(amp_golden, true_fp32_convs):
+    """Whole (small) generator pass of the channels-last engine against the reference's own output."""
+    for name in ("gen_small_1", "gen_small_2"):
+        c = amp_golden[name]
+        rb = str(int(c["meta"][0]))
+        h = dict(upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=16, resblock=rb,
+                 resblock_dilation_sizes=[[1, 3, 5]] * 3 if rb == "1" else [[1, 3]] * 3)
+        gen, eng = _engine_from_sd(c["sd"], h, torch.float32)
+        mel = torch.tensor(c["mel"], device=DEV)
+        wave, pcm = eng(mel, want_pcm=True)
+        got = wave.double().cpu().numpy()
+        assert got.shape == c["y_f64"].shape
+        e64 = O.max_normalised_error(got, c["y_f64"])
+        assert e64 <= 2e-5, (name, e64)                      # fp32 convolutions of cuDNN in between: a few 1e-6
+        ref_pcm = A.pcm_stereo(c["y_f32"][:, 0, :])
+        diff = np.abs(pcm.cpu().numpy()[0].astype(np.int32) - ref_pcm.astype(np.int32))
+        assert diff.max() <= 1 and (diff == 0).mean() >= 0.95, (name, diff.max(), (diff == 0).mean())
+        # and the [B, C, T] harness around the same weights agrees
+        with torch.no_grad():
+            y_h = gen(mel)
+        assert (y_h - wave).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("resblock,activation", [("1", "snakebeta"), ("2", "snake")])
+def test_engine_vs_ncw_harness_model_config(resblock, activation, true_fp32_convs):
+    """The shipped config's channel plan (1536 -> 24 over six stages): fp32 engine == fp32 [B, C, T] harness; bf16 close;
+    CUDA-graph replay reproduces the eager result bit for bit."""
+    from afa_b200.engine import ChannelsLastVocoder, GraphedEngine
+    from afa_b200.vocoder import BINAURAL_22KHZ_80BAND_256X, BigVGANGenerator
+
+    h = dict(BINAURAL_22KHZ_80BAND_256X)
+    h.update(upsample_initial_channel=192, resblock=resblock, activation=activation)
+    torch.manual_seed(1234)
+    gen = BigVGANGenerator(h).to(DEV).eval()
+    with torch.no_grad():
+        for n, p in gen.named_parameters():
+            if n.endswith("alpha") or n.endswith("beta"):
+                p.normal_(0, 0.5)
+            elif n.endswith("weight"):
+                p.mul_(6.0)
+            elif n.endswith("bias"):
+                p.normal_(0, 0.1)
+    mel = torch.rand(2, 80, 23, device=DEV) * 14.5 - 12.0
+    eng = ChannelsLastVocoder(gen, dtype=torch.float32)
+    with torch.no_grad():
+        y_ref = gen(mel)
+    wave, _ = eng(mel)
+    scale = max(y_ref.abs().max().item(), 1e-6)
+    assert wave.shape == y_ref.shape == (2, 1, 23 * 256)
+    err = (wave - y_ref).abs().max().item() / scale
+    assert err <= 2e-4, err
+    ge = GraphedEngine(eng, 2, 23, want_pcm=True)
+    w_g, p_g = ge(mel)
+    assert torch.equal(w_g, wave)
+    eng_b = ChannelsLastVocoder(gen, dtype=torch.bfloat16)
+    w_b, _ = eng_b(mel)
+    # bf16 through ~110 layers with 6x-amplified weights: judge by the relative L2 error, bound the worst sample loosely
+    assert ((w_b - y_ref).norm() / y_ref.norm()).item() <= 0.05
+    assert (w_b - y_ref).abs().max().item() / scale <= 0.3
+
+
+def test_cl_error_codes():
+    from afa_b200 import _lib
+
+    _, FC = _fc()
+    t32, taps, _ = _taps()
+    x = torch.randn(2, 50, 8, device=DEV)
+    a = torch.zeros(8, device=DEV)
+    with pytest.raises(_lib.AfaError, match="alias"):
+        FC.amp_activation1d_cl(x, 50, a, a, taps[0], taps[1], True, out=x)
+    with pytest.raises(RuntimeError, match="xsum"):
+        FC.amp_activation1d_cl(x, 50, a, a, taps[0], taps[1], True, xsum=torch.empty_like(x))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        FC.amp_activation1d_cl(x.transpose(1, 2), 8, a, a, taps[0], taps[1], True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FC.amp_activation1d_cl(x.cpu(), 50, a, a, taps[0], taps[1], True)
+    x40 = torch.randn(2, 50, 40, device=DEV)
+    a40 = torch.zeros(40, device=DEV)
+    with pytest.raises(_lib.AfaError, match="32"):
+        FC.tail_cl(x40, 50, a40, a40, taps[0], taps[1], True, torch.zeros(40, 7, device=DEV))
+    # empty inputs are legal no-ops
+    y = FC.amp_activation1d_cl(torch.empty(0, 5, 8, device=DEV), 5, a, a, taps[0], taps[1], True)
+    assert y.shape == (0, 5, 8)

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(EXPORTED_SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.afa_version() == 100
+    assert lib.afa_version() == 110
 
 
 def test_argument_errors_need_no_gpu(lib):
@@ -51,8 +51,25 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.afa_activation1d_fwd(vp(16), vp(32), vp(64), vp(64), taps, taps, -1, 1, 8, 0, 0, None) == -1
     assert lib.afa_activation1d_fwd(vp(18), vp(32), vp(64), vp(64), taps, taps, 1, 1, 8, 0, 0, None) == -5  # 2-byte aligned fp32
     assert lib.afa_activation1d_fwd(vp(16), vp(32), vp(64), vp(64), taps, taps, 1 << 20, 1 << 12, 1 << 20, 0, 0, None) == -3
-    assert lib.afa_set_tuning(0, 4, 0) == -1 and lib.afa_set_tuning(2, 0, 0) == -1
+    assert lib.afa_set_tuning(0, 4, 0) == -1 and lib.afa_set_tuning(3, 0, 0) == -1
     assert lib.afa_set_tuning(0, 9, 0) == 0 and lib.afa_set_tuning(0, 0, 0) == 0
+    assert lib.afa_set_tuning(2, 4, 0) == 0 and lib.afa_set_tuning(2, 0, 0) == 0 and lib.afa_set_tuning(2, -1, 0) == -1
+    # channels-last AMP entry points: argument checks come before any CUDA call
+    i64 = ctypes.c_int64
+    cl = lib.afa_amp_activation1d_fwd_cl
+    assert cl(None, 0, None, 0, None, None, 0, None, 0, 0, None, None, taps, taps, 1, 4, 8, 0, 0, None) == -1
+    assert cl(vp(16), 32, None, 0, None, vp(48), 32, vp(32), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1   # xsum without res
+    assert cl(vp(16), 32, None, 0, None, None, 0, vp(16), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1    # y aliases x
+    assert cl(vp(16), 31, None, 0, None, None, 0, vp(32), 32, 0, vp(64), vp(64), taps, taps, 2, 4, 8, 0, 0, None) == -1    # batch stride too small
+    assert cl(vp(16), 32, None, 0, None, None, 0, vp(32), 32, 7, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1    # y_tpad < T
+    assert cl(vp(16), 32, None, 0, None, None, 0, vp(32), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 3, 0, None) == -2
+    tail = lib.afa_tail_fwd_cl
+    assert tail(vp(16), 320, vp(64), vp(64), taps, taps, vp(64), None, 0, None, None, 2, 32767.0, 2, 40, 8, 0, 0, None) == -1   # no output
+    assert tail(vp(16), 320, vp(64), vp(64), taps, taps, vp(64), None, 0, vp(128), None, 2, 32767.0, 2, 40, 8, 0, 0, None) == -1  # channels > 32
+    assert tail(vp(16), 64, vp(64), vp(64), taps, taps, vp(64), None, 0, None, vp(128), 2, 32767.0, 3, 8, 8, 0, 0, None) == -1    # batch % interleave
+    arr = (vp * 2)(vp(16), vp(32))
+    assert lib.afa_resblock_mean(arr, arr, 5, None, 1.0, vp(64), 4, 4, 0, None) == -1
+    assert lib.afa_resblock_mean(arr, arr, 2, None, 1.0, vp(64), 0, 4, 0, None) == 0                                               # empty: no-op
     ws = lib.afa_bwd_workspace_bytes(2, 3, 1000, 0)
     assert ws >= 2 * 4 * 2 * 3 and lib.afa_bwd_workspace_bytes(4, 3, 1000, 0) > ws
     assert lib.afa_bwd_workspace_bytes(2, 3, 0, 0) <= 16
