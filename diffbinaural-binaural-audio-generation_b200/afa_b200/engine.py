@@ -127,8 +127,9 @@ class ChannelsLastVocoder:
                 a = self._act(it["a1"], r, T, bias=r_pending, out_tpad=tp)
             else:                                                            # x = xt + x, then a1(x)
                 r_new = torch.empty(x.shape[0], T, x.shape[2], dtype=x.dtype, device=x.device)
-                a = self._act(it["a1"], t, T, bias=self._sum(t_bias, r_pending), res=r, xsum=r_new, out_tpad=tp)
-                r, r_pending = r_new, None
+                r_pending = self._sum(t_bias, r_pending)                     # biases the new residual stream still lacks
+                a = self._act(it["a1"], t, T, bias=r_pending, res=r, xsum=r_new, out_tpad=tp)
+                r = r_new
             t, t_bias = it["c1"](a), it["c1"].bias
             if it["c2"] is not None:
                 tp2 = it["c2"].tpad(T)

@@ -49,7 +49,8 @@ def _f32(name, p, n, device):
 
 def amp_activation1d_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, *, bias=None, res=None,
                         xsum=None, out=None, out_tpad: int = 0):
-    """y = Activation1d(x + bias + res) on channels-last data; returns y (and fills `xsum` = x + bias + res).
+    """y = Activation1d(x + res + bias) on channels-last data; returns y and fills `xsum` = x + res (the bias
+    stays pending on the new residual stream: pass it on to the next call / to `resblock_mean`).
 
     x: [B, >=T, C] view (only rows < T are read).  out: [B, >=max(T, out_tpad), C] view or None (allocated
     dense, out_tpad rows).  Rows [T, out_tpad) of out are zero-filled."""
@@ -64,9 +65,9 @@ def amp_activation1d_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bo
     _check_cl("out", out, B, T, C, dt, dev, rows=tp)
     if res is not None:
         _check_cl("res", res, B, T, C, dt, dev)
+    if (xsum is None) != (res is None):
+        raise RuntimeError("res and xsum come together: xsum = x + res is the new residual stream")
     if xsum is not None:
-        if res is None:
-            raise RuntimeError("xsum is only produced together with res")
         _check_cl("xsum", xsum, B, T, C, dt, dev)
     alpha = _f32("alpha", alpha, C, dev)
     beta = _f32("beta", beta, C, dev)

@@ -248,8 +248,8 @@ const char* afa_last_error(void) { return g_err; }
 int64_t afa_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int afa_set_tuning(int which, int chunks, int threads) {
-    if (which == 2) {   // channels-last walk: segment length = 12 * chunks samples
-        if (chunks < 0 || chunks > 4096) return fail(AFA_ERR_BAD_ARG, "channels-last segment length must be 12 * [1, 4096]");
+    if (which == 2) {   // channels-last walk: segment length = 12 * chunks + 2 samples
+        if (chunks < 0 || chunks > 4096) return fail(AFA_ERR_BAD_ARG, "channels-last segment length must be 12 * [1, 4096] + 2");
         g_tune_chunks[2] = chunks;
         return 0;
     }
@@ -378,12 +378,17 @@ namespace {
 
 // Segment length of the channels-last walk: long segments amortise the 10 extra steps (halo warm-up and
 // drain) per segment; small launches want enough threads to fill 148 SMs a few times over.
-int cl_segment(int64_t batch, int64_t channels, int64_t T) {
-    if (g_tune_chunks[2]) return 12 * g_tune_chunks[2];
-    const int64_t want_threads = 148ll * 5 * afa::kClThreads * 3;
-    int L = 96;
-    while (L > 24 && batch * channels * ((T + L - 1) / L) < want_threads) L -= 24;
-    return L;
+// Segment length of the channels-last walk, L = 12 n + 2 (the L + 10 steps are n + 1 groups of 12).  Long
+// segments amortise the 10 warm-up / drain steps, but the grid runs in waves of (resident CTAs/SM) x 148 CTAs
+// whose duration grows with L, and a launch of only 2-3 long waves ends in a ragged tail (measured:
+// profiles/r01_cl_sweep_*.log): long segments only where the launch still has several waves.
+int cl_segment(int64_t batch, int64_t channels, int64_t T, bool res) {
+    if (g_tune_chunks[2]) return 12 * g_tune_chunks[2] + 2;
+    const double wave = 148.0 * (res ? 4 : 5);
+    auto waves = [&](int L) { return (double)(batch * ((T + L - 1) / L) * channels) / afa::kClThreads / wave; };
+    if (res) return waves(98) >= 4.0 ? 98 : (waves(74) >= 2.0 ? 74 : 50);
+    if (waves(146) >= 3.0) return 146;
+    return waves(98) >= 2.0 ? 98 : 50;
 }
 
 template <typename T>
@@ -409,7 +414,7 @@ int afa_amp_activation1d_fwd_cl(const void* x, int64_t x_bstride, const void* re
     if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
     if (dtype != AFA_DTYPE_F32 && dtype != AFA_DTYPE_BF16) return fail(AFA_ERR_BAD_DTYPE, "dtype %d is not AFA_DTYPE_F32/BF16", dtype);
     if (batch < 0 || channels <= 0 || T < 0) return fail(AFA_ERR_BAD_ARG, "bad shape batch=%lld channels=%lld T=%lld", (long long)batch, (long long)channels, (long long)T);
-    if (xsum && !res) return fail(AFA_ERR_BAD_ARG, "xsum is only produced together with res");
+    if ((xsum != nullptr) != (res != nullptr)) return fail(AFA_ERR_BAD_ARG, "res and xsum come together: xsum = x + res is the new residual stream");
     if (y == x || y == res || (xsum && (xsum == x || xsum == y || xsum == res)))
         return fail(AFA_ERR_BAD_ARG, "outputs must not alias inputs or each other (segments re-read their neighbours' halo)");
     if (y_tpad == 0) y_tpad = T;
@@ -420,7 +425,7 @@ int afa_amp_activation1d_fwd_cl(const void* x, int64_t x_bstride, const void* re
     const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
     if (((uintptr_t)x | (uintptr_t)res | (uintptr_t)xsum | (uintptr_t)y) & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
     if (batch == 0 || T == 0) return 0;
-    const int L = cl_segment(batch, channels, T);
+    const int L = cl_segment(batch, channels, T, res != nullptr);
     const int64_t nseg = (T + L - 1) / L;
     const int64_t total = batch * nseg * channels;
     if (total >= (1ll << 31) - afa::kClThreads) return fail(AFA_ERR_TOO_LARGE, "batch*channels*ceil(T/%d)=%lld exceeds 2^31", L, (long long)total);
@@ -431,7 +436,8 @@ int afa_amp_activation1d_fwd_cl(const void* x, int64_t x_bstride, const void* re
     a.x_bs = x_bstride; a.res_bs = res_bstride; a.xsum_bs = xsum_bstride; a.y_bs = y_bstride;
     a.total = (uint32_t)total;
     a.chan = make_fastdiv((uint32_t)channels);
-    a.nseg = make_fastdiv((uint32_t)nseg);
+    a.batch = make_fastdiv((uint32_t)batch);
+    a.nseg = (uint32_t)nseg;
     a.T = (int32_t)T; a.L = L; a.y_tpad = (int32_t)y_tpad; a.flags = flags;
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == AFA_DTYPE_F32 ? launch_cl<float>(a, res != nullptr, st) : launch_cl<__nv_bfloat16>(a, res != nullptr, st);
@@ -451,7 +457,7 @@ int afa_tail_fwd_cl(const void* x, int64_t x_bstride, const float* alpha, const 
     if (x_bstride < T * channels) return fail(AFA_ERR_BAD_ARG, "batch stride must cover T*channels elements");
     if (T * channels >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "T*channels exceeds 2^31");
     if (batch == 0 || T == 0) return 0;
-    const int L = 96;                                  // walk length; 90 outputs per segment
+    const int L = 98;                                  // walk length (12 n + 2); 92 outputs per segment
     const int64_t nseg = (T + (L - 6) - 1) / (L - 6);
     const int64_t warps = batch * nseg;
     if (warps >= (1ll << 31) / 32) return fail(AFA_ERR_TOO_LARGE, "too many segments");

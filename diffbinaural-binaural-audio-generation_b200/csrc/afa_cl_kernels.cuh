@@ -7,7 +7,7 @@
 // profiles/r01_vocoder_breakdown.log).  Keeping the activations channels-last end to end removes the
 // conversions, and the prologue below removes the bias and residual kernels:
 //
-//   afa_cl_fwd_kernel      x' = x + bias[c] (+ res);  [xsum = x';]  y = down2x(snake(up2x(x')))
+//   afa_cl_fwd_kernel      x' = x (+ res);  [xsum = x';]  y = down2x(snake(up2x(x' + bias[c])))
 //                          reference: Conv1d bias of c1/c2 + `x = xt + x` + the next Activation1d
 //                          (BigVGAN/bigvgan.py:132-141, act.py:25-30)
 //   afa_cl_tail_kernel     activation_post -> conv_post (C -> 1, k = 7, zero pad) -> clamp | tanh
@@ -34,7 +34,7 @@ constexpr int kClThreads = 128;
 struct ClArgs {
     const void* x;
     const void* res;      // optional second addend (residual stream), same shape
-    void* xsum;           // optional: x' = x + bias + res is written here (the new residual stream)
+    void* xsum;           // with res: x + res is written here (the new residual stream; `bias` stays pending)
     void* y;
     const float* bias;    // optional [C] fp32
     const float* alpha;
@@ -42,7 +42,8 @@ struct ClArgs {
     FwdTaps taps;
     int64_t x_bs, res_bs, xsum_bs, y_bs;   // batch strides in elements (rows may be padded in time)
     uint32_t total;       // batch * nseg * C threads
-    FastDiv chan, nseg;
+    FastDiv chan, batch;
+    uint32_t nseg;
     int32_t T, L, y_tpad, flags;
 };
 
@@ -67,6 +68,32 @@ template <> __device__ __forceinline__ float cl_load<float>(const float* p) { re
 template <> __device__ __forceinline__ float cl_load<__nv_bfloat16>(const __nv_bfloat16* p) {
     return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
 }
+// The prefetch ring holds RAW loaded words; they become floats only at the step that consumes them.  The
+// conversion is `asm volatile` on purpose: written as plain C++ the compiler hoists all 12 (24) shifts of a trip
+// to the top of the loop body, so every load of the previous trip -- including the one issued last -- must have
+// landed there (ncu: one SHF carried 10 % of all stall samples, long_scoreboard).  Pinned, each load keeps its
+// full 12-step lead.
+template <typename T> struct ClRaw;
+template <> struct ClRaw<float> {
+    using raw_t = float;
+    static __device__ __forceinline__ raw_t load(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float cvt(raw_t v) {
+        float o;
+        asm volatile("mov.b32 %0, %1;" : "=f"(o) : "f"(v));
+        return o;
+    }
+};
+template <> struct ClRaw<__nv_bfloat16> {
+    using raw_t = uint32_t;
+    static __device__ __forceinline__ raw_t load(const __nv_bfloat16* p) {
+        return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p));
+    }
+    static __device__ __forceinline__ float cvt(raw_t v) {
+        uint32_t o;
+        asm volatile("shl.b32 %0, %1, 16;" : "=r"(o) : "r"(v));
+        return __uint_as_float(o);
+    }
+};
 template <typename T> __device__ __forceinline__ void cl_store(T* p, float v);
 template <> __device__ __forceinline__ void cl_store<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void cl_store<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -87,41 +114,66 @@ struct TailSink {
 // ------------------------------------------------------------------------------------------------
 // The walk of one (batch, channel, segment).  px/pr/ps/py point at this channel's column of batch b
 // (element t at p[t * Cs]).  Step q (-4 <= q <= L+5) consumes x'[t0+q-1], handles the 2x-rate pair
-// (s[2m-1], s[2m]), m = t0-3+q, and completes y[t0+q-6]; L is a multiple of kClS.
-// MODE 0: the whole reach [t0-5, t0+L+4] lies inside the row (branch-free); MODE 1: anything else
-// (index clamps = replicate pad of x, selects for the replicate pad of the activated signal).
+// (s[2m-1], s[2m]), m = t0-3+q, and completes y[t0+q-6].  L = 12 n + 2: the L + 10 steps are n + 1 GROUPS
+// of 12; group g covers steps q in [12g-4, 12g+8).
+//
+// Memory schedule (what the ncu captures of the first version asked for): the 12 inputs of group g+1 are
+// requested in ONE burst at the top of group g, right after group g's own raw words have been turned into
+// floats, so every load has a whole group (12 steps, ~2000 cycles under load) to land.  Written with one load
+// per step, the compiler clustered the conversions at the top of the loop body anyway and left the loads
+// spread over the first half of the body: the last ones had 40 % of a trip to land and one SHF carried 10 %
+// of all stall samples (long_scoreboard).
+//
+// MODE 0: the whole reach [t0-5, t0+L+4] lies inside the row (branch-free); MODE 1: anything else (index
+// clamps = replicate pad of x, selects for the replicate pad of the activated signal).
 // SINK 0: store y;  SINK 1: feed conv_post (tail kernel; all 32 lanes walk in lockstep).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool RES, int SINK>
 __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __restrict__ pr, T* __restrict__ ps,
                                         T* __restrict__ py, const int Cs, const int t0, const int L, const int Tlen,
                                         const float a, const float ib, const float bias, const FwdTaps& tp,
-                                        TailSink* sink) {
+                                        TailSink* sink, const uint32_t mask) {
     constexpr int S = kClS;
+    using raw = ClRaw<T>;
     float2 up[S], ac[S];
-    float xq[S], rq[RES ? S : 1];
+    typename raw::raw_t xq[S], rq[RES ? S : 1];   // raw words of the NEXT group, in flight
+    float xf[S];                                   // inputs of the CURRENT group: x (+ res)
     float s_first = 0.f, s_last = 0.f;
 
-    auto xaddr = [&](int t) -> int64_t {
-        if (MODE == 1) t = min(max(t, 0), Tlen - 1);
-        return (int64_t)t * Cs;
-    };
-    // the first S inputs: x[t0-5 .. t0-5+S-1]
+    // request the 12 inputs x[tb .. tb+11] (group slots 0..11)
+    auto request = [&](const int tb) {
+        if (MODE == 0) {
+            const T* p = px + (int64_t)tb * Cs;
+            const T* q = RES ? pr + (int64_t)tb * Cs : nullptr;
 #pragma unroll
-    for (int i = 0; i < S; ++i) {
-        const int64_t o = xaddr(t0 - 5 + i);
-        xq[(i - 4 + 4 * S) % S] = cl_load(px + o);
-        if (RES) rq[(i - 4 + 4 * S) % S] = cl_load(pr + o);
-    }
-    // running pointers (MODE 0): next prefetch = x[t0-5+S], next store = y[t0], next xsum = x'[t0]
-    const T* pp = px + (int64_t)(t0 - 5 + S) * Cs;
-    const T* ppr = RES ? pr + (int64_t)(t0 - 5 + S) * Cs : nullptr;
+            for (int i = 0; i < S; ++i) {
+                xq[i] = raw::load(p);
+                p += Cs;
+                if (RES) { rq[i] = raw::load(q); q += Cs; }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const int64_t o = (int64_t)min(max(tb + i, 0), Tlen - 1) * Cs;
+                xq[i] = raw::load(px + o);
+                if (RES) rq[i] = raw::load(pr + o);
+            }
+        }
+    };
+    auto land = [&]() {
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            xf[i] = raw::cvt(xq[i]);
+            if (RES) xf[i] += raw::cvt(rq[i]);
+        }
+    };
+    request(t0 - 5);                                   // group 0: steps -4..7
     T* pyr = (SINK == 0) ? py + (int64_t)t0 * Cs : nullptr;
-    T* psr = (RES && ps) ? ps + (int64_t)t0 * Cs : nullptr;
+    T* psr = RES ? ps + (int64_t)t0 * Cs : nullptr;
 
-    // bias folded into the initial value of every pending upsampler pair (non-RES); RES adds it explicitly
-    float2 bias2 = make_float2(0.f, 0.f);
-    if (!RES) {
+    // bias folded into the initial value of every pending upsampler pair
+    float2 bias2;
+    {
         float sx = 0.f, sy = 0.f;
 #pragma unroll
         for (int j = 0; j < 6; ++j) { sx += tp.p.cu[j].x; sy += tp.p.cu[j].y; }
@@ -130,9 +182,9 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
     if (MODE != 0) {
         auto xval = [&](int t) -> float {
             const int64_t o = (int64_t)min(max(t, 0), Tlen - 1) * Cs;
-            float v = cl_load(px + o) + bias;
+            float v = cl_load(px + o);
             if (RES) v += cl_load(pr + o);
-            return v;
+            return v + bias;
         };
         if (t0 <= 2) {  // s[0], which the left replicate pad of the activated signal repeats       filter.py:98
             const float x0 = xval(0), x1 = xval(1), x2 = xval(2);
@@ -150,27 +202,13 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
         }
     }
 
-    // `pre`: the input of step q+S is still needed (false in the last trip); `own`: x'[t0+q-1] belongs to
-    // this segment (xsum store)
-    auto step = [&](const int Q, const int q, const bool first_iter, const bool pre, const bool own) {
-        const int slot = (Q + 4 * S) % S;
-        float xv = xq[slot];
+    // Q: static part of the step number (ring slots); `own`: x'[t0+q-1] belongs to this segment (xsum store)
+    auto step = [&](const int Q, const int q, const bool first_iter, const bool own) {
+        const float xv = xf[(Q + 4 + 4 * S) % S];
         if (RES) {
-            xv = (xv + rq[slot]) + bias;
-            if (psr != nullptr && own && !(first_iter && Q < 1)) {
+            if (!(first_iter && Q < 1) && own) {
                 if (MODE == 0 || t0 + q - 1 < Tlen) cl_store(psr, xv);
                 psr += Cs;
-            }
-        }
-        if (pre) {   // prefetch the input of step q + S
-            if (MODE == 0) {
-                xq[slot] = cl_load(pp);
-                pp += Cs;
-                if (RES) { rq[slot] = cl_load(ppr); ppr += Cs; }
-            } else {
-                const int64_t o = xaddr(t0 + q - 1 + S);
-                xq[slot] = cl_load(px + o);
-                if (RES) rq[slot] = cl_load(pr + o);
             }
         }
         // --- upsampler, transposed form                                            resample.py:32-36
@@ -179,8 +217,7 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
         for (int j = 0; j < 6; ++j) {
             if (!(first_iter && Q + j < 1)) {
                 float2& pend = up[(Q + j + 4 * S) % S];
-                pend = (j == 5) ? (RES ? __fmul2_rn(tp.p.cu[5], xx) : __ffma2_rn(tp.p.cu[5], xx, bias2))
-                                : __ffma2_rn(tp.p.cu[j], xx, pend);
+                pend = __ffma2_rn(tp.p.cu[j], xx, (j == 5) ? bias2 : pend);
             }
         }
         if (first_iter && Q < 1) return;
@@ -236,15 +273,35 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
         }
     };
 
+    // group 0 (steps -4..7) and group 1 (steps 8..19) are straight-line code (the warm-up and the first outputs have
+    // static special cases); groups 2..n run in the rolled loop.  Every group body is
+    //     request(group g+1)  ->  12 steps on xf  ->  land() (raw words of g+1 -> xf)
+    // i.e. the loads' only consumer sits at the END of the body: the scheduler then issues them first and they
+    // have the whole body to land.  (With the consumer at the top of the next body, ptxas sank the loads to the
+    // bottom of this one -- zero lead -- and a __syncwarp "fence" only pinned their order among memory operations.)
+    const int n_groups = (L + 10) / S;                 // L = 12 n + 2  ->  n + 1 >= 2 groups
+    land();
+    request(t0 - 5 + S);
 #pragma unroll
-    for (int q = -4; q < 6 + S; ++q) step(q, q, true, q + S <= L + 5, q <= L);
-    const int NF = L / S - 1;
+    for (int q = -4; q < 8; ++q) step(q, q, true, q <= L);
+    land();
+    if (n_groups > 2) request(t0 - 5 + 2 * S);
+#pragma unroll
+    for (int q = 8; q < 8 + S; ++q) step(q, q, true, q <= L);
+    if (n_groups > 2) land();
+    // the rolled loop has NO branch inside (one basic block: loads, steps, conversions); the last group is peeled
 #pragma unroll 1
-    for (int it = 0; it < NF; ++it) {
-        const int qb = 6 + S + it * S;
-        const bool pre = it < NF - 1;
+    for (int g = 2; g < n_groups - 1; ++g) {
+        const int qb = g * S - 4;
+        request(t0 - 5 + (g + 1) * S);
 #pragma unroll
-        for (int k = 0; k < S; ++k) step(6 + k, qb + k, false, pre, pre || k <= S - 6);
+        for (int k = 0; k < S; ++k) step(8 + k, qb + k, false, true);
+        land();
+    }
+    if (n_groups > 2) {
+        const int qb = (n_groups - 1) * S - 4;
+#pragma unroll
+        for (int k = 0; k < S; ++k) step(8 + k, qb + k, false, k < S - 5);
     }
 }
 
@@ -256,28 +313,33 @@ __global__ void __launch_bounds__(kClThreads, RES ? 4 : 5) afa_cl_fwd_kernel(con
     const uint32_t g = blockIdx.x * kClThreads + threadIdx.x;
     const bool active = g < args.total;
     const uint32_t gc = active ? g : args.total - 1u;
-    const uint32_t sc = args.chan.div(gc);              // batch * nseg + segment
+    // thread order: channel fastest, then batch, then segment -- with the LAST segment of the rows first and
+    // the first one second: the edge-mode walks (and the zero fill) are the slow ones, so they must not be the
+    // last CTAs of the grid (ncu: one straggling SM doubled the launch time when they were)
+    const uint32_t sc = args.chan.div(gc);              // slot * batch + b
     const uint32_t c = gc - sc * args.chan.d;
-    const uint32_t b = args.nseg.div(sc);
-    const uint32_t s = sc - b * args.nseg.d;
+    const uint32_t slot = args.batch.div(sc);
+    const uint32_t b = sc - slot * args.batch.d;
+    const uint32_t s = slot == 0 ? args.nseg - 1u : slot - 1u;
     const int L = args.L, Tlen = args.T, Cs = (int)args.chan.d;
     const int t0 = (int)s * L;
 
     const T* px = static_cast<const T*>(args.x) + (int64_t)b * args.x_bs + c;
     const T* pr = RES ? static_cast<const T*>(args.res) + (int64_t)b * args.res_bs + c : nullptr;
-    T* ps = (RES && args.xsum) ? static_cast<T*>(args.xsum) + (int64_t)b * args.xsum_bs + c : nullptr;
+    T* ps = RES ? static_cast<T*>(args.xsum) + (int64_t)b * args.xsum_bs + c : nullptr;
     T* py = static_cast<T*>(args.y) + (int64_t)b * args.y_bs + c;
     const ChanParams cp = load_chan_params(args.alpha, args.beta, (int)c, args.flags);
     const float bias = args.bias ? __ldg(args.bias + c) : 0.f;
 
     const bool fast = !active || (t0 >= 5 && t0 + L + 5 < Tlen);
+    const uint32_t amask = __ballot_sync(0xffffffffu, active);
     if (__all_sync(0xffffffffu, fast)) {
-        if (active) walk_cl<T, 0, RES, 0>(px, pr, ps, py, Cs, t0, L, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr);
+        if (active) walk_cl<T, 0, RES, 0>(px, pr, ps, py, Cs, t0, L, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask);
     } else if (active) {
-        walk_cl<T, 1, RES, 0>(px, pr, ps, py, Cs, t0, L, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr);
+        walk_cl<T, 1, RES, 0>(px, pr, ps, py, Cs, t0, L, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask);
     }
     // rows [T, y_tpad) of y are the zero padding a polyphase (dilated) convolution reads next
-    if (active && s == args.nseg.d - 1u) {
+    if (active && s == args.nseg - 1u) {
         for (int t = Tlen; t < args.y_tpad; ++t) cl_store(py + (int64_t)t * Cs, 0.f);
     }
 }
@@ -310,7 +372,7 @@ __global__ void __launch_bounds__(kClThreads, 4) afa_cl_tail_kernel(const __grid
     sink.pcm_scale = args.pcm_scale;
     sink.use_tanh = args.use_tanh;
     sink.lane = lane;
-    walk_cl<T, 1, false, 1>(px, nullptr, nullptr, nullptr, C, t0, args.L, Tlen, cp.a_eff, cp.ib, 0.f, args.taps, &sink);
+    walk_cl<T, 1, false, 1>(px, nullptr, nullptr, nullptr, C, t0, args.L, Tlen, cp.a_eff, cp.ib, 0.f, args.taps, &sink, 0xffffffffu);
 }
 
 // ------------------------------------------------------------------------------------------------

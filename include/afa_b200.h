@@ -100,8 +100,10 @@ int afa_activation1d_bwd(const void *x, const void *gy, void *gx,
  * ------------------------------------------------------------------------------------------------ */
 
 /*
- * x' = x + bias[c] + res ;  xsum = x' (optional, needs res) ;  y = down2x(snake(up2x(x'))).
- * bias: float32 [channels] device or NULL; res / xsum: NULL or arrays shaped like x.  y_tpad >= T (0 = T):
+ * y = down2x(snake(up2x(x + res + bias[c]))) ;  xsum = x + res  (the new residual stream; `bias` -- the sum of
+ * the convolution biases not yet applied to x and res -- stays pending with the caller, who passes it again,
+ * plus the next convolution's, to the next call and finally to afa_resblock_mean).
+ * bias: float32 [channels] device or NULL; res and xsum: both NULL or both arrays shaped like x.  y_tpad >= T (0 = T):
  * rows [T, y_tpad) of every batch entry of y are written as zeros (the zero padding a dilated convolution
  * run as a (k x 1) convolution over the [y_tpad/d, d] polyphase view reads).  Outputs must not alias inputs.
  */
@@ -144,7 +146,7 @@ int afa_tail_fwd_cl(const void *x, int64_t x_bstride,
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).
  * afa_set_tuning: which=0 forward, 1 backward; chunks = 16-byte chunks per thread segment
  * (odd, one of the compiled values), threads = CTA size.  0 keeps the built-in choice.
- * which=2: channels-last forward, segment length = 12 * chunks samples.
+ * which=2: channels-last forward, segment length = 12 * chunks + 2 samples.
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
  * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects.
  */

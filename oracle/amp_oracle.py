@@ -124,13 +124,13 @@ def generator_forward(sd, mel, h, logscale=True):
 # the decomposition the channels-last kernels implement (layout [B, T, C])
 # --------------------------------------------------------------------------------------
 def amp_activation1d_cl(x_btc, alpha, beta=None, logscale=True, bias=None, res=None, taps_up=None, taps_down=None):
-    """afa_amp_activation1d_fwd_cl: x' = x + bias[c] + res; returns (x', Activation1d(x')) in [B, T, C]."""
+    """afa_amp_activation1d_fwd_cl: returns (xsum = x + res, y = Activation1d(x + res + bias[c])) in [B, T, C];
+    the bias stays pending on the residual stream (the caller carries it to the next call / the mean)."""
     xs = np.asarray(x_btc, dtype=np.float64)
-    if bias is not None:
-        xs = xs + np.asarray(bias, dtype=np.float64)[None, None, :]
     if res is not None:
         xs = xs + np.asarray(res, dtype=np.float64)
-    y = O.activation1d_forward(np.ascontiguousarray(xs.transpose(0, 2, 1)), alpha, beta, logscale, taps_up, taps_down)
+    xb = xs if bias is None else xs + np.asarray(bias, dtype=np.float64)[None, None, :]
+    y = O.activation1d_forward(np.ascontiguousarray(xb.transpose(0, 2, 1)), alpha, beta, logscale, taps_up, taps_down)
     return xs, np.ascontiguousarray(y.transpose(0, 2, 1))
 
 
@@ -183,8 +183,8 @@ def ampblock_decomposed(sd, prefix, x_bct, kernel_size, dilations, amp1: bool, l
         if n == 0:
             _, a = act(a_idx, r, bias=r_pend)
         else:
-            r, a = act(a_idx, t, bias=add(t_bias, r_pend), res=r)
-            r_pend = None
+            r_pend = add(t_bias, r_pend)                     # biases the new residual stream still lacks
+            r, a = act(a_idx, t, bias=r_pend, res=r)
         t = to_cl(conv1d(to_ncw(a), np.asarray(sd[c1 + "weight"], dtype=np.float64), None, get_padding(kernel_size, d), d))
         t_bias = sd[c1 + "bias"]
         if amp1:

@@ -58,7 +58,7 @@ def test_argument_errors_need_no_gpu(lib):
     i64 = ctypes.c_int64
     cl = lib.afa_amp_activation1d_fwd_cl
     assert cl(None, 0, None, 0, None, None, 0, None, 0, 0, None, None, taps, taps, 1, 4, 8, 0, 0, None) == -1
-    assert cl(vp(16), 32, None, 0, None, vp(48), 32, vp(32), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1   # xsum without res
+    assert cl(vp(16), 32, None, 0, None, vp(48), 32, vp(32), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1   # xsum without res (they come together)
     assert cl(vp(16), 32, None, 0, None, None, 0, vp(16), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1    # y aliases x
     assert cl(vp(16), 31, None, 0, None, None, 0, vp(32), 32, 0, vp(64), vp(64), taps, taps, 2, 4, 8, 0, 0, None) == -1    # batch stride too small
     assert cl(vp(16), 32, None, 0, None, None, 0, vp(32), 32, 7, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1    # y_tpad < T
