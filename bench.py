@@ -264,16 +264,21 @@ def run_e2e(wl: Workload, steps: int, warmup: int):
     return dt / steps, h2d, h2d
 
 
-def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: int, t_mel: int, reps: int = 1):
+def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: int, t_mel: int, reps: int = 1,
+                compare_ncw: bool = True):
     """audio-seconds per second of the whole generator (BASELINE configs 3/4): `total_clips` 10-second binaural
-    clips dealt round-robin over ranks; per batch: pinned H2D of the mels -> CUDA-graph replay of the bf16 generator
-    (fused Activation1d + cuDNN convolutions) on L and R -> D2H of the waveforms.  Random-init weights."""
+    clips dealt round-robin over ranks; per batch: pinned H2D of the mels -> CUDA-graph replay of the bf16
+    channels-last engine (afa_b200/engine.py: cuDNN NHWC convolutions + the fused AMP kernels, tail fused down to
+    interleaved int16 stereo PCM, which is what inference_e2e.py:193-205 writes) on L and R -> D2H of the PCM.
+    Random-init weights.  `compare_ncw` also times the [B, C, T] harness (reference layout) on one batch."""
     import torch
     import torch.distributed as dist
 
     from afa_b200 import shard_indices
+    from afa_b200.engine import ChannelsLastVocoder, GraphedEngine
     from afa_b200.vocoder import BigVGANGenerator, GraphedVocoder
 
+    torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234)
     gen = BigVGANGenerator().to(dev)
     with torch.no_grad():
@@ -282,13 +287,14 @@ def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: i
                 p.normal_(0, 0.5)
     gen = gen.bfloat16().eval()
     B = 2 * clips_per_batch
-    gv = GraphedVocoder(gen, B, t_mel, dtype=torch.bfloat16, device=dev)
+    eng = ChannelsLastVocoder(gen, dtype=torch.bfloat16)
+    ge = GraphedEngine(eng, B, t_mel, want_pcm=True, pcm_interleave=2)
     mine = shard_indices(total_clips, rank, world)
     n_batches = (len(mine) + clips_per_batch - 1) // clips_per_batch
     mel_host = (torch.rand(B, 80, t_mel) * 14.5 - 12.0).pin_memory()          # U(-12, 2.5): DiffBinaural's mel clamp range
-    wav_host = torch.empty(B, 1, t_mel * gen.hop, dtype=torch.bfloat16).pin_memory()
+    pcm_host = torch.empty(clips_per_batch, t_mel * gen.hop, 2, dtype=torch.int16).pin_memory()
     for _ in range(2):
-        wav_host.copy_(gv(mel_host.to(dev, non_blocking=True)), non_blocking=True)
+        pcm_host.copy_(ge(mel_host.to(dev, non_blocking=True))[1], non_blocking=True)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -296,24 +302,107 @@ def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: i
     e0.record()
     for _ in range(reps):
         for _b in range(n_batches):
-            y = gv(mel_host.to(dev, non_blocking=True))
-            wav_host.copy_(y, non_blocking=True)
+            _, pcm = ge(mel_host.to(dev, non_blocking=True))
+            pcm_host.copy_(pcm, non_blocking=True)
     e1.record()
     torch.cuda.synchronize(dev)
     t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the only collective of the inference path: gather finished waveforms (one per rank here)
-        outs = [torch.empty_like(gv.static_out) for _ in range(world)]
-        dist.all_gather(outs, gv.static_out)
+        # the only collective of the inference path: gather finished PCM (one batch per rank here)
+        outs = [torch.empty_like(ge.static_pcm) for _ in range(world)]
+        dist.all_gather(outs, ge.static_pcm)
     ms = float(t.item())
-    return {
+    out = {
         "audio_sec_per_sec": round(total_clips * 10.0 / (ms * 1e-3), 1), "unit": "binaural audio-s per wall-s",
         "total_clips": total_clips, "clips_per_batch": clips_per_batch, "ms_total": round(ms, 2),
-        "ms_per_clip_per_gpu": round(ms / max(1, len(mine)), 3), "dtype": "bf16 generator, fp32 math inside Activation1d",
-        "includes": "pinned H2D of mels, CUDA-graph replay (fused Activation1d + cuDNN convs), D2H of waveforms",
+        "ms_per_clip_per_gpu": round(ms / max(1, len(mine)), 3),
+        "dtype": "bf16 generator (channels-last engine), fp32 math inside the fused AMP kernels, int16 PCM out",
+        "includes": "pinned H2D of mels, CUDA-graph replay (cuDNN NHWC convs + fused AMP kernels incl. tail), D2H of stereo PCM",
         "params": sum(p.numel() for p in gen.parameters()),
     }
+    if compare_ncw and rank == 0:
+        try:
+            del ge
+            torch.cuda.empty_cache()
+            gv = GraphedVocoder(gen, B, t_mel, dtype=torch.bfloat16, device=dev)
+            mel_dev = mel_host.to(dev)
+            for _ in range(2):
+                gv(mel_dev)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(3):
+                gv(mel_dev)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms_ncw = e0.elapsed_time(e1) / 3
+            out["ncw_harness_ms_per_clip"] = round(ms_ncw / clips_per_batch, 3)
+            out["ncw_harness_audio_sec_per_sec_one_gpu"] = round(clips_per_batch * 10.0 / (ms_ncw * 1e-3), 1)
+        except Exception as exc:  # noqa: BLE001
+            out["ncw_harness_error"] = repr(exc)[:120]
+    return out
+
+
+def run_cl_step(dev, clips: int, t_mel: int, steps: int = 5):
+    """The fused AMP kernels of one channels-last generator pass (bf16, CUDA-graph replay, rotating buffers):
+    72 x activation+bias, 36 x activation+bias+residual (writes the new residual stream), 6 x resblock mean,
+    1 x tail.  GB/s counts algorithmic bytes: 4 B/element, 8 B/element, 14 B/element, (2 C + 6) B/sample."""
+    import torch
+
+    from afa_b200 import _lib, functional as F_afa, functional_cl as FC
+    from afa_b200.modules import kaiser_sinc_filter1d
+
+    dt = torch.bfloat16
+    h = F_afa.host_taps(kaiser_sinc_filter1d(0.25, 0.3, 12))
+    B = 2 * clips
+    work, bytes_total, launches = [], 0, 0
+    for (c, mult, _calls) in AMP_STAGES:
+        T = mult * t_mel
+        bufs = [torch.randn(B, T, c, device=dev, dtype=dt) for _ in range(4)]
+        outs = [torch.empty(B, T, c, device=dev, dtype=dt) for _ in range(3)]
+        alpha, beta, bias = (torch.randn(c, device=dev) * 0.5 for _ in range(3))
+        work.append((c, T, bufs, outs, alpha, beta, bias))
+        n = B * T * c
+        bytes_total += 12 * n * 4 + 6 * n * 8 + n * 14
+        launches += 19
+    c, T, bufs, outs, alpha, beta, bias = work[-1]
+    w_post = torch.randn(c, 7, device=dev) * 0.05
+    bytes_total += B * T * (2 * c + 6)
+    launches += 1
+    wave = torch.empty(B, T, device=dev)
+    pcm = torch.empty(clips, T, 2, dtype=torch.int16, device=dev)
+
+    def step():
+        for (c, T, bufs, outs, alpha, beta, bias) in work:
+            for k in range(12):
+                FC.amp_activation1d_cl(bufs[k % 4], T, alpha, beta, h, h, True, bias=bias, out=outs[k % 3])
+            for k in range(6):
+                FC.amp_activation1d_cl(bufs[k % 4], T, alpha, beta, h, h, True, bias=bias, res=bufs[(k + 1) % 4],
+                                       xsum=outs[(k + 1) % 3], out=outs[k % 3])
+            FC.resblock_mean(bufs[:3], [bufs[3], bufs[0], bufs[1]], bias, 1.0 / 3.0, out=outs[0])
+        c, T, bufs, outs, alpha, beta, bias = work[-1]
+        FC.tail_cl(bufs[0], T, alpha, beta, h, h, True, w_post, None, wave=wave, pcm=pcm, want_pcm=True)
+
+    step()
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    elems = sum(B * T * c * 18 for (c, T, *_r) in work)
+    return {"ms_per_pass": round(ms, 3), "gbps": round(bytes_total / (ms * 1e-3) / 1e9, 1), "launches_per_pass": launches,
+            "activation_elements_per_pass": elems, "gelem_per_s": round(elems / (ms * 1e-3) / 1e9, 1),
+            "dtype": "bf16 I/O, f32 math", "layout": "[B, T, C]", "clips": clips,
+            "kernels": "afa_cl_fwd_kernel<bf16,false> x72, <bf16,true> x36, afa_mean_kernel x6, afa_cl_tail_kernel x1"}
 
 
 def run_gpu(args):
@@ -434,6 +523,13 @@ def run_gpu(args):
         except Exception as exc:  # noqa: BLE001  (the headline metric must still print)
             vocoder = {"error": repr(exc)[:200]}
         wl = None
+    channels_last = None
+    if not args.no_vocoder and rank == 0 and world == 1:
+        try:
+            torch.cuda.empty_cache()
+            channels_last = run_cl_step(dev, args.clips, args.t_mel)
+        except Exception as exc:  # noqa: BLE001
+            channels_last = {"error": repr(exc)[:200]}
 
     if world > 1 and wl is not None:
         # the only collective: gather one checksum per rank (stands in for gathering finished waveforms)
@@ -464,6 +560,7 @@ def run_gpu(args):
             "clocks": clocks.summary(),
             "audio_sec_per_sec_activation_only": round(world * args.clips * 10.0 / (ms_per_step * 1e-3), 2),
             "vocoder": vocoder,
+            "channels_last_amp_kernels": channels_last,
         }
         print(json.dumps(line))
     if world > 1:
