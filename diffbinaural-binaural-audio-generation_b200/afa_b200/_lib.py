@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = (
     "afa_amp_activation1d_fwd_cl",
     "afa_resblock_mean",
     "afa_tail_fwd_cl",
+    "afa_amp_act_conv_supported",
+    "afa_amp_act_conv_fwd_cl",
     "afa_set_tuning",
     "afa_kernel_info",
     "afa_kernel_info_shape",
@@ -68,6 +70,11 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_tail_fwd_cl.restype = i32
         lib.afa_tail_fwd_cl.argtypes = [vp, i64, vp, vp, fp, fp, vp, vp, i32, vp, vp, i32, f32, i64, i64, i64,
                                         i32, i32, vp]
+        lib.afa_amp_act_conv_supported.restype = i32
+        lib.afa_amp_act_conv_supported.argtypes = [i64, i32, i32, i32]
+        lib.afa_amp_act_conv_fwd_cl.restype = i32
+        lib.afa_amp_act_conv_fwd_cl.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp, fp, fp, vp, i32, i32,
+                                                i64, i64, i64, i32, i32, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32

@@ -22,7 +22,7 @@ def _sources():
 
 
 def _deps():
-    return _sources() + [os.path.join(_CSRC, "afa_kernels.cuh"), os.path.join(_CSRC, "afa_cl_kernels.cuh"),
+    return _sources() + [os.path.join(_CSRC, "afa_kernels.cuh"), os.path.join(_CSRC, "afa_cl_kernels.cuh"), os.path.join(_CSRC, "afa_actconv_kernels.cuh"),
                          os.path.join(_INCLUDE, "afa_b200.h")]
 
 

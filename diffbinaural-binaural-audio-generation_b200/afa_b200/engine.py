@@ -44,13 +44,17 @@ class _Act:
 
 
 class _Conv:
-    def __init__(self, conv: torch.nn.Conv1d, dtype):
+    def __init__(self, conv: torch.nn.Conv1d, dtype, fuse: bool = False):
         self.w = _cl_weight(conv.weight, dtype)
         self.bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
         self.k = conv.kernel_size[0]
         self.d = conv.dilation[0]
         if conv.stride[0] != 1 or conv.padding[0] != (self.k * self.d - self.d) // 2 or conv.groups != 1:
             raise NotImplementedError("engine convolutions are stride-1, 'same'-padded, dense")
+        # narrow stages: the activation in front of this convolution runs as its prologue (one fused kernel)
+        self.fused = (fuse and conv.in_channels == conv.out_channels
+                      and FC.act_conv_supported(conv.in_channels, self.k, self.d, dtype))
+        self.w_kcc = conv.weight.detach().to(dtype).permute(2, 0, 1).contiguous() if self.fused else None
 
     def tpad(self, T: int) -> int:
         return (T + self.d - 1) // self.d * self.d
@@ -66,9 +70,15 @@ class _Conv:
 class ChannelsLastVocoder:
     """mel [B, num_mels, T_mel] -> (wave float32 [B, 1, T], pcm int16 [B/2, T, 2] | None)."""
 
-    def __init__(self, gen: BigVGANGenerator, dtype=torch.bfloat16):
+    def __init__(self, gen: BigVGANGenerator, dtype=torch.bfloat16, parallel_resblocks: bool = True,
+                 fuse_narrow_convs: bool = True):
         self.dtype = dtype
+        fz = bool(fuse_narrow_convs)
         self.h = gen.h
+        # the num_kernels resblocks of a stage are independent until their mean: run them on side streams so that
+        # one block's small launches fill the tails of another's (captured as parallel branches of the CUDA graph)
+        self.parallel_resblocks = parallel_resblocks
+        self._side_streams = None
         self.device = next(gen.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("ChannelsLastVocoder runs on CUDA only (there is no CPU fallback)")
@@ -82,10 +92,10 @@ class ChannelsLastVocoder:
             for j in range(gen.num_kernels):
                 rb = gen.resblocks[i * gen.num_kernels + j]
                 if isinstance(rb, AMPBlock1):
-                    its = [dict(a1=_Act(a1), c1=_Conv(c1, dtype), a2=_Act(a2), c2=_Conv(c2, dtype))
+                    its = [dict(a1=_Act(a1), c1=_Conv(c1, dtype, fz), a2=_Act(a2), c2=_Conv(c2, dtype, fz))
                            for c1, c2, a1, a2 in zip(rb.convs1, rb.convs2, rb.activations[::2], rb.activations[1::2])]
                 elif isinstance(rb, AMPBlock2):
-                    its = [dict(a1=_Act(a), c1=_Conv(c, dtype), a2=None, c2=None) for c, a in zip(rb.convs, rb.activations)]
+                    its = [dict(a1=_Act(a), c1=_Conv(c, dtype, fz), a2=None, c2=None) for c, a in zip(rb.convs, rb.activations)]
                 else:
                     raise NotImplementedError(type(rb).__name__)
                 blocks.append(its)
@@ -116,28 +126,59 @@ class ChannelsLastVocoder:
     def _act(self, a: _Act, x, T, **kw):
         return FC.amp_activation1d_cl(x, T, a.alpha, a.beta, a.taps_up, a.taps_down, a.logscale, **kw)
 
+    def _act_conv(self, a: _Act, conv: _Conv, x, T, **kw):
+        """conv(Activation1d(x + res + bias)) without the convolution's bias: one fused kernel on the narrow stages,
+        else the activation kernel (zero-filling the polyphase padding rows) followed by cuDNN."""
+        if conv.fused:
+            return FC.amp_act_conv_cl(x, T, a.alpha, a.beta, a.taps_up, a.taps_down, a.logscale, conv.w_kcc, conv.k,
+                                      conv.d, **kw)
+        return conv(self._act(a, x, T, out_tpad=conv.tpad(T), **kw))
+
     def _resblock(self, its, x, T, up_bias):
         """One AMPBlock on the raw upsampler output x (its bias `up_bias` still pending).
         Returns (xt, pending bias of xt, residual stream, bias still missing from the residual stream)."""
         r, r_pending = x, up_bias
         t, t_bias = None, None
         for n, it in enumerate(its):
-            tp = it["c1"].tpad(T)
             if n == 0:
-                a = self._act(it["a1"], r, T, bias=r_pending, out_tpad=tp)
+                t = self._act_conv(it["a1"], it["c1"], r, T, bias=r_pending)
             else:                                                            # x = xt + x, then a1(x)
                 r_new = torch.empty(x.shape[0], T, x.shape[2], dtype=x.dtype, device=x.device)
                 r_pending = self._sum(t_bias, r_pending)                     # biases the new residual stream still lacks
-                a = self._act(it["a1"], t, T, bias=r_pending, res=r, xsum=r_new, out_tpad=tp)
+                t = self._act_conv(it["a1"], it["c1"], t, T, bias=r_pending, res=r, xsum=r_new)
                 r = r_new
-            t, t_bias = it["c1"](a), it["c1"].bias
+            t_bias = it["c1"].bias
             if it["c2"] is not None:
-                tp2 = it["c2"].tpad(T)
-                a = self._act(it["a2"], t, T, bias=t_bias, out_tpad=tp2)
-                t, t_bias = it["c2"](a), it["c2"].bias
+                t = self._act_conv(it["a2"], it["c2"], t, T, bias=t_bias)
+                t_bias = it["c2"].bias
         if t.shape[1] != T:
             t = t[:, :T].contiguous()                                        # only if the LAST convolution is dilated (AMPBlock2)
         return t, t_bias, r, r_pending
+
+    def _resblocks(self, st, x, T):
+        if not self.parallel_resblocks or len(st["blocks"]) < 2:
+            return [self._resblock(its, x, T, st["bias"]) for its in st["blocks"]]
+        dev = x.device
+        cur = torch.cuda.current_stream(dev)
+        if self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream(dev) for _ in range(len(st["blocks"]) - 1)]
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs, joins = [None] * len(st["blocks"]), []
+        for j, its in enumerate(st["blocks"][1:], start=1):
+            side = self._side_streams[j - 1]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                outs[j] = self._resblock(its, x, T, st["bias"])
+                for t in (outs[j][0], outs[j][2]):
+                    t.record_stream(cur)                    # consumed by the mean kernel on the main stream
+                ev = torch.cuda.Event()
+                ev.record(side)
+                joins.append(ev)
+        outs[0] = self._resblock(st["blocks"][0], x, T, st["bias"])
+        for ev in joins:
+            cur.wait_event(ev)
+        return outs
 
     @torch.no_grad()
     def __call__(self, mel: torch.Tensor, want_pcm: bool = False, pcm_interleave: int = 2):
@@ -152,7 +193,7 @@ class ChannelsLastVocoder:
             y4 = F.conv_transpose2d(x4, st["w"], None, (st["u"], 1), (st["p"], 0))
             T = y4.shape[2]
             x = y4.permute(0, 2, 3, 1).reshape(B, T, st["cout"])
-            outs = [self._resblock(its, x, T, st["bias"]) for its in st["blocks"]]
+            outs = self._resblocks(st, x, T)
             bias_sum = self._sum(*[b for o in outs for b in (o[1], o[3])])
             x = FC.resblock_mean([o[0] for o in outs], [o[2] for o in outs], bias_sum, 1.0 / self.num_kernels)
         a = self.post_act

@@ -88,6 +88,56 @@ def amp_activation1d_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bo
     return out
 
 
+def act_conv_supported(channels: int, kernel_size: int, dilation: int, dtype) -> bool:
+    """Is the fused activation -> convolution kernel compiled for this configuration?"""
+    if dtype != torch.bfloat16:
+        return False
+    return bool(_lib.load_library().afa_amp_act_conv_supported(channels, kernel_size, dilation, _lib.AFA_DTYPE_BF16))
+
+
+def amp_act_conv_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, w_kcc, kernel_size: int, dilation: int,
+                    *, bias=None, res=None, xsum=None, out=None):
+    """y = conv1d(Activation1d(x + res + bias), w, 'same' padding, dilation, NO bias) in one kernel; xsum = x + res.
+
+    bf16 channels-last tensors; w_kcc: bf16 [kernel_size, C, C] = conv.weight.permute(2, 0, 1).contiguous().
+    Reference: `xt = a(x); xt = c(xt)` (bigvgan.py:134-138); the convolution's bias stays pending with the caller."""
+    if not x.is_cuda:
+        raise RuntimeError("channels-last AMP ops run on CUDA tensors only (there is no CPU fallback)")
+    B, _, C = x.shape
+    dev, dt = x.device, x.dtype
+    if dt != torch.bfloat16:
+        raise TypeError(f"the fused activation+convolution runs on bfloat16 activations, got {dt}")
+    _check_cl("x", x, B, T, C, dt, dev)
+    if out is None:
+        out = torch.empty(B, T, C, dtype=dt, device=dev)
+    _check_cl("out", out, B, T, C, dt, dev)
+    if (xsum is None) != (res is None):
+        raise RuntimeError("res and xsum come together: xsum = x + res is the new residual stream")
+    if res is not None:
+        _check_cl("res", res, B, T, C, dt, dev)
+        _check_cl("xsum", xsum, B, T, C, dt, dev)
+    if w_kcc.dtype != torch.bfloat16 or tuple(w_kcc.shape) != (kernel_size, C, C) or not w_kcc.is_contiguous() or w_kcc.device != dev:
+        raise RuntimeError(f"w_kcc must be a contiguous bfloat16 [{kernel_size}, {C}, {C}] tensor on {dev}")
+    alpha = _f32("alpha", alpha, C, dev)
+    beta = _f32("beta", beta, C, dev)
+    bias = _f32("bias", bias, C, dev)
+    if B == 0 or T == 0:
+        return out
+    lib = _lib.load_library()
+    with torch.cuda.device_of(x):
+        rc = lib.afa_amp_act_conv_fwd_cl(
+            x.data_ptr(), _bstride(x),
+            None if res is None else res.data_ptr(), 0 if res is None else _bstride(res),
+            None if bias is None else bias.data_ptr(),
+            None if xsum is None else xsum.data_ptr(), 0 if xsum is None else _bstride(xsum),
+            out.data_ptr(), _bstride(out),
+            alpha.data_ptr(), None if beta is None else beta.data_ptr(), taps_up, taps_down,
+            w_kcc.data_ptr(), kernel_size, dilation, B, C, T, _dtype_code(x), _flags(logscale, beta),
+            torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "afa_amp_act_conv_fwd_cl")
+    return out
+
+
 def resblock_mean(xts, xress, bias_sum=None, scale=None, out=None):
     """out = scale * (sum_j (xts[j] + xress[j]) + bias_sum[c]); all tensors dense [B, T, C] (or any dense [..., C])."""
     K = len(xts)

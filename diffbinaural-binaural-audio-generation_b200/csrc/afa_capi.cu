@@ -10,6 +10,7 @@
 #include "afa_b200.h"
 #include "afa_kernels.cuh"
 #include "afa_cl_kernels.cuh"
+#include "afa_actconv_kernels.cuh"
 
 #ifndef AFA_CHUNK_LIST
 #define AFA_CHUNK_LIST(X) X(5) X(9) X(13) X(17)
@@ -521,6 +522,113 @@ int afa_resblock_mean(const void* const* xt, const void* const* xres, int num_ke
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_mean_kernel launch");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Activation1d as the prologue of the AMPBlock convolution (afa_actconv_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+template <bool RES, int NT8, int KS>
+int launch_actconv_t(const afa::ActConvArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
+    auto k = afa::afa_cl_actconv_kernel<RES, NT8, KS>;
+    static thread_local const void* configured[8] = {nullptr};
+    static thread_local int configured_dev[8] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    bool done = false;
+    for (int i = 0; i < 8; ++i) done = done || (configured[i] == (const void*)k && configured_dev[i] == dev + 1);
+    if (!done) {
+        e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        for (int i = 0; i < 8; ++i)
+            if (!configured[i]) { configured[i] = (const void*)k; configured_dev[i] = dev + 1; break; }
+    }
+    k<<<grid, afa::kAcThreads, smem, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_actconv_kernel launch");
+}
+
+template <bool RES>
+int launch_actconv(const afa::ActConvArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
+    switch (a.C) {
+        case 8: return launch_actconv_t<RES, 1, 1>(a, smem, grid, st);
+        case 16: return launch_actconv_t<RES, 2, 1>(a, smem, grid, st);
+        case 24: return launch_actconv_t<RES, 3, 2>(a, smem, grid, st);
+        case 32: return launch_actconv_t<RES, 4, 2>(a, smem, grid, st);
+        case 48: return launch_actconv_t<RES, 6, 3>(a, smem, grid, st);
+        case 64: return launch_actconv_t<RES, 8, 4>(a, smem, grid, st);
+    }
+    return fail(AFA_ERR_BAD_ARG, "fused activation+convolution is compiled for channels in {8,16,24,32,48,64}, got %d", a.C);
+}
+
+}  // namespace
+
+extern "C" {
+
+int afa_amp_act_conv_supported(int64_t channels, int kernel_size, int dilation, int dtype) {
+    if (dtype != AFA_DTYPE_BF16) return 0;
+    if (!(channels == 8 || channels == 16 || channels == 24 || channels == 32 || channels == 48 || channels == 64)) return 0;
+    if (kernel_size < 1 || kernel_size > 11 || !(kernel_size & 1) || dilation < 1 || dilation > 5) return 0;
+    return 1;
+}
+
+int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, int64_t res_bstride, const float* bias,
+                            void* xsum, int64_t xsum_bstride, void* y, int64_t y_bstride, const float* alpha,
+                            const float* beta, const float* taps_up12, const float* taps_down12, const void* w_kcc,
+                            int kernel_size, int dilation, int64_t batch, int64_t channels, int64_t T, int dtype,
+                            int flags, void* stream) {
+    if (!x || !y || !alpha || !taps_up12 || !taps_down12 || !w_kcc) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
+    if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
+    if (dtype != AFA_DTYPE_BF16) return fail(AFA_ERR_BAD_DTYPE, "the fused activation+convolution runs on bf16 activations (tensor-core path); dtype %d", dtype);
+    if (batch < 0 || channels <= 0 || T < 0) return fail(AFA_ERR_BAD_ARG, "bad shape batch=%lld channels=%lld T=%lld", (long long)batch, (long long)channels, (long long)T);
+    if (!afa_amp_act_conv_supported(channels, kernel_size, dilation, dtype))
+        return fail(AFA_ERR_BAD_ARG, "unsupported configuration: channels=%lld (need one of 8,16,24,32,48,64), kernel_size=%d (odd, <= 11), dilation=%d (<= 5)", (long long)channels, kernel_size, dilation);
+    if ((xsum != nullptr) != (res != nullptr)) return fail(AFA_ERR_BAD_ARG, "res and xsum come together: xsum = x + res is the new residual stream");
+    if (y == x || y == res || (xsum && (xsum == x || xsum == y || xsum == res)))
+        return fail(AFA_ERR_BAD_ARG, "outputs must not alias inputs or each other (tiles re-read their neighbours' halo)");
+    const int64_t row = T * channels;
+    if (x_bstride < row || (res && res_bstride < row) || (xsum && xsum_bstride < row) || y_bstride < row)
+        return fail(AFA_ERR_BAD_ARG, "batch strides must cover T*channels elements");
+    if (row >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "T*channels=%lld exceeds 2^31", (long long)row);
+    if (((uintptr_t)x | (uintptr_t)res | (uintptr_t)xsum) & 1) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
+    if (((uintptr_t)y & 3) || ((uintptr_t)w_kcc & 15) || (y_bstride & 1)) return fail(AFA_ERR_ALIGNMENT, "y must be 4-byte aligned (even batch stride), the weights 16-byte aligned");
+    if (batch == 0 || T == 0) return 0;
+    const int C = (int)channels;
+    afa::ActConvArgs a;
+    a.x = x; a.res = res; a.xsum = xsum; a.y = y; a.bias = bias; a.alpha = alpha; a.beta = beta;
+    a.w = (const __nv_bfloat16*)w_kcc;
+    fold_fwd_taps(taps_up12, taps_down12, &a.taps);
+    a.x_bs = x_bstride; a.res_bs = res_bstride; a.xsum_bs = xsum_bstride; a.y_bs = y_bstride;
+    a.T = (int32_t)T; a.C = C; a.flags = flags; a.batch = (int32_t)batch;
+    a.k = kernel_size; a.dil = dilation;
+    const int P = (kernel_size / 2) * dilation;
+    a.n_sub = afa::kAcThreads / C;                                   // (sub-segment, channel) pairs fill the CTA
+    if (a.n_sub > 12) a.n_sub = 12;
+    const int cpad = (C + 15) / 16 * 16;
+    a.a_stride = cpad + 8;
+    a.w_stride = cpad + 8;
+    // sub-segment length 12 n + 2: as long as two CTAs still fit in shared memory (about 100 KB each), shorter
+    // for short rows so that a launch keeps enough tiles
+    const size_t w_bytes = (size_t)kernel_size * C * a.w_stride * 2;
+    int n = 7;
+    while (n > 2 && w_bytes + (size_t)a.n_sub * (12 * n + 2) * a.a_stride * 2 > 100 * 1024) --n;
+    while (n > 2 && (int64_t)a.n_sub * (12 * n + 2) - 2 * P > 2 * T) --n;
+    a.Lsub = 12 * n + 2;
+    a.a_rows = a.n_sub * a.Lsub;
+    a.TT = (a.a_rows - 2 * P) / 16 * 16;
+    if (a.TT < 16) return fail(AFA_ERR_BAD_ARG, "tile too small for kernel_size=%d dilation=%d at channels=%d", kernel_size, dilation, C);
+    a.n_tiles = (int32_t)((T + a.TT - 1) / a.TT);
+    const size_t smem = w_bytes + (size_t)a.a_rows * a.a_stride * 2;
+    const int64_t grid = (int64_t)a.n_tiles * batch;
+    if (grid >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "too many tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    return res ? launch_actconv<true>(a, smem, (uint32_t)grid, st) : launch_actconv<false>(a, smem, (uint32_t)grid, st);
 }
 
 }  // extern "C"

@@ -111,6 +111,14 @@ struct TailSink {
     int lane;
 };
 
+// shared-memory tile of the fused activation -> convolution kernel (afa_actconv_kernels.cuh): this lane's column
+struct TileSink {
+    __nv_bfloat16* col;   // element of tile row r at col[r * stride]
+    int stride;           // elements per tile row
+    int tile_t0;          // time index of tile row 0
+    int own_lo, own_hi;   // x + res is stored to xsum only for rows in [own_lo, own_hi)
+};
+
 // ------------------------------------------------------------------------------------------------
 // The walk of one (batch, channel, segment).  px/pr/ps/py point at this channel's column of batch b
 // (element t at p[t * Cs]).  Step q (-4 <= q <= L+5) consumes x'[t0+q-1], handles the 2x-rate pair
@@ -126,13 +134,14 @@ struct TailSink {
 //
 // MODE 0: the whole reach [t0-5, t0+L+4] lies inside the row (branch-free); MODE 1: anything else (index
 // clamps = replicate pad of x, selects for the replicate pad of the activated signal).
-// SINK 0: store y;  SINK 1: feed conv_post (tail kernel; all 32 lanes walk in lockstep).
+// SINK 0: store y;  SINK 1: feed conv_post (tail kernel; all 32 lanes walk in lockstep);  SINK 2: write the
+// activated sample as bf16 into a shared-memory tile (zero outside the row: the convolution's zero padding).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool RES, int SINK>
 __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __restrict__ pr, T* __restrict__ ps,
                                         T* __restrict__ py, const int Cs, const int t0, const int L, const int Tlen,
                                         const float a, const float ib, const float bias, const FwdTaps& tp,
-                                        TailSink* sink, const uint32_t mask) {
+                                        TailSink* sink, const uint32_t mask, const TileSink* ts = nullptr) {
     constexpr int S = kClS;
     using raw = ClRaw<T>;
     float2 up[S], ac[S];
@@ -169,7 +178,9 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
     };
     request(t0 - 5);                                   // group 0: steps -4..7
     T* pyr = (SINK == 0) ? py + (int64_t)t0 * Cs : nullptr;
-    T* psr = RES ? ps + (int64_t)t0 * Cs : nullptr;
+    T* psr = (RES && SINK != 2) ? ps + (int64_t)t0 * Cs : nullptr;
+    __nv_bfloat16* ptile = nullptr;
+    if constexpr (SINK == 2) ptile = ts->col + (t0 - ts->tile_t0) * ts->stride;
 
     // bias folded into the initial value of every pending upsampler pair
     float2 bias2;
@@ -206,7 +217,10 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
     auto step = [&](const int Q, const int q, const bool first_iter, const bool own) {
         const float xv = xf[(Q + 4 + 4 * S) % S];
         if (RES) {
-            if (!(first_iter && Q < 1) && own) {
+            if constexpr (SINK == 2) {        // tiles overlap by the convolution's reach: store only this tile's own rows
+                const int t = t0 + q - 1;
+                if (!(first_iter && Q < 1) && t >= ts->own_lo && t < ts->own_hi) cl_store(ps + (int64_t)t * Cs, xv);
+            } else if (!(first_iter && Q < 1) && own) {
                 if (MODE == 0 || t0 + q - 1 < Tlen) cl_store(psr, xv);
                 psr += Cs;
             }
@@ -248,6 +262,10 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
         if constexpr (SINK == 0) {
             if (MODE == 0 || t0 + q - 6 < Tlen) cl_store(pyr, yv);
             pyr += Cs;
+        } else if constexpr (SINK == 2) {
+            const int tv = t0 + q - 6;
+            *ptile = __float2bfloat16_rn((MODE == 0 || (tv >= 0 && tv < Tlen)) ? yv : 0.f);
+            ptile += ts->stride;
         } else {
             // conv_post (k = 7, zero padding), transposed form: a[tv] feeds out[tv+3-j] with w[j]   bigvgan.py:380
             const int tv = t0 + q - 6;

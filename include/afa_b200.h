@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 110            /* 0.1.1: + AMP-block entry points on channels-last activations */
+#define AFA_VERSION 120            /* 0.1.2: + AMP-block entry points on channels-last activations, fused activation -> convolution */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
@@ -141,6 +141,27 @@ int afa_tail_fwd_cl(const void *x, int64_t x_bstride,
                     float *wave, int16_t *pcm, int pcm_interleave, float pcm_scale,
                     int64_t batch, int64_t channels, int64_t T,
                     int dtype, int flags, void *stream);
+
+/*
+ * Activation1d as the PROLOGUE of the AMPBlock convolution, for the narrow stages of the generator:
+ *   y = conv1d(down2x(snake(up2x(x + res + bias[c]))), w, no bias, 'same' padding, dilation) ; xsum = x + res
+ *   <->  `xt = a(x); xt = c(xt)`  BigVGAN/bigvgan.py:134-138 (AMPBlock1), :234-235 (AMPBlock2)
+ * Same conventions as afa_amp_activation1d_fwd_cl (the convolution's own bias stays pending with the caller).
+ * w_kcc: bf16 device array [kernel_size][channels_out][channels_in] (= conv.weight.permute(2, 0, 1)), 16-byte
+ * aligned; channels_out == channels_in == channels.  bf16 activations only (the convolution runs on the
+ * tensor cores with fp32 accumulation).  afa_amp_act_conv_supported() says whether a configuration is compiled.
+ */
+int afa_amp_act_conv_supported(int64_t channels, int kernel_size, int dilation, int dtype);
+int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
+                            const void *res, int64_t res_bstride,
+                            const float *bias,
+                            void *xsum, int64_t xsum_bstride,
+                            void *y, int64_t y_bstride,
+                            const float *alpha, const float *beta,
+                            const float *taps_up12, const float *taps_down12,
+                            const void *w_kcc, int kernel_size, int dilation,
+                            int64_t batch, int64_t channels, int64_t T,
+                            int dtype, int flags, void *stream);
 
 /*
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).

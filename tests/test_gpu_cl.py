@@ -340,3 +340,76 @@ def test_cl_error_codes():
     # empty inputs are legal no-ops
     y = FC.amp_activation1d_cl(torch.empty(0, 5, 8, device=DEV), 5, a, a, taps[0], taps[1], True)
     assert y.shape == (0, 5, 8)
+
+
+def _bf16_round(a):
+    return torch.tensor(a, dtype=torch.float32).to(torch.bfloat16).double().numpy()
+
+
+def test_act_conv_fused_grid():
+    """Activation1d as the prologue of the dilated convolution (tensor-core path, bf16): every compiled channel count,
+    kernel sizes 3/7/11 x dilations 1/3/5, T around the tile boundaries, with and without the residual prologue.
+    Oracle: float64 activation on the bf16 inputs, rounded to bf16 (the tile the MMA reads), float64 convolution."""
+    _, FC = _fc()
+    t32, taps, taps64 = _taps()
+    rng = np.random.default_rng(11)
+    n = 0
+    for C in (8, 16, 24, 32, 48, 64):
+        for (k, d) in ((3, 1), (3, 5), (7, 3), (11, 1), (11, 5)):
+            for T in (1, 17, 160, 415, 1000, 1733):
+                if (n % 3) and T in (17, 415):
+                    n += 1
+                    continue
+                B = 1 + n % 2
+                with_res = (n % 2) == 0
+                n += 1
+                assert FC.act_conv_supported(C, k, d, torch.bfloat16)
+                x = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.bfloat16, device=DEV)
+                res = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.bfloat16, device=DEV) if with_res else None
+                xsum = torch.full((B, T, C), 9.0, dtype=torch.bfloat16, device=DEV) if with_res else None
+                bias = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+                alpha = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+                beta = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+                w = torch.tensor(rng.standard_normal((k, C, C)) / np.sqrt(k * C), dtype=torch.bfloat16, device=DEV)
+                y = FC.amp_act_conv_cl(x, T, alpha, beta, taps[0], taps[1], True, w, k, d, bias=bias, res=res, xsum=xsum)
+                torch.cuda.synchronize()
+                xs_ref, y_ref = A.amp_act_conv_cl(
+                    x.double().cpu().numpy(), alpha.double().cpu().numpy(), beta.double().cpu().numpy(), True,
+                    w.double().cpu().numpy(), d, bias.double().cpu().numpy(), None if res is None else res.double().cpu().numpy(),
+                    taps64, taps64, round_act=_bf16_round)
+                tag = f"C={C} k={k} d={d} T={T} B={B} res={with_res}"
+                err = O.max_normalised_error(y.double().cpu().numpy(), y_ref)
+                # the tile is bf16 (a 1-ulp flip of an activated sample moves y by <= 2^-8 |w| |a|), the output is bf16
+                assert err <= TOL_BF16, (tag, err)
+                if with_res:
+                    assert O.max_normalised_error(xsum.double().cpu().numpy(), xs_ref) <= 4e-3, tag
+
+
+def test_act_conv_fused_matches_unfused_pipeline():
+    """Model shapes (stage 4 / 5, one clip): the fused kernel against the activation kernel followed by cuDNN."""
+    import torch.nn.functional as F
+
+    _, FC = _fc()
+    t32, taps, _ = _taps()
+    torch.manual_seed(5)
+    for C, T in ((48, 110208), (24, 220416)):
+        for (k, d) in ((3, 1), (7, 5), (11, 3)):
+            B = 2
+            x = torch.randn(B, T, C, device=DEV, dtype=torch.bfloat16)
+            res = torch.randn(B, T, C, device=DEV, dtype=torch.bfloat16)
+            bias = torch.randn(C, device=DEV) * 0.3
+            alpha = torch.randn(C, device=DEV) * 0.5
+            beta = torch.randn(C, device=DEV) * 0.5
+            conv_w = (torch.randn(C, C, k, device=DEV) / (k * C) ** 0.5).to(torch.bfloat16)
+            w_kcc = conv_w.permute(2, 0, 1).contiguous()
+            xsum_f = torch.empty_like(x)
+            y_f = FC.amp_act_conv_cl(x, T, alpha, beta, taps[0], taps[1], True, w_kcc, k, d, bias=bias, res=res, xsum=xsum_f)
+            xsum_u = torch.empty_like(x)
+            a_u = FC.amp_activation1d_cl(x, T, alpha, beta, taps[0], taps[1], True, bias=bias, res=res, xsum=xsum_u)
+            y_u = F.conv1d(a_u.transpose(1, 2).float(), conv_w.float(), None, 1, (k * d - d) // 2, d).transpose(1, 2)
+            assert torch.equal(xsum_f, xsum_u), (C, k, d)
+            scale = y_u.abs().max().item()
+            err = (y_f.float() - y_u).abs().max().item() / scale
+            assert err <= 6e-3, (C, k, d, err)          # bf16 rounding of y (2^-9 relative) on top of identical bf16 tiles
+            del x, res, y_f, a_u, y_u
+            torch.cuda.empty_cache()

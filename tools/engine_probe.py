@@ -32,10 +32,16 @@ def timeit(fn, n=5):
 for clips in (int(c) for c in os.environ.get("PROBE_CLIPS", "1,4").split(",")):
     B = 2 * clips
     mel = torch.rand(B, 80, 861, device=dev) * 14.5 - 12
+    eng1 = ChannelsLastVocoder(gen, dtype=torch.bfloat16, parallel_resblocks=False)
+    ge1 = GraphedEngine(eng1, B, 861, want_pcm=True)
+    t_e1 = timeit(lambda: ge1(mel))
+    w_e1 = ge1(mel)[0].clone()
+    del ge1
     eng = ChannelsLastVocoder(gen, dtype=torch.bfloat16)
     ge = GraphedEngine(eng, B, 861, want_pcm=True)
     t_e = timeit(lambda: ge(mel))
     w_e = ge(mel)[0].clone()
+    print(f"clips={clips}: serial resblocks {t_e1:.2f} ms, parallel {t_e:.2f} ms, identical {bool(torch.equal(w_e, w_e1))}", flush=True)
     if os.environ.get("PROBE_NCW", "1") == "1":
         gv = GraphedVocoder(gen, B, 861, dtype=torch.bfloat16, device=dev)
         t_v = timeit(lambda: gv(mel.bfloat16()))

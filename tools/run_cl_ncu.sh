@@ -1,6 +1,8 @@
+# ncu evidence for the channels-last kernels (run under gpurun, one GPU)
 set -x
-SWEEP_L=48,72,96,120,144,192 timeout 300 python tools/cl_sweep.py > gpurun_out/cl_sweep3.log 2>&1
-for L in 96 192; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:afa_cl_fwd -s 2 -c 2 -o gpurun_out/cl_L$L -f python tools/cl_ncu_case.py 384 13776 8 $L > gpurun_out/ncu_cl_L$L.log 2>&1
-done
-ls -la gpurun_out/*.ncu-rep
+python tools/engine_pass.py 4 > gpurun_out/engine_pass.log 2>&1 || exit 1
+# launch list of the LAST of 3 eager passes (cuDNN autotune happens in the first): ~330 launches per pass
+PASSES=3 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_cl_launches_engine_bf16_clips4.csv python tools/engine_pass.py 4 > gpurun_out/ncu_launches.log 2>&1
+python tools/cl_ncu_case.py 384 13776 8 0 > /dev/null 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:afa_cl_fwd -s 2 -c 2 -o gpurun_out/r01_cl_fwd_bf16_B8_C384_T13776 -f python tools/cl_ncu_case.py 384 13776 8 0 > gpurun_out/ncu_cl_full.log 2>&1
+ls -la gpurun_out/*.ncu-rep gpurun_out/*.csv | tail -5
