@@ -140,39 +140,57 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_kernel(const __g
         // B x4 = two output-channel tiles: lane -> c_out (lane % 8) + 8 * (lane / 16), k half (lane / 8) % 2;  x2 = one tile
         const int b_row4 = (lane & 7) + ((lane >> 4) << 3), b_colb = ((lane >> 3) & 1) * 16;
         const int b_row2 = lane & 7;
-        for (int mt = warp; mt < n_mt; mt += kAcThreads / 32) {
-            if (t_out0 + mt * 16 >= Tlen) break;
-            float acc[NT8][4];
+        // MT time tiles per sweep: their accumulation chains are independent (mma.sync latency is hidden by
+        // MT * NT8 chains instead of NT8) and they share every weight fragment
+        constexpr int MT = (NT8 <= 2) ? 4 : (NT8 <= 4 ? 3 : 2);
+        for (int mt0 = warp * MT; mt0 < n_mt; mt0 += (kAcThreads / 32) * MT) {
+            if (t_out0 + mt0 * 16 >= Tlen) break;
+            float acc[MT][NT8][4];
 #pragma unroll
-            for (int n = 0; n < NT8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int n = 0; n < NT8; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
             for (int j = 0; j < args.k; ++j) {
-                const uint32_t a_addr = a_base + (uint32_t)((mt * 16 + j * args.dil + a_row) * a_stride_b + a_colb);
                 const uint32_t w_addr = w_base + (uint32_t)(j * C * w_stride_b);
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    uint32_t a0, a1, a2, a3;
-                    ldmatrix_x4(a_addr + ks * 32, a0, a1, a2, a3);
+                    uint32_t af[MT][4];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        // tiles past the end of this CTA's range re-read the last valid one (results discarded)
+                        const int mt = min(mt0 + m, n_mt - 1);
+                        ldmatrix_x4(a_base + (uint32_t)((mt * 16 + j * args.dil + a_row) * a_stride_b + a_colb + ks * 32),
+                                    af[m][0], af[m][1], af[m][2], af[m][3]);
+                    }
 #pragma unroll
                     for (int n = 0; n + 1 < NT8; n += 2) {
                         uint32_t b0, b1, b2, b3;
                         ldmatrix_x4(w_addr + (uint32_t)((n * 8 + b_row4) * w_stride_b + b_colb + ks * 32), b0, b1, b2, b3);
-                        mma_bf16_16816(acc[n], a0, a1, a2, a3, b0, b1);
-                        mma_bf16_16816(acc[n + 1], a0, a1, a2, a3, b2, b3);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            mma_bf16_16816(acc[m][n], af[m][0], af[m][1], af[m][2], af[m][3], b0, b1);
+                            mma_bf16_16816(acc[m][n + 1], af[m][0], af[m][1], af[m][2], af[m][3], b2, b3);
+                        }
                     }
                     if (NT8 & 1) {
                         uint32_t b0, b1;
                         ldmatrix_x2(w_addr + (uint32_t)(((NT8 - 1) * 8 + b_row2) * w_stride_b + b_colb + ks * 32), b0, b1);
-                        mma_bf16_16816(acc[NT8 - 1], a0, a1, a2, a3, b0, b1);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) mma_bf16_16816(acc[m][NT8 - 1], af[m][0], af[m][1], af[m][2], af[m][3], b0, b1);
                     }
                 }
             }
             // C fragment: rows lane / 4 and lane / 4 + 8, channels 8 n + 2 (lane % 4) + {0, 1}
-            const int r0 = t_out0 + mt * 16 + (lane >> 2), r1 = r0 + 8;
             const int cc = 2 * (lane & 3);
 #pragma unroll
-            for (int n = 0; n < NT8; ++n) {
-                if (r0 < Tlen) *reinterpret_cast<__nv_bfloat162*>(yb + (int64_t)r0 * C + n * 8 + cc) = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
-                if (r1 < Tlen) *reinterpret_cast<__nv_bfloat162*>(yb + (int64_t)r1 * C + n * 8 + cc) = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
+            for (int m = 0; m < MT; ++m) {
+                if (mt0 + m >= n_mt) break;
+                const int r0 = t_out0 + (mt0 + m) * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+                for (int n = 0; n < NT8; ++n) {
+                    if (r0 < Tlen) *reinterpret_cast<__nv_bfloat162*>(yb + (int64_t)r0 * C + n * 8 + cc) = __floats2bfloat162_rn(acc[m][n][0], acc[m][n][1]);
+                    if (r1 < Tlen) *reinterpret_cast<__nv_bfloat162*>(yb + (int64_t)r1 * C + n * 8 + cc) = __floats2bfloat162_rn(acc[m][n][2], acc[m][n][3]);
+                }
             }
         }
     }

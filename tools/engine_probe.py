@@ -32,6 +32,12 @@ def timeit(fn, n=5):
 for clips in (int(c) for c in os.environ.get("PROBE_CLIPS", "1,4").split(",")):
     B = 2 * clips
     mel = torch.rand(B, 80, 861, device=dev) * 14.5 - 12
+    eng0 = ChannelsLastVocoder(gen, dtype=torch.bfloat16, fuse_narrow_convs=False)
+    ge0 = GraphedEngine(eng0, B, 861, want_pcm=True)
+    t_e0 = timeit(lambda: ge0(mel))
+    w_e0 = ge0(mel)[0].clone()
+    del ge0
+    print(f"clips={clips}: unfused narrow convs {t_e0:.2f} ms ({clips * 10 / t_e0 * 1e3:.0f} audio-s/s)", flush=True)
     eng1 = ChannelsLastVocoder(gen, dtype=torch.bfloat16, parallel_resblocks=False)
     ge1 = GraphedEngine(eng1, B, 861, want_pcm=True)
     t_e1 = timeit(lambda: ge1(mel))
@@ -41,7 +47,8 @@ for clips in (int(c) for c in os.environ.get("PROBE_CLIPS", "1,4").split(",")):
     ge = GraphedEngine(eng, B, 861, want_pcm=True)
     t_e = timeit(lambda: ge(mel))
     w_e = ge(mel)[0].clone()
-    print(f"clips={clips}: serial resblocks {t_e1:.2f} ms, parallel {t_e:.2f} ms, identical {bool(torch.equal(w_e, w_e1))}", flush=True)
+    print(f"clips={clips}: serial resblocks {t_e1:.2f} ms, parallel {t_e:.2f} ms, identical {bool(torch.equal(w_e, w_e1))}; "
+          f"fused vs unfused max|diff| {float((w_e - w_e0).abs().max()):.3e} (max |w| {float(w_e0.abs().max()):.3e})", flush=True)
     if os.environ.get("PROBE_NCW", "1") == "1":
         gv = GraphedVocoder(gen, B, 861, dtype=torch.bfloat16, device=dev)
         t_v = timeit(lambda: gv(mel.bfloat16()))
