@@ -68,8 +68,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_resblock_mean.restype = i32
         lib.afa_resblock_mean.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), i32, vp, f32, vp, i64, i64, i32, vp]
         lib.afa_tail_fwd_cl.restype = i32
-        lib.afa_tail_fwd_cl.argtypes = [vp, i64, vp, vp, fp, fp, vp, vp, i32, vp, vp, i32, f32, i64, i64, i64,
-                                        i32, i32, vp]
+        lib.afa_tail_fwd_cl.argtypes = [vp, i64, vp, vp, fp, fp, vp, vp, i32, vp, vp, i32, f32, vp, i32, i64,
+                                        i64, i64, i64, i32, i32, vp]
         lib.afa_amp_act_conv_supported.restype = i32
         lib.afa_amp_act_conv_supported.argtypes = [i64, i32, i32, i32]
         lib.afa_amp_act_conv_fwd_cl.restype = i32

@@ -183,7 +183,9 @@ class ChannelsLastVocoder:
         return outs
 
     @torch.no_grad()
-    def __call__(self, mel: torch.Tensor, want_pcm: bool = False, pcm_interleave: int = 2):
+    def __call__(self, mel: torch.Tensor, want_pcm: bool = False, pcm_interleave: int = 2, frame_map=None, t_out: int = 0):
+        """`frame_map` (int32 [B, T_mel], device) + `t_out`: scatter every mel frame's hop of samples to frame
+        frame_map[b, i] of an output of t_out samples that starts as silence (zero-frame restoration)."""
         B = mel.shape[0]
         x = mel.to(self.dtype).transpose(1, 2).contiguous()                  # [B, T_mel, num_mels]
         x = self.pre(x)
@@ -200,8 +202,9 @@ class ChannelsLastVocoder:
             x = FC.resblock_mean([o[0] for o in outs], [o[2] for o in outs], bias_sum, 1.0 / self.num_kernels)
         a = self.post_act
         wave, pcm = FC.tail_cl(x, T, a.alpha, a.beta, a.taps_up, a.taps_down, a.logscale, self.w_post, self.b_post,
-                               use_tanh=self.use_tanh, want_wave=True, want_pcm=want_pcm, pcm_interleave=pcm_interleave)
-        return wave.view(B, 1, T), pcm
+                               use_tanh=self.use_tanh, want_wave=True, want_pcm=want_pcm, pcm_interleave=pcm_interleave,
+                               frame_map=frame_map, hop=T // mel.shape[2] if frame_map is not None else 0, t_out=t_out)
+        return wave.view(B, 1, -1), pcm
 
 
 class GraphedEngine:

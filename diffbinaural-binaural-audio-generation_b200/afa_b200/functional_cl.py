@@ -166,10 +166,13 @@ def resblock_mean(xts, xress, bias_sum=None, scale=None, out=None):
 
 
 def tail_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, w_post, bias_post=None, use_tanh=False,
-            want_wave=True, want_pcm=False, pcm_interleave: int = 2, pcm_scale: float = 32767.0, wave=None, pcm=None):
+            want_wave=True, want_pcm=False, pcm_interleave: int = 2, pcm_scale: float = 32767.0, wave=None, pcm=None,
+            frame_map=None, hop: int = 0, t_out: int = 0):
     """activation_post -> conv_post (C -> 1, k = 7) -> clamp | tanh on channels-last x [B, >=T, C].
 
-    Returns (wave float32 [B, T] or None, pcm int16 [B // il, T, il] or None)."""
+    Returns (wave float32 [B, T_out] or None, pcm int16 [B // il, T_out, il] or None).  With `frame_map` (int32
+    [B, T // hop] on the device) whole frames are scattered into rows of `t_out` samples that start as silence
+    (zero-frame restoration, inference_e2e.py:80-111); otherwise T_out = T."""
     if not x.is_cuda:
         raise RuntimeError("channels-last AMP ops run on CUDA tensors only (there is no CPU fallback)")
     B, _, C = x.shape
@@ -179,18 +182,27 @@ def tail_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, w_post, 
     beta = _f32("beta", beta, C, dev)
     w_post = _f32("w_post", w_post, C * 7, dev)
     bias_post = _f32("bias_post", bias_post, 1, dev)
+    if frame_map is not None:
+        if frame_map.dtype != torch.int32 or not frame_map.is_contiguous() or frame_map.device != dev or hop < 1 \
+                or T % hop or tuple(frame_map.shape) != (B, T // hop):
+            raise RuntimeError(f"frame_map must be a contiguous int32 [{B}, T // hop] tensor on {dev}")
+        t_out = int(t_out)
+        make = torch.zeros                                   # frames nobody writes are the silence
+    else:
+        t_out, hop, make = T, 0, torch.empty
     if want_wave and wave is None:
-        wave = torch.empty(B, T, dtype=torch.float32, device=dev)
+        wave = make(B, t_out, dtype=torch.float32, device=dev)
     if want_pcm and pcm is None:
         if B % pcm_interleave:
             raise RuntimeError(f"batch {B} is not a multiple of pcm_interleave {pcm_interleave}")
-        pcm = torch.empty(B // pcm_interleave, T, pcm_interleave, dtype=torch.int16, device=dev)
+        pcm = make(B // pcm_interleave, t_out, pcm_interleave, dtype=torch.int16, device=dev)
     lib = _lib.load_library()
     with torch.cuda.device_of(x):
         rc = lib.afa_tail_fwd_cl(
             x.data_ptr(), _bstride(x), alpha.data_ptr(), None if beta is None else beta.data_ptr(), taps_up, taps_down,
             w_post.data_ptr(), None if bias_post is None else bias_post.data_ptr(), 1 if use_tanh else 0,
             None if wave is None else wave.data_ptr(), None if pcm is None else pcm.data_ptr(), pcm_interleave,
-            float(pcm_scale), B, C, T, _dtype_code(x), _flags(logscale, beta), torch.cuda.current_stream(dev).cuda_stream)
+            float(pcm_scale), None if frame_map is None else frame_map.data_ptr(), hop, t_out,
+            B, C, T, _dtype_code(x), _flags(logscale, beta), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "afa_tail_fwd_cl")
     return wave, pcm

@@ -446,8 +446,8 @@ int afa_amp_activation1d_fwd_cl(const void* x, int64_t x_bstride, const void* re
 
 int afa_tail_fwd_cl(const void* x, int64_t x_bstride, const float* alpha, const float* beta, const float* taps_up12,
                     const float* taps_down12, const float* w_post, const float* bias_post, int use_tanh, float* wave,
-                    int16_t* pcm, int pcm_interleave, float pcm_scale, int64_t batch, int64_t channels, int64_t T,
-                    int dtype, int flags, void* stream) {
+                    int16_t* pcm, int pcm_interleave, float pcm_scale, const int32_t* frame_map, int hop, int64_t T_out,
+                    int64_t batch, int64_t channels, int64_t T, int dtype, int flags, void* stream) {
     if (!x || !alpha || !taps_up12 || !taps_down12 || !w_post) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
     if (!wave && !pcm) return fail(AFA_ERR_BAD_ARG, "at least one of wave / pcm is required");
     if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
@@ -457,6 +457,14 @@ int afa_tail_fwd_cl(const void* x, int64_t x_bstride, const float* alpha, const 
     if (pcm && (pcm_interleave < 1 || batch % pcm_interleave)) return fail(AFA_ERR_BAD_ARG, "batch=%lld is not a multiple of pcm_interleave=%d", (long long)batch, pcm_interleave);
     if (x_bstride < T * channels) return fail(AFA_ERR_BAD_ARG, "batch stride must cover T*channels elements");
     if (T * channels >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "T*channels exceeds 2^31");
+    if (frame_map) {
+        if (hop < 1 || T % hop) return fail(AFA_ERR_BAD_ARG, "frame_map needs T=%lld to be a whole number of hop=%d frames", (long long)T, hop);
+        if (T_out < T) return fail(AFA_ERR_BAD_ARG, "T_out=%lld is shorter than T=%lld", (long long)T_out, (long long)T);
+    } else {
+        if (T_out == 0) T_out = T;
+        if (T_out != T) return fail(AFA_ERR_BAD_ARG, "T_out must equal T without a frame_map");
+        hop = 1;
+    }
     if (batch == 0 || T == 0) return 0;
     const int L = 98;                                  // walk length (12 n + 2); 92 outputs per segment
     const int64_t nseg = (T + (L - 6) - 1) / (L - 6);
@@ -471,6 +479,10 @@ int afa_tail_fwd_cl(const void* x, int64_t x_bstride, const float* alpha, const 
     a.T = (int32_t)T; a.C = (int32_t)channels; a.L = L; a.flags = flags; a.use_tanh = use_tanh;
     a.il = pcm ? pcm_interleave : 1;
     a.pcm_scale = pcm_scale;
+    a.frame_map = frame_map;
+    a.hop = hop;
+    a.n_frames = (int32_t)(T / hop);
+    a.T_out = T_out;
     const uint32_t wpb = afa::kClThreads / 32;
     const uint32_t grid = (uint32_t)((warps + wpb - 1) / wpb);
     cudaStream_t st = (cudaStream_t)stream;

@@ -61,6 +61,11 @@ struct TailArgs {
     FastDiv nseg;
     int32_t T, C, L, flags, use_tanh, il;
     float pcm_scale;
+    // optional scatter of whole frames (zero-frame restoration, inference_e2e.py:80-111): sample t of batch entry b
+    // lands at frame_map[b * n_frames + t / hop] * hop + t % hop of an output row of T_out samples
+    const int32_t* frame_map;
+    int32_t hop, n_frames;
+    int64_t T_out;
 };
 
 template <typename T> __device__ __forceinline__ float cl_load(const T* p);
@@ -105,6 +110,8 @@ struct TailSink {
     float bias;
     float* wave;      // row of this batch entry (lane 0 stores)
     int16_t* pcm;
+    const int32_t* fmap;   // this batch entry's frame map, or nullptr
+    int hop;
     int il;
     float pcm_scale;
     int use_tanh;
@@ -285,8 +292,13 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
             if (sink->lane == 0 && to < Tlen) {
                 v += sink->bias;
                 v = sink->use_tanh ? tanhf(v) : fminf(fmaxf(v, -1.0f), 1.0f);     // bigvgan.py:382-385
-                if (sink->wave) sink->wave[to] = v;
-                if (sink->pcm) sink->pcm[(int64_t)to * sink->il] = (int16_t)(v * sink->pcm_scale);   // astype("int16") truncates
+                int64_t pos = to;
+                if (sink->fmap) {
+                    const int f = to / sink->hop;
+                    pos = (int64_t)__ldg(sink->fmap + f) * sink->hop + (to - f * sink->hop);
+                }
+                if (sink->wave) sink->wave[pos] = v;
+                if (sink->pcm) sink->pcm[pos * sink->il] = (int16_t)(v * sink->pcm_scale);   // astype("int16") truncates
             }
         }
     };
@@ -384,9 +396,11 @@ __global__ void __launch_bounds__(kClThreads, 4) afa_cl_tail_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 7; ++j) sink.w[j] = (lane < C) ? __ldg(args.w + c * 7 + j) : 0.f;
     sink.bias = args.bias ? __ldg(args.bias) : 0.f;
-    sink.wave = args.wave ? args.wave + (int64_t)b * Tlen : nullptr;
+    sink.wave = args.wave ? args.wave + (int64_t)b * args.T_out : nullptr;
     sink.il = args.il;
-    sink.pcm = args.pcm ? args.pcm + ((int64_t)(b / (uint32_t)args.il) * Tlen) * args.il + (b % (uint32_t)args.il) : nullptr;
+    sink.pcm = args.pcm ? args.pcm + ((int64_t)(b / (uint32_t)args.il) * args.T_out) * args.il + (b % (uint32_t)args.il) : nullptr;
+    sink.fmap = args.frame_map ? args.frame_map + (int64_t)b * args.n_frames : nullptr;
+    sink.hop = args.hop;
     sink.pcm_scale = args.pcm_scale;
     sink.use_tanh = args.use_tanh;
     sink.lane = lane;

@@ -133,12 +133,17 @@ int afa_resblock_mean(const void *const *xt, const void *const *xres, int num_ke
  * (use_tanh = 0) or tanh.  channels <= 32.  Outputs (at least one): wave float32 [batch][T]; pcm int16 with
  * element (b, t) at ((b / pcm_interleave) * T + t) * pcm_interleave + b % pcm_interleave, value
  * (int16)(wave * pcm_scale) truncated toward zero like numpy's astype("int16") (pcm_scale = 32767).
+ * Zero-frame restoration (BigVGAN/inference_e2e.py:38-111, reconstruct_audio_with_silence): with frame_map
+ * (int32 [batch][T / hop], device) sample t of batch entry b is written at frame_map[b][t / hop] * hop + t % hop
+ * of an output row of T_out samples (wave [batch][T_out], pcm [batch / il][T_out][il]); the caller zero-fills the
+ * outputs first (the silence).  frame_map = NULL: identity, T_out = T (or 0).
  */
 int afa_tail_fwd_cl(const void *x, int64_t x_bstride,
                     const float *alpha, const float *beta,
                     const float *taps_up12, const float *taps_down12,
                     const float *w_post, const float *bias_post, int use_tanh,
                     float *wave, int16_t *pcm, int pcm_interleave, float pcm_scale,
+                    const int32_t *frame_map, int hop, int64_t T_out,
                     int64_t batch, int64_t channels, int64_t T,
                     int dtype, int flags, void *stream);
 

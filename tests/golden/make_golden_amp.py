@@ -13,6 +13,7 @@ carry plain `weight` / `bias` arrays.
 """
 from __future__ import annotations
 
+import importlib.util
 import json
 import os
 import sys
@@ -151,6 +152,26 @@ def main():
         out[f"{name}/meta"] = np.array([int(resblock)], dtype=np.int64)
         for n, p in gen.state_dict().items():
             out[f"{name}/sd/{n}"] = p.numpy()
+
+    # ---- zero-frame handling of the inference script                                     inference_e2e.py:38-111
+    spec = importlib.util.spec_from_file_location("ref_inference_e2e", os.path.join(BIG, "inference_e2e.py"))
+    inf = importlib.util.module_from_spec(spec)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(inf)
+        rng = np.random.default_rng(77)
+        for name, t_mel, zero_frames in (("zf_some", 40, [0, 1, 7, 8, 9, 23, 39]), ("zf_none", 17, []), ("zf_all_but_one", 9, [0, 1, 2, 3, 5, 6, 7, 8])):
+            mel = (rng.random((80, t_mel)) * 14.5 - 12.0).astype(np.float32)
+            mel[:, zero_frames] = 0.0
+            filt, mask, idx = inf.detect_and_exclude_zero_frames(mel)
+            audio = rng.standard_normal(filt.shape[1] * 256).astype(np.float32)
+            restored = inf.reconstruct_audio_with_silence(audio, mask, idx, 256, t_mel * 256)
+            out[f"{name}/mel"] = mel
+            out[f"{name}/filtered"] = np.ascontiguousarray(filt)
+            out[f"{name}/zero_mask"] = mask
+            out[f"{name}/nonzero_indices"] = np.asarray(idx, dtype=np.int64)
+            out[f"{name}/audio"] = audio
+            out[f"{name}/restored"] = restored
 
     path = os.path.join(HERE, "amp_golden.npz")
     np.savez_compressed(path, **out)

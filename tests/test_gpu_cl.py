@@ -413,3 +413,32 @@ def test_act_conv_fused_matches_unfused_pipeline():
             assert err <= 6e-3, (C, k, d, err)          # bf16 rounding of y (2^-9 relative) on top of identical bf16 tiles
             del x, res, y_f, a_u, y_u
             torch.cuda.empty_cache()
+
+
+def test_zero_frame_restoration_in_the_tail(amp_golden, true_fp32_convs):
+    """inference_e2e.py:140-201 for one clip: zero frames are dropped before the generator and come back as silence.
+    The tail kernel scatters hops to their frames (frame_map); must equal the reference's host-side restoration of the
+    un-mapped result bit for bit (index work), for equal and for different numbers of kept frames left / right."""
+    from afa_b200 import ingest
+
+    c = amp_golden["gen_small_1"]
+    h = dict(upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=16, resblock="1",
+             resblock_dilation_sizes=[[1, 3, 5]] * 3)
+    gen, eng = _engine_from_sd(c["sd"], h, torch.float32)
+    hop = 8
+    rng = np.random.default_rng(3)
+    t_mel = 30
+    for zl, zr in (([0, 5, 6, 29], [1, 2, 17, 18]), ([3, 4], [9]), ([], [])):
+        ml = (rng.random((80, t_mel)) * 14.5 - 12.0).astype(np.float32)
+        mr = (rng.random((80, t_mel)) * 14.5 - 12.0).astype(np.float32)
+        ml[:, zl] = 0.0
+        mr[:, zr] = 0.0
+        pcm = ingest.vocode_binaural(eng, ml, mr).cpu().numpy()
+        assert pcm.shape == (t_mel * hop, 2) and pcm.dtype == np.int16
+        ref = np.zeros((t_mel * hop, 2), dtype=np.int16)
+        for ch, m in enumerate((ml, mr)):
+            f, mask, idx = ingest.detect_zero_frames(m)
+            _, mono = eng(torch.tensor(f[None], device=DEV), want_pcm=True, pcm_interleave=1)
+            ref[:, ch] = ingest.restore_silence_host(mono[0, :, 0].cpu().numpy(), idx, hop, t_mel * hop)
+            assert np.all(ref[np.repeat(mask, hop), ch] == 0)
+        assert np.array_equal(pcm, ref), (zl, zr)

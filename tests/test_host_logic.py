@@ -64,9 +64,10 @@ def test_argument_errors_need_no_gpu(lib):
     assert cl(vp(16), 32, None, 0, None, None, 0, vp(32), 32, 7, vp(64), vp(64), taps, taps, 1, 4, 8, 0, 0, None) == -1    # y_tpad < T
     assert cl(vp(16), 32, None, 0, None, None, 0, vp(32), 32, 0, vp(64), vp(64), taps, taps, 1, 4, 8, 3, 0, None) == -2
     tail = lib.afa_tail_fwd_cl
-    assert tail(vp(16), 320, vp(64), vp(64), taps, taps, vp(64), None, 0, None, None, 2, 32767.0, 2, 40, 8, 0, 0, None) == -1   # no output
-    assert tail(vp(16), 320, vp(64), vp(64), taps, taps, vp(64), None, 0, vp(128), None, 2, 32767.0, 2, 40, 8, 0, 0, None) == -1  # channels > 32
-    assert tail(vp(16), 64, vp(64), vp(64), taps, taps, vp(64), None, 0, None, vp(128), 2, 32767.0, 3, 8, 8, 0, 0, None) == -1    # batch % interleave
+    assert tail(vp(16), 320, vp(64), vp(64), taps, taps, vp(64), None, 0, None, None, 2, 32767.0, None, 0, 0, 2, 40, 8, 0, 0, None) == -1   # no output
+    assert tail(vp(16), 320, vp(64), vp(64), taps, taps, vp(64), None, 0, vp(128), None, 2, 32767.0, None, 0, 0, 2, 40, 8, 0, 0, None) == -1  # channels > 32
+    assert tail(vp(16), 64, vp(64), vp(64), taps, taps, vp(64), None, 0, None, vp(128), 2, 32767.0, None, 0, 0, 3, 8, 8, 0, 0, None) == -1    # batch % interleave
+    assert tail(vp(16), 64, vp(64), vp(64), taps, taps, vp(64), None, 0, vp(128), None, 2, 32767.0, vp(256), 3, 8, 2, 8, 8, 0, 0, None) == -1   # T % hop
     arr = (vp * 2)(vp(16), vp(32))
     assert lib.afa_resblock_mean(arr, arr, 5, None, 1.0, vp(64), 4, 4, 0, None) == -1
     assert lib.afa_resblock_mean(arr, arr, 2, None, 1.0, vp(64), 0, 4, 0, None) == 0                                               # empty: no-op

@@ -109,3 +109,31 @@ def test_conv_restatements_against_torch():
         b = rng.standard_normal(co)
         ref = F.conv_transpose1d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), u, (k - u) // 2).numpy()
         assert np.abs(A.conv_transpose1d(x, w, b, u, (k - u) // 2) - ref).max() <= 1e-12
+
+
+def test_zero_frame_handling_matches_reference(amp_golden):
+    """afa_b200/ingest.py against the reference's own detect_and_exclude_zero_frames / reconstruct_audio_with_silence
+    (inference_e2e.py:38-111) outputs: index and copy work, so bit-exact."""
+    from afa_b200 import ingest
+
+    for name in ("zf_some", "zf_none", "zf_all_but_one"):
+        c = amp_golden[name]
+        filt, mask, idx = ingest.detect_zero_frames(c["mel"])
+        assert np.array_equal(filt, c["filtered"]) and np.array_equal(mask, c["zero_mask"]), name
+        assert np.array_equal(idx, c["nonzero_indices"]), name
+        restored = ingest.restore_silence_host(c["audio"], idx, 256, c["mel"].shape[1] * 256)
+        assert restored.dtype == c["restored"].dtype and np.array_equal(restored, c["restored"]), name
+
+
+def test_wav_roundtrip(tmp_path):
+    from scipy.io import wavfile
+
+    from afa_b200 import ingest
+
+    pcm = (np.random.default_rng(1).integers(-32767, 32767, size=(1000, 2))).astype(np.int16)
+    path = str(tmp_path / "x.wav")
+    ingest.write_wav(path, 22050, pcm)
+    sr, back = wavfile.read(path)
+    assert sr == 22050 and back.dtype == np.int16 and np.array_equal(back, pcm)
+    np.save(str(tmp_path / "m.npy"), np.zeros((1, 80, 7), dtype=np.float64))
+    assert ingest.load_mel_npy(str(tmp_path / "m.npy")).shape == (80, 7)
