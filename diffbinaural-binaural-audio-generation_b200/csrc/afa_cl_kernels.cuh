@@ -29,6 +29,10 @@
 namespace afa {
 
 constexpr int kClS = 12;        // ring size = steps per rolled-loop trip = prefetch distance
+// 1: every request of a group also asks L2 for the group after it (prefetch.global.L2; interior walks only)
+#ifndef AFA_CL_L2_PREFETCH
+#define AFA_CL_L2_PREFETCH 0
+#endif
 constexpr int kClThreads = 128;
 
 struct ClArgs {
@@ -166,6 +170,14 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
                 xq[i] = raw::load(p);
                 p += Cs;
                 if (RES) { rq[i] = raw::load(q); q += Cs; }
+            }
+            if (AFA_CL_L2_PREFETCH && SINK == 0) {     // p / q now point at the group after the one just requested
+#pragma unroll
+                for (int i = 0; i < S; i += AFA_CL_L2_PREFETCH) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                    p += AFA_CL_L2_PREFETCH * Cs;
+                    if (RES) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); q += AFA_CL_L2_PREFETCH * Cs; }
+                }
             }
         } else {
 #pragma unroll
@@ -361,7 +373,7 @@ __global__ void __launch_bounds__(kClThreads, RES ? 4 : 5) afa_cl_fwd_kernel(con
     const ChanParams cp = load_chan_params(args.alpha, args.beta, (int)c, args.flags);
     const float bias = args.bias ? __ldg(args.bias + c) : 0.f;
 
-    const bool fast = !active || (t0 >= 5 && t0 + L + 5 < Tlen);
+    const bool fast = !active || (t0 >= 5 && t0 + L + 5 + (AFA_CL_L2_PREFETCH ? kClS : 0) < Tlen);
     const uint32_t amask = __ballot_sync(0xffffffffu, active);
     if (__all_sync(0xffffffffu, fast)) {
         if (active) walk_cl<T, 0, RES, 0>(px, pr, ps, py, Cs, t0, L, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask);
