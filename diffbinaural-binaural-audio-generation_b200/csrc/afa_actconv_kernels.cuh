@@ -196,4 +196,203 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_kernel(const __g
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Same kernel with phase 2 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// ncu on the mma.sync version (C = 24, k = 7): tensor pipe 28 % + FMA pipe 40 % busy, back to back -- legacy
+// HMMA.16816 retires ~1000 MAC/clk/SM on this part, an eighth of the tcgen05 rate, so the "side job" was a third
+// of the kernel.  Here one thread issues, per block of 128 output rows, k * KS instructions
+// tcgen05.mma.cta_group::1.kind::f16  (M = 128 time steps, N = c_out padded to 16, K = 16 input channels):
+//   * operands straight from shared memory through matrix descriptors, K-major, no swizzle: the canonical layout
+//     ((8, m), 2) : ((16 B, SBO), LBO) with SBO = 128 B makes a row's address LINEAR in the row index
+//     (row * 16 B + k_chunk * LBO), so phase 1 writes the tile as column strips [c / 8][row][8] and the k taps of the
+//     (dilated) convolution are nothing but descriptor start addresses shifted by j * dilation rows;
+//   * all row blocks of the tile are issued up front into disjoint TMEM column ranges (n_mb * NPAD <= 256 columns),
+//     one tcgen05.commit -> mbarrier per block; the 8 warps drain finished blocks (tcgen05.ld 32x32b: a thread
+//     receives one time step's c_out accumulators = one contiguous row of y) while later blocks still compute.
+// ------------------------------------------------------------------------------------------------
+struct ActConvTcArgs {
+    ActConvArgs a;
+    int32_t rows_alloc;   // rows per column strip of the activation tile (odd: strips fall into different banks)
+    int32_t n_mb;         // blocks of 128 output rows per tile
+    int32_t tmem_cols;    // power of two >= n_mb * NPAD
+};
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version = 1 [46,48), no swizzle
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+// bounded wait: a wrong descriptor must end in a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();
+    }
+}
+
+constexpr int kAcMaxBlocks = 8;
+#ifndef AFA_TC_DEBUG
+#define AFA_TC_DEBUG 0
+#endif
+
+// NPAD: c_out padded to a multiple of 16 (the MMA's N);  KS: input-channel steps of 16
+template <bool RES, int NPAD, int KS>
+__global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_tc_kernel(const __grid_constant__ ActConvTcArgs targs) {
+    using T = __nv_bfloat16;
+    const ActConvArgs& args = targs.a;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NSTRIP = KS * 2;                                   // 16-byte column strips (8 channels each)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // [kAcMaxBlocks]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 64);
+    T* wsm = reinterpret_cast<T*>(smem_raw + 128);                   // [k][NSTRIP][NPAD][8]
+    T* asm_ = wsm + (size_t)args.k * NSTRIP * NPAD * 8;              // [NSTRIP][rows_alloc][8]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = args.C, Tlen = args.T;
+    const int tslot = (int)(blockIdx.x / (uint32_t)args.batch);
+    const int b = (int)(blockIdx.x - (uint32_t)tslot * (uint32_t)args.batch);
+    const int tile = tslot == 0 ? args.n_tiles - 1 : tslot - 1;
+    const int P = (args.k / 2) * args.dil;
+    const int t_out0 = tile * args.TT;
+    const int tile_t0 = t_out0 - P;
+    const int rows_alloc = targs.rows_alloc;
+
+    // ---- TMEM allocation (warp 0), mbarriers, weights in the B layout, zero padding
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)targs.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < targs.n_mb; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    {
+        const int cstrips = C / 8;
+        const int total = args.k * NSTRIP * NPAD;
+        for (int i = tid; i < total; i += kAcThreads) {
+            const int n = i % NPAD, kc = (i / NPAD) % NSTRIP, j = i / (NPAD * NSTRIP);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (n < C && kc < cstrips) v = __ldg(reinterpret_cast<const uint4*>(args.w + ((size_t)j * C + n) * C + kc * 8));
+            *reinterpret_cast<uint4*>(wsm + (size_t)i * 8) = v;
+        }
+        for (int kc = cstrips; kc < NSTRIP; ++kc)
+            for (int r = tid; r < rows_alloc; r += kAcThreads)
+                *reinterpret_cast<uint4*>(asm_ + ((size_t)kc * rows_alloc + r) * 8) = make_uint4(0, 0, 0, 0);
+    }
+
+    // ---- phase 1: the activation walk of (sub-segment, channel) pairs into the column strips
+    {
+        const int s = tid / C, c = tid - s * C;
+        const bool active = s < args.n_sub;
+        const int t0 = tile_t0 + s * args.Lsub;
+        const bool fast = !active || (t0 >= 5 && t0 + args.Lsub + 5 < Tlen);
+        const bool all_fast = __syncthreads_and(fast ? 1 : 0) != 0;
+        if (active) {
+            const T* px = static_cast<const T*>(args.x) + (int64_t)b * args.x_bs + c;
+            const T* pr = RES ? static_cast<const T*>(args.res) + (int64_t)b * args.res_bs + c : nullptr;
+            T* ps = RES ? static_cast<T*>(args.xsum) + (int64_t)b * args.xsum_bs + c : nullptr;
+            const ChanParams cp = load_chan_params(args.alpha, args.beta, c, args.flags);
+            const float bias = args.bias ? __ldg(args.bias + c) : 0.f;
+            TileSink ts;
+            ts.col = asm_ + ((size_t)(c >> 3) * rows_alloc) * 8 + (c & 7);
+            ts.stride = 8;
+            ts.tile_t0 = tile_t0;
+            ts.own_lo = t_out0;
+            ts.own_hi = min(t_out0 + args.TT, Tlen);
+            const uint32_t amask = __activemask();
+            if (all_fast) walk_cl<T, 0, RES, 2>(px, pr, ps, nullptr, C, t0, args.Lsub, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask, &ts);
+            else walk_cl<T, 1, RES, 2>(px, pr, ps, nullptr, C, t0, args.Lsub, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask, &ts);
+        }
+    }
+    // generic-proxy writes of the tiles -> visible to the tensor core's async proxy; TMEM address -> everyone
+    fence_proxy_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- phase 2, issue: all row blocks up front; block mb is issued by lane 0 of warp mb (one thread per MMA stream,
+    //      eight streams side by side -- a single issuer spent ~100 cycles per MMA building descriptors and was the
+    //      longest thing in the kernel at k = 11).  Descriptors differ only in their start-address field: add rows.
+    if (lane == 0 && warp < targs.n_mb && !(AFA_TC_DEBUG & 1)) {
+        // cute::UMMA::InstrDescriptor: D = f32 [4,6) = 1, A = bf16 [7,10) = 1, B = bf16 [10,13) = 1, both K-major, N >> 3 [17,23), M >> 4 [24,29)
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t lbo_a = (uint32_t)rows_alloc * 16u, lbo_b = (uint32_t)NPAD * 16u;
+        const int mb = warp;
+        const uint64_t a0 = umma_desc_kmajor(smem_u32(asm_) + (uint32_t)(mb * 128) * 16u, lbo_a);
+        const uint64_t b0 = umma_desc_kmajor(smem_u32(wsm), lbo_b);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(mb * NPAD);
+        uint32_t a_row = 0, b_row = 0;                               // start-address offsets in 16-byte units
+        for (int j = 0; j < args.k; ++j) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+                umma_bf16_ss(d_tmem, a0 + (uint64_t)(a_row + (uint32_t)(ks * 2) * (uint32_t)rows_alloc),
+                             b0 + (uint64_t)(b_row + (uint32_t)(ks * 2 * NPAD)), idesc, (j | ks) != 0 ? 1u : 0u);
+            a_row += (uint32_t)args.dil;
+            b_row += (uint32_t)(NSTRIP * NPAD);
+        }
+        umma_commit(&bars[mb]);
+    }
+    __syncwarp();
+
+    // ---- phase 2, drain: warp w reads TMEM lanes 32 (w % 4) ..; the two warp groups take alternate row blocks
+    {
+        const int q = warp & 3, grp = warp >> 2;
+        T* yb = static_cast<T*>(args.y) + (int64_t)b * args.y_bs;
+        for (int mb = grp; mb < targs.n_mb; mb += 2) {
+            if (!(AFA_TC_DEBUG & 1)) mbar_wait_bounded(&bars[mb], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r = mb * 128 + q * 32 + lane;                  // output row within the tile = TMEM lane
+            const int t = t_out0 + r;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * NPAD);
+            uint32_t v[NPAD];
+#pragma unroll
+            for (int c8 = 0; c8 < NPAD / 8; ++c8) if (!(AFA_TC_DEBUG & 2)) tmem_ld8(taddr + c8 * 8, *reinterpret_cast<uint32_t(*)[8]>(&v[c8 * 8]));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (r < args.TT && t < Tlen && !(AFA_TC_DEBUG & 4)) {
+                T* dst = yb + (int64_t)t * C;
+#pragma unroll
+                for (int c8 = 0; c8 < NPAD / 8; ++c8) {
+                    if (c8 * 8 < C) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[c8 * 8 + 2 * e]), __uint_as_float(v[c8 * 8 + 2 * e + 1]));
+                            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(dst + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)targs.tmem_cols) : "memory");
+    }
+}
+
 }  // namespace afa

@@ -22,6 +22,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_tune_chunks[3] = {0, 0, 0};   // [2]: channels-last walk, segment length in units of 12 samples
 int g_tune_threads[3] = {0, 0, 0};
+int g_actconv_path = 1;   // fused activation+convolution: 1 = tcgen05 (falls back to mma.sync when the tile does not fit), 0 = mma.sync
 
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 int fail(int code, const char* fmt, ...) {
@@ -249,12 +250,17 @@ const char* afa_last_error(void) { return g_err; }
 int64_t afa_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int afa_set_tuning(int which, int chunks, int threads) {
+    if (which == 3) {   // fused activation+convolution: 1 = tcgen05 (default), 0 = legacy mma.sync
+        if (chunks != 0 && chunks != 1) return fail(AFA_ERR_BAD_ARG, "tensor path must be 0 (mma.sync) or 1 (tcgen05)");
+        g_actconv_path = chunks;
+        return 0;
+    }
     if (which == 2) {   // channels-last walk: segment length = 12 * chunks + 2 samples
         if (chunks < 0 || chunks > 4096) return fail(AFA_ERR_BAD_ARG, "channels-last segment length must be 12 * [1, 4096] + 2");
         g_tune_chunks[2] = chunks;
         return 0;
     }
-    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd) or 2 (channels-last fwd)");
+    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd) or 3 (fused conv tensor path)");
     bool ok = chunks == 0;
 #define X(CH) ok = ok || chunks == CH;
     AFA_CHUNK_LIST(X)
@@ -566,6 +572,42 @@ int launch_actconv_t(const afa::ActConvArgs& a, size_t smem, uint32_t grid, cuda
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_actconv_kernel launch");
 }
 
+template <bool RES, int NPAD, int KS>
+int launch_actconv_tc_t(const afa::ActConvTcArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
+    auto k = afa::afa_cl_actconv_tc_kernel<RES, NPAD, KS>;
+    static thread_local const void* configured[8] = {nullptr};
+    static thread_local int configured_dev[8] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    bool done = false;
+    for (int i = 0; i < 8; ++i) done = done || (configured[i] == (const void*)k && configured_dev[i] == dev + 1);
+    if (!done) {
+        e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        for (int i = 0; i < 8; ++i)
+            if (!configured[i]) { configured[i] = (const void*)k; configured_dev[i] = dev + 1; break; }
+    }
+    k<<<grid, afa::kAcThreads, smem, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_actconv_tc_kernel launch");
+}
+
+template <bool RES>
+int launch_actconv_tc(const afa::ActConvTcArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
+    switch (a.a.C) {
+        case 8: return launch_actconv_tc_t<RES, 16, 1>(a, smem, grid, st);
+        case 16: return launch_actconv_tc_t<RES, 16, 1>(a, smem, grid, st);
+        case 24: return launch_actconv_tc_t<RES, 32, 2>(a, smem, grid, st);
+        case 32: return launch_actconv_tc_t<RES, 32, 2>(a, smem, grid, st);
+        case 48: return launch_actconv_tc_t<RES, 48, 3>(a, smem, grid, st);
+        case 64: return launch_actconv_tc_t<RES, 64, 4>(a, smem, grid, st);
+    }
+    return fail(AFA_ERR_BAD_ARG, "fused activation+convolution is compiled for channels in {8,16,24,32,48,64}, got %d", a.a.C);
+}
+
+
 template <bool RES>
 int launch_actconv(const afa::ActConvArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
     switch (a.C) {
@@ -623,6 +665,36 @@ int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, i
     a.n_sub = afa::kAcThreads / C;                                   // (sub-segment, channel) pairs fill the CTA
     if (a.n_sub > 12) a.n_sub = 12;
     const int cpad = (C + 15) / 16 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    // tcgen05 path: column-strip tile, all blocks of 128 output rows issued up front into TMEM
+    if (g_actconv_path == 1 && (((uintptr_t)y & 15) == 0) && (y_bstride % 8 == 0)) {
+        const int npad = C <= 16 ? 16 : cpad;
+        const int nstrip = cpad / 8;
+        const size_t wb = (size_t)kernel_size * nstrip * npad * 16;
+        for (int n = 7; n >= 3; --n) {
+            const int lsub = 12 * n + 2;
+            const int a_rows = a.n_sub * lsub;
+            if ((int64_t)a_rows - 2 * P > 2 * T && n > 3) continue;       // short rows: keep enough tiles
+            const int tt = (a_rows - 2 * P) / 16 * 16;
+            if (tt < 16) break;
+            const int n_mb = (tt + 127) / 128;
+            const int rows_alloc = (n_mb * 128 + 2 * P > a_rows ? n_mb * 128 + 2 * P : a_rows) | 1;   // MMA reach and phase-1 rows
+            const size_t smem_tc = 128 + wb + (size_t)nstrip * rows_alloc * 16;
+            if (n_mb > afa::kAcMaxBlocks || n_mb * npad > 512 || smem_tc > 110 * 1024) continue;
+            afa::ActConvTcArgs ta;
+            a.Lsub = lsub; a.a_rows = a_rows; a.TT = tt; a.a_stride = 8; a.w_stride = 8;
+            a.n_tiles = (int32_t)((T + tt - 1) / tt);
+            ta.a = a;
+            ta.rows_alloc = rows_alloc;
+            ta.n_mb = n_mb;
+            int cols = 32;
+            while (cols < n_mb * npad) cols *= 2;
+            ta.tmem_cols = cols;
+            const int64_t grid_tc = (int64_t)a.n_tiles * batch;
+            if (grid_tc >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "too many tiles");
+            return res ? launch_actconv_tc<true>(ta, smem_tc, (uint32_t)grid_tc, st) : launch_actconv_tc<false>(ta, smem_tc, (uint32_t)grid_tc, st);
+        }
+    }
     a.a_stride = cpad + 8;
     a.w_stride = cpad + 8;
     // sub-segment length 12 n + 2: as long as two CTAs still fit in shared memory (about 100 KB each), shorter
@@ -639,7 +711,6 @@ int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, i
     const size_t smem = w_bytes + (size_t)a.a_rows * a.a_stride * 2;
     const int64_t grid = (int64_t)a.n_tiles * batch;
     if (grid >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "too many tiles");
-    cudaStream_t st = (cudaStream_t)stream;
     return res ? launch_actconv<true>(a, smem, (uint32_t)grid, st) : launch_actconv<false>(a, smem, (uint32_t)grid, st);
 }
 
