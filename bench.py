@@ -309,9 +309,11 @@ def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: i
     t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the only collective of the inference path: gather finished PCM (one batch per rank here)
-        outs = [torch.empty_like(ge.static_pcm) for _ in range(world)]
-        dist.all_gather(outs, ge.static_pcm)
+        # the only collective of the inference path: gather finished PCM (one batch per rank here); NCCL has no int16,
+        # an interleaved stereo sample pair travels as one int32
+        pcm32 = ge.static_pcm.view(torch.int32)
+        outs = [torch.empty_like(pcm32) for _ in range(world)]
+        dist.all_gather(outs, pcm32)
     ms = float(t.item())
     out = {
         "audio_sec_per_sec": round(total_clips * 10.0 / (ms * 1e-3), 1), "unit": "binaural audio-s per wall-s",

@@ -40,8 +40,13 @@ def gather_waveforms(local: torch.Tensor, n_items: int, rank: int, world_size: i
         pad = torch.zeros((n_max - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         padded = torch.cat([local, pad], dim=0)
     padded = padded.contiguous()
-    bufs = [torch.empty_like(padded) for _ in range(world_size)]
-    dist.all_gather(bufs, padded, group=group)
+    # NCCL has no 16-bit integer type: interleaved stereo int16 PCM [n, T, 2] travels as one int32 per sample pair
+    as_pairs = padded.dtype == torch.int16 and padded.dim() >= 1 and padded.shape[-1] % 2 == 0
+    wire = padded.view(torch.int32) if as_pairs else padded
+    bufs = [torch.empty_like(wire) for _ in range(world_size)]
+    dist.all_gather(bufs, wire, group=group)
+    if as_pairs:
+        bufs = [b.view(torch.int16) for b in bufs]
     out = torch.empty((n_items,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     for r in range(world_size):
         idx = shard_indices(n_items, r, world_size)

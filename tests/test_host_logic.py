@@ -225,6 +225,10 @@ def _gather_worker(rank, world, port, n_items, out_dir):
     local = torch.stack([torch.full((2, 5), float(i)) + torch.arange(5.0) for i in mine]) if mine else torch.zeros(0, 2, 5)
     full = gather_waveforms(local, n_items, rank, world)
     torch.save(full, os.path.join(out_dir, f"r{rank}.pt"))
+    # interleaved int16 stereo PCM [n, T, 2] (what the channels-last engine's tail writes) travels as int32 pairs
+    pcm = torch.stack([(torch.arange(12).reshape(6, 2) * (i + 1) - 7 * i).to(torch.int16) for i in mine]) if mine \
+        else torch.zeros(0, 6, 2, dtype=torch.int16)
+    torch.save(gather_waveforms(pcm, n_items, rank, world), os.path.join(out_dir, f"p{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -235,6 +239,9 @@ def test_clip_sharding_gather_two_ranks_gloo(tmp_path, n_items):
     world, port = 2, _free_port()
     mp.spawn(_gather_worker, args=(world, port, n_items, str(tmp_path)), nprocs=world, join=True)
     expect = torch.stack([torch.full((2, 5), float(i)) + torch.arange(5.0) for i in range(n_items)])
+    expect_pcm = torch.stack([(torch.arange(12).reshape(6, 2) * (i + 1) - 7 * i).to(torch.int16) for i in range(n_items)])
     for r in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert torch.equal(got, expect)
+        got_pcm = torch.load(os.path.join(str(tmp_path), f"p{r}.pt"))
+        assert got_pcm.dtype == torch.int16 and torch.equal(got_pcm, expect_pcm)
