@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__  # noqa
 import torch
 import torch.nn as nn
-from afa_b200 import functional as F_afa, functional_cl as FC
+from afa_b200 import _lib, functional as F_afa, functional_cl as FC
 from afa_b200.engine import _Conv
 from afa_b200.modules import kaiser_sinc_filter1d
 
@@ -14,6 +14,7 @@ torch.backends.cudnn.benchmark = True
 B = int(os.environ.get("SWEEP_B", "8"))
 h = F_afa.host_taps(kaiser_sinc_filter1d(0.25, 0.3, 12))
 dt = torch.bfloat16
+_lib.set_tuning(3, int(os.environ.get('TC_PATH', '1')))
 
 
 def timeit(fn, n=10):
