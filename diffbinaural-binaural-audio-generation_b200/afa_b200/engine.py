@@ -101,7 +101,10 @@ class ChannelsLastVocoder:
                 blocks.append(its)
             up_bias = None if up.bias is None else up.bias.detach().float().contiguous()
             self.stages.append(dict(
-                w=_cl_weight(up.weight, dtype), bias=up_bias, k=up.kernel_size[0], u=up.stride[0], p=up.padding[0],
+                # upsamplers run along W ([B, C, 1, T]): cuDNN's strided-dgrad kernels are 2-5x faster in this orientation
+                # than along H (measured: 3.0 -> 0.5 ms per 4-clip pass), the opposite of the stride-1 convolutions
+                w=up.weight.detach().to(dtype).unsqueeze(2).contiguous(memory_format=torch.channels_last),
+                bias=up_bias, k=up.kernel_size[0], u=up.stride[0], p=up.padding[0],
                 cout=up.out_channels, blocks=blocks))
         self.post_act = _Act(gen.activation_post)
         self.w_post = gen.conv_post.weight.detach().float().reshape(-1, 7).contiguous()       # [1, C, 7] -> [C, 7]
@@ -193,9 +196,9 @@ class ChannelsLastVocoder:
             x = x + self.pre_bias
         T = x.shape[1]
         for st in self.stages:
-            x4 = x.view(B, T, 1, x.shape[2]).permute(0, 3, 1, 2)             # logical [B, C, T, 1]
-            y4 = F.conv_transpose2d(x4, st["w"], None, (st["u"], 1), (st["p"], 0))
-            T = y4.shape[2]
+            x4 = x.view(B, 1, T, x.shape[2]).permute(0, 3, 1, 2)             # logical [B, C, 1, T]
+            y4 = F.conv_transpose2d(x4, st["w"], None, (1, st["u"]), (0, st["p"]))
+            T = y4.shape[3]
             x = y4.permute(0, 2, 3, 1).reshape(B, T, st["cout"])
             outs = self._resblocks(st, x, T)
             bias_sum = self._sum(*[b for o in outs for b in (o[1], o[3])])
@@ -215,16 +218,23 @@ class GraphedEngine:
         self.engine = engine
         dev = engine.device
         self.static_in = torch.zeros(batch, engine.h["num_mels"], t_mel, device=dev, dtype=torch.float32)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):                                   # warm-up: cuDNN algorithm picks, bias sums
-                engine(self.static_in, want_pcm=want_pcm, pcm_interleave=pcm_interleave)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_wave, self.static_pcm = engine(self.static_in, want_pcm=want_pcm, pcm_interleave=pcm_interleave)
+        # cuDNN picks its convolution algorithms by timing them (benchmark mode) during the warm-up passes; the capture
+        # then replays those choices.  The global switch is restored afterwards.
+        old_benchmark = torch.backends.cudnn.benchmark
+        torch.backends.cudnn.benchmark = True
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):                                   # warm-up: cuDNN algorithm picks, bias sums
+                    engine(self.static_in, want_pcm=want_pcm, pcm_interleave=pcm_interleave)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_wave, self.static_pcm = engine(self.static_in, want_pcm=want_pcm, pcm_interleave=pcm_interleave)
+        finally:
+            torch.backends.cudnn.benchmark = old_benchmark
 
     def __call__(self, mel: torch.Tensor):
         self.static_in.copy_(mel, non_blocking=True)

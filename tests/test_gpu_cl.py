@@ -308,9 +308,17 @@ def test_engine_vs_ncw_harness_model_config(resblock, activation, true_fp32_conv
     assert wave.shape == y_ref.shape == (2, 1, 23 * 256)
     err = (wave - y_ref).abs().max().item() / scale
     assert err <= 2e-4, err
-    ge = GraphedEngine(eng, 2, 23, want_pcm=True)
-    w_g, p_g = ge(mel)
-    assert torch.equal(w_g, wave)
+    # graph capture picks cuDNN algorithms in benchmark mode: compare against an eager pass made under the same mode
+    old_benchmark = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        wave_b, _ = eng(mel)
+        ge = GraphedEngine(eng, 2, 23, want_pcm=True)
+        w_g, p_g = ge(mel)
+    finally:
+        torch.backends.cudnn.benchmark = old_benchmark
+    assert torch.equal(w_g, wave_b)
+    assert (wave_b - y_ref).abs().max().item() / scale <= 2e-4
     eng_b = ChannelsLastVocoder(gen, dtype=torch.bfloat16)
     w_b, _ = eng_b(mel)
     # bf16 through ~110 layers with 6x-amplified weights: judge by the relative L2 error, bound the worst sample loosely
