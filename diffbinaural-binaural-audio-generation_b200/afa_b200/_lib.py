@@ -73,7 +73,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_amp_act_conv_supported.restype = i32
         lib.afa_amp_act_conv_supported.argtypes = [i64, i32, i32, i32]
         lib.afa_amp_act_conv_fwd_cl.restype = i32
-        lib.afa_amp_act_conv_fwd_cl.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp, fp, fp, vp, i32, i32,
+        lib.afa_amp_act_conv_fwd_cl.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, fp, fp, vp, i32, i32,
                                                 i64, i64, i64, i32, i32, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]

@@ -129,33 +129,53 @@ class ChannelsLastVocoder:
     def _act(self, a: _Act, x, T, **kw):
         return FC.amp_activation1d_cl(x, T, a.alpha, a.beta, a.taps_up, a.taps_down, a.logscale, **kw)
 
-    def _act_conv(self, a: _Act, conv: _Conv, x, T, **kw):
+    def _act_conv(self, a: _Act, conv: _Conv, x, T, addend=None, **kw):
         """conv(Activation1d(x + res + bias)) without the convolution's bias: one fused kernel on the narrow stages,
         else the activation kernel (zero-filling the polyphase padding rows) followed by cuDNN."""
         # measured on the model's shapes (tools/actconv_sweep.py): at 24 channels the fused kernel is 1.7-2.3x faster than
         # activation + cuDNN with or without the residual prologue; at 48 channels only the plain variant wins
-        if conv.fused and (kw.get("res") is None or x.shape[2] <= 32):
+        if conv.fused and (addend is not None or kw.get("res") is None or x.shape[2] <= 32):
             return FC.amp_act_conv_cl(x, T, a.alpha, a.beta, a.taps_up, a.taps_down, a.logscale, conv.w_kcc, conv.k,
-                                      conv.d, **kw)
+                                      conv.d, addend=addend, **kw)
+        assert addend is None
         return conv(self._act(a, x, T, out_tpad=conv.tpad(T), **kw))
 
     def _resblock(self, its, x, T, up_bias):
         """One AMPBlock on the raw upsampler output x (its bias `up_bias` still pending).
-        Returns (xt, pending bias of xt, residual stream, bias still missing from the residual stream)."""
+        Returns (xt, pending bias of xt, residual stream or None, bias still missing from the residual stream):
+        the block's output is xt + residual + both pending biases (residual None: xt already contains it)."""
         r, r_pending = x, up_bias
         t, t_bias = None, None
+        last = len(its) - 1
         for n, it in enumerate(its):
-            if n == 0:
-                t = self._act_conv(it["a1"], it["c1"], r, T, bias=r_pending)
+            # narrow stages: the LAST convolution of an iteration adds the residual stream in its epilogue (fp32, one
+            # rounding), so `x = xt + x` costs nothing and the next activation has no residual prologue
+            final_conv = it["c2"] if it["c2"] is not None else it["c1"]
+            fold_add = final_conv.fused and t is None
+            if t is None:                                                    # the block's input: r (+ pending bias)
+                kw = dict(bias=r_pending)
+                src = r
             else:                                                            # x = xt + x, then a1(x)
                 r_new = torch.empty(x.shape[0], T, x.shape[2], dtype=x.dtype, device=x.device)
                 r_pending = self._sum(t_bias, r_pending)                     # biases the new residual stream still lacks
-                t = self._act_conv(it["a1"], it["c1"], t, T, bias=r_pending, res=r, xsum=r_new)
+                kw = dict(bias=r_pending, res=r, xsum=r_new)
+                src = t
                 r = r_new
-            t_bias = it["c1"].bias
-            if it["c2"] is not None:
-                t = self._act_conv(it["a2"], it["c2"], t, T, bias=t_bias)
+            if it["c2"] is None:
+                t = self._act_conv(it["a1"], it["c1"], src, T, addend=r if fold_add else None, **kw)
+                t_bias = it["c1"].bias
+            else:
+                t = self._act_conv(it["a1"], it["c1"], src, T, **kw)
+                t = self._act_conv(it["a2"], it["c2"], t, T, bias=it["c1"].bias, addend=r if fold_add else None)
                 t_bias = it["c2"].bias
+            if fold_add:
+                # t = conv + r is the new residual stream (lacking t_bias and whatever r lacked); restart the chain
+                r_pending = self._sum(t_bias, r_pending)
+                if n == last:
+                    if t.shape[1] != T:
+                        t = t[:, :T].contiguous()
+                    return t, None, None, r_pending
+                r, t, t_bias = t, None, None
         if t.shape[1] != T:
             t = t[:, :T].contiguous()                                        # only if the LAST convolution is dilated (AMPBlock2)
         return t, t_bias, r, r_pending
@@ -176,7 +196,8 @@ class ChannelsLastVocoder:
             with torch.cuda.stream(side):
                 outs[j] = self._resblock(its, x, T, st["bias"])
                 for t in (outs[j][0], outs[j][2]):
-                    t.record_stream(cur)                    # consumed by the mean kernel on the main stream
+                    if t is not None:
+                        t.record_stream(cur)                # consumed by the mean kernel on the main stream
                 ev = torch.cuda.Event()
                 ev.record(side)
                 joins.append(ev)

@@ -96,8 +96,10 @@ def act_conv_supported(channels: int, kernel_size: int, dilation: int, dtype) ->
 
 
 def amp_act_conv_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, w_kcc, kernel_size: int, dilation: int,
-                    *, bias=None, res=None, xsum=None, out=None):
-    """y = conv1d(Activation1d(x + res + bias), w, 'same' padding, dilation, NO bias) in one kernel; xsum = x + res.
+                    *, bias=None, res=None, xsum=None, out=None, addend=None):
+    """y = conv1d(Activation1d(x + res + bias), w, 'same' padding, dilation, NO bias) [+ addend] in one kernel;
+    xsum = x + res.  `addend` ([B, T, C]) is the block's residual stream, added in fp32 before y is rounded: y is then
+    the new residual stream (`x = xt + x`, bigvgan.py:141) and the next activation needs no residual prologue.
 
     bf16 channels-last tensors; w_kcc: bf16 [kernel_size, C, C] = conv.weight.permute(2, 0, 1).contiguous().
     Reference: `xt = a(x); xt = c(xt)` (bigvgan.py:134-138); the convolution's bias stays pending with the caller."""
@@ -116,6 +118,8 @@ def amp_act_conv_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, 
     if res is not None:
         _check_cl("res", res, B, T, C, dt, dev)
         _check_cl("xsum", xsum, B, T, C, dt, dev)
+    if addend is not None:
+        _check_cl("addend", addend, B, T, C, dt, dev)
     if w_kcc.dtype != torch.bfloat16 or tuple(w_kcc.shape) != (kernel_size, C, C) or not w_kcc.is_contiguous() or w_kcc.device != dev:
         raise RuntimeError(f"w_kcc must be a contiguous bfloat16 [{kernel_size}, {C}, {C}] tensor on {dev}")
     alpha = _f32("alpha", alpha, C, dev)
@@ -130,6 +134,7 @@ def amp_act_conv_cl(x, T: int, alpha, beta, taps_up, taps_down, logscale: bool, 
             None if res is None else res.data_ptr(), 0 if res is None else _bstride(res),
             None if bias is None else bias.data_ptr(),
             None if xsum is None else xsum.data_ptr(), 0 if xsum is None else _bstride(xsum),
+            None if addend is None else addend.data_ptr(), 0 if addend is None else _bstride(addend),
             out.data_ptr(), _bstride(out),
             alpha.data_ptr(), None if beta is None else beta.data_ptr(), taps_up, taps_down,
             w_kcc.data_ptr(), kernel_size, dilation, B, C, T, _dtype_code(x), _flags(logscale, beta),
@@ -146,7 +151,7 @@ def resblock_mean(xts, xress, bias_sum=None, scale=None, out=None):
     ref = xts[0]
     if not ref.is_cuda:
         raise RuntimeError("channels-last AMP ops run on CUDA tensors only (there is no CPU fallback)")
-    for t in list(xts) + list(xress):
+    for t in list(xts) + [r for r in xress if r is not None]:
         if t.shape != ref.shape or t.dtype != ref.dtype or t.device != ref.device or not t.is_contiguous():
             raise RuntimeError("resblock_mean: all tensors must be dense and agree in shape, dtype and device")
     C = ref.shape[-1]
@@ -155,7 +160,7 @@ def resblock_mean(xts, xress, bias_sum=None, scale=None, out=None):
     if out is None:
         out = torch.empty_like(ref)
     arr_t = (ctypes.c_void_p * K)(*[t.data_ptr() for t in xts])
-    arr_r = (ctypes.c_void_p * K)(*[t.data_ptr() for t in xress])
+    arr_r = (ctypes.c_void_p * K)(*[None if t is None else t.data_ptr() for t in xress])
     lib = _lib.load_library()
     with torch.cuda.device_of(ref):
         rc = lib.afa_resblock_mean(arr_t, arr_r, K, None if bias_sum is None else bias_sum.data_ptr(),

@@ -35,8 +35,9 @@ struct ActConvArgs {
     const float* alpha;
     const float* beta;
     const __nv_bfloat16* w;     // [k][C][C] = [tap][c_out][c_in] bf16
+    const void* addend;         // optional [B, T, C]: y = conv(...) + addend (the residual add `x = xt + x`, bigvgan.py:141)
     FwdTaps taps;
-    int64_t x_bs, res_bs, xsum_bs, y_bs;
+    int64_t x_bs, res_bs, xsum_bs, y_bs, addend_bs;
     int32_t T, C, flags, batch;
     int32_t k, dil;             // kernel size (odd), dilation
     int32_t n_sub, Lsub;        // phase 1: sub-segments per tile, rows per sub-segment (12 n + 2)
@@ -186,8 +187,19 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_kernel(const __g
             for (int m = 0; m < MT; ++m) {
                 if (mt0 + m >= n_mt) break;
                 const int r0 = t_out0 + (mt0 + m) * 16 + (lane >> 2), r1 = r0 + 8;
+                const T* ab = args.addend ? static_cast<const T*>(args.addend) + (int64_t)b * args.addend_bs : nullptr;
 #pragma unroll
                 for (int n = 0; n < NT8; ++n) {
+                    if (ab) {
+                        if (r0 < Tlen) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ab + (int64_t)r0 * C + n * 8 + cc));
+                            acc[m][n][0] += f.x; acc[m][n][1] += f.y;
+                        }
+                        if (r1 < Tlen) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ab + (int64_t)r1 * C + n * 8 + cc));
+                            acc[m][n][2] += f.x; acc[m][n][3] += f.y;
+                        }
+                    }
                     if (r0 < Tlen) *reinterpret_cast<__nv_bfloat162*>(yb + (int64_t)r0 * C + n * 8 + cc) = __floats2bfloat162_rn(acc[m][n][0], acc[m][n][1]);
                     if (r1 < Tlen) *reinterpret_cast<__nv_bfloat162*>(yb + (int64_t)r1 * C + n * 8 + cc) = __floats2bfloat162_rn(acc[m][n][2], acc[m][n][3]);
                 }
@@ -373,9 +385,16 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_tc_kernel(const 
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (r < args.TT && t < Tlen && !(AFA_TC_DEBUG & 4)) {
                 T* dst = yb + (int64_t)t * C;
+                const T* add = args.addend ? static_cast<const T*>(args.addend) + (int64_t)b * args.addend_bs + (int64_t)t * C : nullptr;
 #pragma unroll
                 for (int c8 = 0; c8 < NPAD / 8; ++c8) {
                     if (c8 * 8 < C) {
+                        if (add) {                                   // the residual add of the block, in fp32 before the one rounding
+                            float f[8];
+                            IO<T>::load_chunk(add + c8 * 8, f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[c8 * 8 + e] = __float_as_uint(__uint_as_float(v[c8 * 8 + e]) + f[e]);
+                        }
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {

@@ -513,9 +513,9 @@ int afa_resblock_mean(const void* const* xt, const void* const* xres, int num_ke
     afa::MeanArgs a;
     for (int j = 0; j < afa::kMeanMaxK; ++j) { a.y[j] = nullptr; a.r[j] = nullptr; }
     for (int j = 0; j < num_kernels; ++j) {
-        if (!xt[j] || !xres[j]) return fail(AFA_ERR_BAD_ARG, "null tensor pointer at index %d", j);
+        if (!xt[j]) return fail(AFA_ERR_BAD_ARG, "null tensor pointer at index %d", j);
         a.y[j] = xt[j];
-        a.r[j] = xres[j];
+        a.r[j] = xres[j];                                   // may be null: xt[j] already contains its residual stream
         ptr_or |= (uintptr_t)xt[j] | (uintptr_t)xres[j];
     }
     const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
@@ -633,10 +633,10 @@ int afa_amp_act_conv_supported(int64_t channels, int kernel_size, int dilation, 
 }
 
 int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, int64_t res_bstride, const float* bias,
-                            void* xsum, int64_t xsum_bstride, void* y, int64_t y_bstride, const float* alpha,
-                            const float* beta, const float* taps_up12, const float* taps_down12, const void* w_kcc,
-                            int kernel_size, int dilation, int64_t batch, int64_t channels, int64_t T, int dtype,
-                            int flags, void* stream) {
+                            void* xsum, int64_t xsum_bstride, const void* addend, int64_t addend_bstride, void* y,
+                            int64_t y_bstride, const float* alpha, const float* beta, const float* taps_up12,
+                            const float* taps_down12, const void* w_kcc, int kernel_size, int dilation, int64_t batch,
+                            int64_t channels, int64_t T, int dtype, int flags, void* stream) {
     if (!x || !y || !alpha || !taps_up12 || !taps_down12 || !w_kcc) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
     if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
     if (dtype != AFA_DTYPE_BF16) return fail(AFA_ERR_BAD_DTYPE, "the fused activation+convolution runs on bf16 activations (tensor-core path); dtype %d", dtype);
@@ -647,8 +647,10 @@ int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, i
     if (y == x || y == res || (xsum && (xsum == x || xsum == y || xsum == res)))
         return fail(AFA_ERR_BAD_ARG, "outputs must not alias inputs or each other (tiles re-read their neighbours' halo)");
     const int64_t row = T * channels;
-    if (x_bstride < row || (res && res_bstride < row) || (xsum && xsum_bstride < row) || y_bstride < row)
+    if (x_bstride < row || (res && res_bstride < row) || (xsum && xsum_bstride < row) || y_bstride < row || (addend && addend_bstride < row))
         return fail(AFA_ERR_BAD_ARG, "batch strides must cover T*channels elements");
+    if (addend && (addend == y || addend == xsum)) return fail(AFA_ERR_BAD_ARG, "addend must not alias an output");
+    if (addend && (((uintptr_t)addend & 15) || (addend_bstride % 8))) return fail(AFA_ERR_ALIGNMENT, "addend must be 16-byte aligned (batch stride a multiple of 8)");
     if (row >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "T*channels=%lld exceeds 2^31", (long long)row);
     if (((uintptr_t)x | (uintptr_t)res | (uintptr_t)xsum) & 1) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
     if (((uintptr_t)y & 3) || ((uintptr_t)w_kcc & 15) || (y_bstride & 1)) return fail(AFA_ERR_ALIGNMENT, "y must be 4-byte aligned (even batch stride), the weights 16-byte aligned");
@@ -657,6 +659,7 @@ int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, i
     afa::ActConvArgs a;
     a.x = x; a.res = res; a.xsum = xsum; a.y = y; a.bias = bias; a.alpha = alpha; a.beta = beta;
     a.w = (const __nv_bfloat16*)w_kcc;
+    a.addend = addend; a.addend_bs = addend_bstride;
     fold_fwd_taps(taps_up12, taps_down12, &a.taps);
     a.x_bs = x_bstride; a.res_bs = res_bstride; a.xsum_bs = xsum_bstride; a.y_bs = y_bstride;
     a.T = (int32_t)T; a.C = C; a.flags = flags; a.batch = (int32_t)batch;

@@ -444,12 +444,14 @@ __global__ void __launch_bounds__(256) afa_mean_kernel(const __grid_constant__ M
         for (int e = 0; e < VEC; ++e) acc[e] = a.bias_sum ? __ldg(a.bias_sum + cv * VEC + e) : 0.f;
         for (int j = 0; j < a.K; ++j) {
             float v[VEC], u[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) u[e] = 0.f;
             if (VEC == 1) {
                 v[0] = cl_load(static_cast<const T*>(a.y[j]) + i);
-                u[0] = cl_load(static_cast<const T*>(a.r[j]) + i);
+                if (a.r[j]) u[0] = cl_load(static_cast<const T*>(a.r[j]) + i);
             } else {
                 IO<T>::load_chunk(static_cast<const T*>(a.y[j]) + i * VEC, v);
-                IO<T>::load_chunk(static_cast<const T*>(a.r[j]) + i * VEC, u);
+                if (a.r[j]) IO<T>::load_chunk(static_cast<const T*>(a.r[j]) + i * VEC, u);
             }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[e] += v[e] + u[e];

@@ -119,7 +119,7 @@ int afa_amp_activation1d_fwd_cl(const void *x, int64_t x_bstride,
 
 /*
  * out = scale * (sum_{j < num_kernels} (xt[j] + xres[j]) + bias_sum[c]) over dense [rows, channels] arrays
- * (rows = batch*T).  xt[j]: output of the last convolution of resblock j WITHOUT its bias; xres[j]: that
+ * (rows = batch*T); an entry xres[j] may be NULL (xt[j] already contains its residual stream).  xt[j]: output of the last convolution of resblock j WITHOUT its bias; xres[j]: that
  * resblock's residual stream; bias_sum: float32 [channels] = sum of those biases (or NULL); scale = 1/num_kernels.
  * xt / xres are HOST arrays of device pointers.
  */
@@ -149,8 +149,11 @@ int afa_tail_fwd_cl(const void *x, int64_t x_bstride,
 
 /*
  * Activation1d as the PROLOGUE of the AMPBlock convolution, for the narrow stages of the generator:
- *   y = conv1d(down2x(snake(up2x(x + res + bias[c]))), w, no bias, 'same' padding, dilation) ; xsum = x + res
- *   <->  `xt = a(x); xt = c(xt)`  BigVGAN/bigvgan.py:134-138 (AMPBlock1), :234-235 (AMPBlock2)
+ *   y = conv1d(down2x(snake(up2x(x + res + bias[c]))), w, no bias, 'same' padding, dilation) + addend ; xsum = x + res
+ *   <->  `xt = a(x); xt = c(xt)` [+ `x = xt + x`]  BigVGAN/bigvgan.py:134-141 (AMPBlock1), :234-236 (AMPBlock2)
+ * addend (optional, [batch, T, channels], 16-byte aligned): the block's residual stream, added in fp32 to the
+ * convolution's accumulators before the single rounding of y -- then y IS the new residual stream and the next
+ * activation needs no residual prologue.
  * Same conventions as afa_amp_activation1d_fwd_cl (the convolution's own bias stays pending with the caller).
  * w_kcc: bf16 device array [kernel_size][channels_out][channels_in] (= conv.weight.permute(2, 0, 1)), 16-byte
  * aligned; channels_out == channels_in == channels.  bf16 activations only (the convolution runs on the
@@ -161,6 +164,7 @@ int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
                             const void *res, int64_t res_bstride,
                             const float *bias,
                             void *xsum, int64_t xsum_bstride,
+                            const void *addend, int64_t addend_bstride,
                             void *y, int64_t y_bstride,
                             const float *alpha, const float *beta,
                             const float *taps_up12, const float *taps_down12,

@@ -135,23 +135,28 @@ def amp_activation1d_cl(x_btc, alpha, beta=None, logscale=True, bias=None, res=N
 
 
 def amp_act_conv_cl(x_btc, alpha, beta, logscale, w_kcc, dilation, bias=None, res=None, taps_up=None, taps_down=None,
-                    round_act=None):
-    """afa_amp_act_conv_fwd_cl: (xsum = x + res, y = conv1d(Activation1d(x + res + bias), w, 'same', dilation)) in
-    [B, T, C]; w_kcc: [k, C_out, C_in].  `round_act` (a function) models the bf16 rounding of the activated tile."""
+                    round_act=None, addend=None):
+    """afa_amp_act_conv_fwd_cl: (xsum = x + res, y = conv1d(Activation1d(x + res + bias), w, 'same', dilation) + addend)
+    in [B, T, C]; w_kcc: [k, C_out, C_in].  `round_act` (a function) models the bf16 rounding of the activated tile."""
     xs, a = amp_activation1d_cl(x_btc, alpha, beta, logscale, bias, res, taps_up, taps_down)
     if round_act is not None:
         a = round_act(a)
     w = np.ascontiguousarray(np.asarray(w_kcc, dtype=np.float64).transpose(1, 2, 0))      # [C_out, C_in, k]
     k = w.shape[2]
     y = conv1d(np.ascontiguousarray(a.transpose(0, 2, 1)), w, None, get_padding(k, dilation), dilation)
-    return xs, np.ascontiguousarray(y.transpose(0, 2, 1))
+    y = np.ascontiguousarray(y.transpose(0, 2, 1))
+    if addend is not None:
+        y = y + np.asarray(addend, dtype=np.float64)
+    return xs, y
 
 
 def resblock_mean(xts, xress, bias_sum=None, scale=None):
     """afa_resblock_mean: scale * (sum_j (xt_j + xres_j) + bias_sum[c]); scale defaults to 1/len."""
     acc = np.zeros_like(np.asarray(xts[0], dtype=np.float64))
     for a, r in zip(xts, xress):
-        acc = acc + np.asarray(a, dtype=np.float64) + np.asarray(r, dtype=np.float64)
+        acc = acc + np.asarray(a, dtype=np.float64)
+        if r is not None:                                   # None: xt_j already contains its residual stream
+            acc = acc + np.asarray(r, dtype=np.float64)
     if bias_sum is not None:
         acc = acc + np.asarray(bias_sum, dtype=np.float64)
     return acc * (1.0 / len(xts) if scale is None else scale)

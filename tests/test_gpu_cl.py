@@ -455,3 +455,38 @@ def test_zero_frame_restoration_in_the_tail(amp_golden, true_fp32_convs):
             ref[:, ch] = ingest.restore_silence_host(monos[ch], idx, hop, t_mel * hop)
             assert np.all(ref[np.repeat(mask, hop), ch] == 0)
         assert np.array_equal(pcm, ref), (zl, zr)
+
+
+def test_act_conv_addend_and_mean_without_residual():
+    """The residual add folded into the convolution's epilogue (`x = xt + x`, bigvgan.py:141): y = conv(act(x + bias)) + addend
+    with one rounding, on both tensor paths; and the mean kernel with a missing residual entry."""
+    from afa_b200 import _lib
+
+    _, FC = _fc()
+    t32, taps, taps64 = _taps()
+    rng = np.random.default_rng(31)
+    for C, k, d, T, B in ((24, 7, 3, 1000, 2), (48, 11, 5, 415, 1), (8, 3, 1, 17, 2), (32, 3, 5, 1733, 1)):
+        x = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.bfloat16, device=DEV)
+        r = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.bfloat16, device=DEV)
+        bias = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+        alpha = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+        beta = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+        w = torch.tensor(rng.standard_normal((k, C, C)) / np.sqrt(k * C), dtype=torch.bfloat16, device=DEV)
+        _, y_ref = A.amp_act_conv_cl(x.double().cpu().numpy(), alpha.double().cpu().numpy(), beta.double().cpu().numpy(), True,
+                                     w.double().cpu().numpy(), d, bias.double().cpu().numpy(), None, taps64, taps64,
+                                     round_act=_bf16_round, addend=r.double().cpu().numpy())
+        outs = []
+        try:
+            for path in (1, 0):
+                _lib.set_tuning(3, path)
+                y = FC.amp_act_conv_cl(x, T, alpha, beta, taps[0], taps[1], True, w, k, d, bias=bias, addend=r)
+                torch.cuda.synchronize()
+                assert O.max_normalised_error(y.double().cpu().numpy(), y_ref) <= TOL_BF16, (C, k, d, T, path)
+                outs.append(y)
+        finally:
+            _lib.set_tuning(3, 1)
+        assert torch.equal(outs[0], outs[1]), (C, k, d, T)
+        m = FC.resblock_mean([outs[0], x], [None, r], bias, 0.5)
+        m_ref = A.resblock_mean([outs[0].double().cpu().numpy(), x.double().cpu().numpy()], [None, r.double().cpu().numpy()],
+                                bias.double().cpu().numpy(), 0.5)
+        assert O.max_normalised_error(m.double().cpu().numpy(), m_ref) <= 4e-3
