@@ -131,7 +131,7 @@ int afa_resblock_mean(const void *const *xt, const void *const *xres, int num_ke
  * wave[b][t] = final(conv_post(activation_post(x)))  with conv_post: channels -> 1, kernel 7, zero padding 3,
  * weight w_post float32 [channels][7] (device), optional bias_post (1 float, device), final = clamp(-1, 1)
  * (use_tanh = 0) or tanh.  channels <= 32.  Outputs (at least one): wave float32 [batch][T]; pcm int16 with
- * element (b, t) at ((b / pcm_interleave) * T + t) * pcm_interleave + b % pcm_interleave, value
+ * element (b, t) at ((b / pcm_interleave) * T_out + t) * pcm_interleave + b % pcm_interleave, value
  * (int16)(wave * pcm_scale) truncated toward zero like numpy's astype("int16") (pcm_scale = 32767).
  * Zero-frame restoration (BigVGAN/inference_e2e.py:38-111, reconstruct_audio_with_silence): with frame_map
  * (int32 [batch][T / hop], device) sample t of batch entry b is written at frame_map[b][t / hop] * hop + t % hop
