@@ -34,6 +34,13 @@ constexpr int kClS = 12;        // ring size = steps per rolled-loop trip = pref
 #define AFA_CL_L2_PREFETCH 0
 #endif
 constexpr int kClThreads = 128;
+// resident CTAs per SM the channels-last walk is compiled for (register cap = 65536 / (128 * n))
+#ifndef AFA_CL_MINB_PLAIN
+#define AFA_CL_MINB_PLAIN 5
+#endif
+#ifndef AFA_CL_MINB_RES
+#define AFA_CL_MINB_RES 4
+#endif
 
 struct ClArgs {
     const void* x;
@@ -351,7 +358,7 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
 // forward kernel: one thread per (batch, segment, channel), channel fastest
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool RES>
-__global__ void __launch_bounds__(kClThreads, RES ? 4 : 5) afa_cl_fwd_kernel(const __grid_constant__ ClArgs args) {
+__global__ void __launch_bounds__(kClThreads, RES ? AFA_CL_MINB_RES : AFA_CL_MINB_PLAIN) afa_cl_fwd_kernel(const __grid_constant__ ClArgs args) {
     const uint32_t g = blockIdx.x * kClThreads + threadIdx.x;
     const bool active = g < args.total;
     const uint32_t gc = active ? g : args.total - 1u;
