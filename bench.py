@@ -599,6 +599,131 @@ def run_vocoder_mode(args):
     return 0
 
 
+def run_train_mode(args):
+    """`--mode train`: BASELINE config 5 -- the generator's forward + backward with the fused Activation1d forward and
+    backward kernels in it (train_binaural_mel.py:431-543, 787-791: BigVGAN(h) under DDP, AdamW, clip_grad_norm_), at
+    the training segment (8192 samples = 32 mel frames, `--t-mel 32`) and `--batch` items per GPU.  The discriminators
+    and losses of the reference are not importable here (nnAudio, librosa, pesq, auraloss absent: SURVEY.md section 8c), so
+    the step is generator forward -> synthetic scalar loss -> backward -> clip -> AdamW, fp32 as the reference trains.
+    `--torch-baseline` also times the same step with the reference's torch-op activation on the same GPU."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    from afa_b200 import _lib
+    from afa_b200.vocoder import BigVGANGenerator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    t_mel = args.t_mel if args.t_mel != T_MEL_10S else 32
+    B = args.batch
+
+    def build(factory=None):
+        torch.manual_seed(1234)                                    # configs/bigvgan_binaural_22khz_80band_256x.json:9
+        gen = BigVGANGenerator() if factory is None else BigVGANGenerator(activation_factory=factory)
+        with torch.no_grad():
+            for n, p in gen.named_parameters():
+                if n.endswith("alpha") or n.endswith("beta"):
+                    p.normal_(0, 0.5)
+        gen = gen.to(dev).train()
+        model = nn.parallel.DistributedDataParallel(gen, device_ids=[local_rank]) if world > 1 else gen
+        opt = torch.optim.AdamW(gen.parameters(), 5e-5, betas=(0.8, 0.99))      # train_binaural_mel.py:548-551, config lr / betas
+        return gen, model, opt
+
+    def time_steps(model, gen, opt, steps, warmup):
+        mel = torch.rand(B, 80, t_mel, device=dev) * 14.5 - 12.0
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            y = model(mel)
+            loss = y.abs().mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(gen.parameters(), 500.0)     # config clip_grad_norm, train_binaural_mel.py:788-790
+            opt.step()
+            return loss
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            loss = one()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(loss.item()), (_lib.launch_count() - l0) // steps
+
+    with ClockSampler(local_rank) as clocks:
+        gen, model, opt = build()
+        ms, loss, launches = time_steps(model, gen, opt, max(1, args.steps), max(3, args.warmup))
+    # share of the fused activation kernels in the step (device time, one profiled step on rank 0)
+    act_ms = None
+    if rank == 0:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+
+            mel = torch.rand(B, 80, t_mel, device=dev) * 14.5 - 12.0
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                opt.zero_grad(set_to_none=True)
+                gen(mel).abs().mean().backward()
+                torch.cuda.synchronize(dev)
+            act_ms = sum(r.device_time_total for r in prof.key_averages() if "afa::" in r.key) / 1e3
+            tot_ms = sum(r.device_time_total for r in prof.key_averages()) / 1e3
+        except Exception:  # noqa: BLE001
+            act_ms = tot_ms = None
+    base = None
+    if args.torch_baseline:
+        del gen, model, opt
+        torch.cuda.empty_cache()
+        from afa_b200.modules import DownSample1d, UpSample1d
+        from oracle import torch_path as TP                       # the reference's op sequence (optional diagnostic leg only)
+
+        class TorchOpActivation1d(nn.Module):
+            def __init__(self, activation):
+                super().__init__()
+                self.act, self.upsample, self.downsample = activation, UpSample1d(2, 12), DownSample1d(2, 12)
+
+            def forward(self, x):
+                beta = getattr(self.act, "beta", None)
+                return TP.activation1d_torch(x, self.act.alpha, beta, bool(self.act.alpha_logscale), self.upsample.filter,
+                                             self.downsample.lowpass.filter)
+
+        gen_t, model_t, opt_t = build(TorchOpActivation1d)
+        ms_t, loss_t, _ = time_steps(model_t, gen_t, opt_t, max(1, args.steps), 3)
+        base = {"ms_per_step": round(ms_t, 3), "loss": loss_t, "what": "same step, reference torch-op Activation1d on the same GPU"}
+    if rank == 0:
+        samples = world * B * t_mel * 256
+        print(json.dumps({
+            "metric": "train_step_generator_fwd_bwd_ms", "value": round(ms, 3), "unit": "ms per step", "n_gpus": world,
+            "steps": max(1, args.steps), "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": (f"BASELINE config 5: BigVGAN generator (bigvgan_binaural_22khz_80band_256x, random init) forward + "
+                                    f"backward + clip_grad_norm + AdamW, batch {B} per GPU, segment {t_mel * 256} samples (T_mel={t_mel}), "
+                                    f"synthetic scalar loss; fused Activation1d forward and backward ([B, C, T] kernels)"),
+                       "parallelism": f"DDP dp{world}" if world > 1 else "single GPU"},
+            "audio_sec_per_sec_trained": round(samples / 22050.0 / (ms * 1e-3), 1),
+            "activation_kernels_ms_per_step": None if act_ms is None else round(act_ms, 3),
+            "all_kernels_ms_per_step": None if act_ms is None else round(tot_ms, 3),
+            "gpu_launches": int(launches) * max(1, args.steps), "loss": loss, "torch_op_activation_baseline": base,
+            "clocks": clocks.summary(),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ----------------------------------------------------------------------------------------------
 # per-shape table (extra; not the driver's contract)
 # ----------------------------------------------------------------------------------------------
@@ -695,8 +820,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the whole-generator audio-s/s companion number")
-    ap.add_argument("--mode", choices=["activation", "vocoder"], default="activation",
-                    help="vocoder: BASELINE config 4 (--total-clips clips sharded over the ranks, strong scaling)")
+    ap.add_argument("--mode", choices=["activation", "vocoder", "train"], default="activation",
+                    help="vocoder: BASELINE config 4 (--total-clips clips sharded over the ranks, strong scaling); "
+                         "train: BASELINE config 5 (generator forward + backward step, --batch per GPU, segment 8192)")
+    ap.add_argument("--batch", type=int, default=32, help="--mode train: items per GPU (config batch_size)")
     ap.add_argument("--total-clips", type=int, default=64)
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=0, help="tuning: 16-byte chunks per thread segment for the forward (0 = library default)")
@@ -711,6 +838,8 @@ def main():
         return run_reference(args)
     if args.mode == "vocoder":
         return run_vocoder_mode(args)
+    if args.mode == "train":
+        return run_train_mode(args)
     return run_gpu(args)
 
 
