@@ -632,7 +632,9 @@ def run_train_mode(args):
                 if n.endswith("alpha") or n.endswith("beta"):
                     p.normal_(0, 0.5)
         gen = gen.to(dev).train()
-        model = nn.parallel.DistributedDataParallel(gen, device_ids=[local_rank]) if world > 1 else gen
+        # train_binaural_mel.py:540-543 wraps the generator in plain DDP; bucket views avoid one gradient copy per step
+        model = nn.parallel.DistributedDataParallel(gen, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                    bucket_cap_mb=int(os.environ.get("AFA_DDP_BUCKET_MB", "25"))) if world > 1 else gen
         opt = torch.optim.AdamW(gen.parameters(), 5e-5, betas=(0.8, 0.99))      # train_binaural_mel.py:548-551, config lr / betas
         return gen, model, opt
 
