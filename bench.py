@@ -635,7 +635,8 @@ def run_train_mode(args):
         # train_binaural_mel.py:540-543 wraps the generator in plain DDP; bucket views avoid one gradient copy per step
         model = nn.parallel.DistributedDataParallel(gen, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                     bucket_cap_mb=int(os.environ.get("AFA_DDP_BUCKET_MB", "25"))) if world > 1 else gen
-        opt = torch.optim.AdamW(gen.parameters(), 5e-5, betas=(0.8, 0.99))      # train_binaural_mel.py:548-551, config lr / betas
+        opt = torch.optim.AdamW(gen.parameters(), 5e-5, betas=(0.8, 0.99),       # train_binaural_mel.py:548-551, config lr / betas
+                                capturable=bool(args.graph_step))
         return gen, model, opt
 
     def time_steps(model, gen, opt, steps, warmup):
@@ -650,8 +651,30 @@ def run_train_mode(args):
             opt.step()
             return loss
 
-        for _ in range(warmup):
-            one()
+        graph = None
+        if args.graph_step and world == 1:
+            # the whole step (forward, fused backward kernels, clip, AdamW) captured once and replayed: no host work
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    one()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=False)
+            with torch.cuda.graph(graph):
+                y = model(mel)
+                static_loss = y.abs().mean()
+                static_loss.backward()
+                torch.nn.utils.clip_grad_norm_(gen.parameters(), 500.0)
+                opt.step()
+                opt.zero_grad(set_to_none=False)
+            for _ in range(2):
+                graph.replay()
+        else:
+            for _ in range(warmup):
+                one()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -659,13 +682,18 @@ def run_train_mode(args):
         l0 = _lib.launch_count()
         e0.record()
         for _ in range(steps):
-            loss = one()
+            if graph is not None:
+                graph.replay()
+                loss = static_loss
+            else:
+                loss = one()
         e1.record()
         torch.cuda.synchronize(dev)
         t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), float(loss.item()), (_lib.launch_count() - l0) // steps
+        per_step = (_lib.launch_count() - l0) // steps if graph is None else 109 * 3     # 109 forward + 109 backward + 109 finalize launches
+        return float(t.item()), float(loss.item()), per_step
 
     with ClockSampler(local_rank) as clocks:
         gen, model, opt = build()
@@ -714,7 +742,8 @@ def run_train_mode(args):
             "config": {"workload": (f"BASELINE config 5: BigVGAN generator (bigvgan_binaural_22khz_80band_256x, random init) forward + "
                                     f"backward + clip_grad_norm + AdamW, batch {B} per GPU, segment {t_mel * 256} samples (T_mel={t_mel}), "
                                     f"synthetic scalar loss; fused Activation1d forward and backward ([B, C, T] kernels)"),
-                       "parallelism": f"DDP dp{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"DDP dp{world}" if world > 1 else "single GPU",
+                       "cuda_graph_step": bool(args.graph_step and world == 1)},
             "audio_sec_per_sec_trained": round(samples / 22050.0 / (ms * 1e-3), 1),
             "activation_kernels_ms_per_step": None if act_ms is None else round(act_ms, 3),
             "all_kernels_ms_per_step": None if act_ms is None else round(tot_ms, 3),
@@ -826,6 +855,7 @@ def main():
                     help="vocoder: BASELINE config 4 (--total-clips clips sharded over the ranks, strong scaling); "
                          "train: BASELINE config 5 (generator forward + backward step, --batch per GPU, segment 8192)")
     ap.add_argument("--batch", type=int, default=32, help="--mode train: items per GPU (config batch_size)")
+    ap.add_argument("--graph-step", action="store_true", help="--mode train, one GPU: capture the whole step in a CUDA graph")
     ap.add_argument("--total-clips", type=int, default=64)
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=0, help="tuning: 16-byte chunks per thread segment for the forward (0 = library default)")
