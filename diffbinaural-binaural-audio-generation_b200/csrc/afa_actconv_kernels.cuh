@@ -229,6 +229,7 @@ struct ActConvTcArgs {
     int32_t rows_alloc;   // rows per column strip of the activation tile (odd: strips fall into different banks)
     int32_t n_mb;         // blocks of 128 output rows per tile
     int32_t tmem_cols;    // power of two >= n_mb * NPAD
+    int32_t xin_rows;     // XS variant: rows of x staged per tile (a_rows + 11), else 0
 };
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes) {
@@ -270,8 +271,11 @@ constexpr int kAcMaxBlocks = 8;
 #define AFA_TC_DEBUG 0
 #endif
 
-// NPAD: c_out padded to a multiple of 16 (the MMA's N);  KS: input-channel steps of 16
-template <bool RES, int NPAD, int KS>
+// NPAD: c_out padded to a multiple of 16 (the MMA's N);  KS: input-channel steps of 16;  XS: the tile's input rows (one
+// contiguous range of the channels-last array) are staged in shared memory by ONE bulk TMA copy issued at kernel entry,
+// so phase 1 reads x with short-latency shared-memory loads instead of waiting on global loads (ncu: long_scoreboard was
+// the top stall of phase 1 with only 16 warps per SM to hide it)
+template <bool RES, int NPAD, int KS, bool XS = false>
 __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_tc_kernel(const __grid_constant__ ActConvTcArgs targs) {
     using T = __nv_bfloat16;
     const ActConvArgs& args = targs.a;
@@ -290,6 +294,17 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_tc_kernel(const 
     const int t_out0 = tile * args.TT;
     const int tile_t0 = t_out0 - P;
     const int rows_alloc = targs.rows_alloc;
+    T* xin = asm_ + (size_t)NSTRIP * rows_alloc * 8;                 // XS: [xin_rows][C]
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem_raw + 72);
+    const int xrow0 = max(0, tile_t0 - 5);                           // first staged row of x
+    if (XS && tid == 0) {
+        const int xrow1 = min(Tlen, tile_t0 + args.a_rows + 6);
+        const uint32_t bytes = (uint32_t)(xrow1 - xrow0) * (uint32_t)C * 2u;
+        mbar_init(xbar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(xbar, bytes);
+        tma_load_1d(xin, static_cast<const T*>(args.x) + (int64_t)b * args.x_bs + (int64_t)xrow0 * C, bytes, xbar);
+    }
 
     // ---- TMEM allocation (warp 0), mbarriers, weights in the B layout, zero padding
     if (warp == 0) {
@@ -321,8 +336,10 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_tc_kernel(const 
         const int t0 = tile_t0 + s * args.Lsub;
         const bool fast = !active || (t0 >= 5 && t0 + args.Lsub + 5 < Tlen);
         const bool all_fast = __syncthreads_and(fast ? 1 : 0) != 0;
+        if (XS) mbar_wait_bounded(xbar, 0);                      // the staged input rows have landed
         if (active) {
-            const T* px = static_cast<const T*>(args.x) + (int64_t)b * args.x_bs + c;
+            // XS: element t of this channel at px[t * C] inside the staged rows (the pointer may lie before the buffer)
+            const T* px = XS ? xin + c - (int64_t)xrow0 * C : static_cast<const T*>(args.x) + (int64_t)b * args.x_bs + c;
             const T* pr = RES ? static_cast<const T*>(args.res) + (int64_t)b * args.res_bs + c : nullptr;
             T* ps = RES ? static_cast<T*>(args.xsum) + (int64_t)b * args.xsum_bs + c : nullptr;
             const ChanParams cp = load_chan_params(args.alpha, args.beta, c, args.flags);
@@ -334,8 +351,8 @@ __global__ void __launch_bounds__(kAcThreads, 2) afa_cl_actconv_tc_kernel(const 
             ts.own_lo = t_out0;
             ts.own_hi = min(t_out0 + args.TT, Tlen);
             const uint32_t amask = __activemask();
-            if (all_fast) walk_cl<T, 0, RES, 2>(px, pr, ps, nullptr, C, t0, args.Lsub, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask, &ts);
-            else walk_cl<T, 1, RES, 2>(px, pr, ps, nullptr, C, t0, args.Lsub, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask, &ts);
+            if (all_fast) walk_cl<T, 0, RES, 2, XS>(px, pr, ps, nullptr, C, t0, args.Lsub, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask, &ts);
+            else walk_cl<T, 1, RES, 2, XS>(px, pr, ps, nullptr, C, t0, args.Lsub, Tlen, cp.a_eff, cp.ib, bias, args.taps, nullptr, amask, &ts);
         }
     }
     // generic-proxy writes of the tiles -> visible to the tensor core's async proxy; TMEM address -> everyone

@@ -22,6 +22,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_tune_chunks[3] = {0, 0, 0};   // [2]: channels-last walk, segment length in units of 12 samples
 int g_tune_threads[3] = {0, 0, 0};
+int g_actconv_xs = 1;     // fused activation+convolution, tcgen05 path: stage the input rows in shared memory (which=4)
 int g_actconv_path = 1;   // fused activation+convolution: 1 = tcgen05 (falls back to mma.sync when the tile does not fit), 0 = mma.sync
 
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
@@ -250,6 +251,11 @@ const char* afa_last_error(void) { return g_err; }
 int64_t afa_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int afa_set_tuning(int which, int chunks, int threads) {
+    if (which == 4) {   // fused activation+convolution, tcgen05 path: 1 = input rows staged by a bulk copy (default), 0 = global loads
+        if (chunks != 0 && chunks != 1) return fail(AFA_ERR_BAD_ARG, "input staging must be 0 or 1");
+        g_actconv_xs = chunks;
+        return 0;
+    }
     if (which == 3) {   // fused activation+convolution: 1 = tcgen05 (default), 0 = legacy mma.sync
         if (chunks != 0 && chunks != 1) return fail(AFA_ERR_BAD_ARG, "tensor path must be 0 (mma.sync) or 1 (tcgen05)");
         g_actconv_path = chunks;
@@ -572,9 +578,9 @@ int launch_actconv_t(const afa::ActConvArgs& a, size_t smem, uint32_t grid, cuda
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_actconv_kernel launch");
 }
 
-template <bool RES, int NPAD, int KS>
+template <bool RES, int NPAD, int KS, bool XS = false>
 int launch_actconv_tc_t(const afa::ActConvTcArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
-    auto k = afa::afa_cl_actconv_tc_kernel<RES, NPAD, KS>;
+    auto k = afa::afa_cl_actconv_tc_kernel<RES, NPAD, KS, XS>;
     static thread_local const void* configured[8] = {nullptr};
     static thread_local int configured_dev[8] = {0};
     int dev = 0;
@@ -592,6 +598,18 @@ int launch_actconv_tc_t(const afa::ActConvTcArgs& a, size_t smem, uint32_t grid,
     g_launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_cl_actconv_tc_kernel launch");
+}
+
+int launch_actconv_tc_xs(const afa::ActConvTcArgs& a, size_t smem, uint32_t grid, cudaStream_t st) {
+    switch (a.a.C) {
+        case 8: return launch_actconv_tc_t<false, 16, 1, true>(a, smem, grid, st);
+        case 16: return launch_actconv_tc_t<false, 16, 1, true>(a, smem, grid, st);
+        case 24: return launch_actconv_tc_t<false, 32, 2, true>(a, smem, grid, st);
+        case 32: return launch_actconv_tc_t<false, 32, 2, true>(a, smem, grid, st);
+        case 48: return launch_actconv_tc_t<false, 48, 3, true>(a, smem, grid, st);
+        case 64: return launch_actconv_tc_t<false, 64, 4, true>(a, smem, grid, st);
+    }
+    return fail(AFA_ERR_BAD_ARG, "fused activation+convolution is compiled for channels in {8,16,24,32,48,64}, got %d", a.a.C);
 }
 
 template <bool RES>
@@ -674,34 +692,54 @@ int afa_amp_act_conv_fwd_cl(const void* x, int64_t x_bstride, const void* res, i
         const int npad = C <= 16 ? 16 : cpad;
         const int nstrip = cpad / 8;
         const size_t wb = (size_t)kernel_size * nstrip * npad * 16;
-        for (int n = 7; n >= 3; --n) {
-            const int lsub = 12 * n + 2;
-            const int a_rows = a.n_sub * lsub;
-            if ((int64_t)a_rows - 2 * P > 2 * T && n > 3) continue;       // short rows: keep enough tiles
-            const int tt = (a_rows - 2 * P) / 16 * 16;
-            if (tt < 16) break;
-            const int n_mb = (tt + 127) / 128;
-            const int rows_alloc = (n_mb * 128 + 2 * P > a_rows ? n_mb * 128 + 2 * P : a_rows) | 1;   // MMA reach and phase-1 rows
-            const size_t smem_tc = 128 + wb + (size_t)nstrip * rows_alloc * 16;
-            if (n_mb > afa::kAcMaxBlocks || n_mb * npad > 512 || smem_tc > 110 * 1024) continue;
+        // without a residual prologue the tile's input rows are staged in shared memory by one bulk copy (XS variant) --
+        // unless the extra buffer would shrink the tile by more than a fifth (wide weights: C = 48, k = 11)
+        const bool xs_ok = g_actconv_xs && !res && (((uintptr_t)x & 15) == 0) && (x_bstride % 8 == 0);
+        struct Cfg { int lsub, a_rows, tt, n_mb, rows_alloc, xin_rows; size_t smem; bool ok; };
+        auto pick = [&](bool xs) {
+            Cfg c{};
+            for (int n = 7; n >= 3; --n) {
+                const int lsub = 12 * n + 2;
+                const int a_rows = a.n_sub * lsub;
+                if ((int64_t)a_rows - 2 * P > 2 * T && n > 3) continue;       // short rows: keep enough tiles
+                const int tt = (a_rows - 2 * P) / 16 * 16;
+                if (tt < 16) break;
+                const int n_mb = (tt + 127) / 128;
+                const int rows_alloc = (n_mb * 128 + 2 * P > a_rows ? n_mb * 128 + 2 * P : a_rows) | 1;   // MMA reach and phase-1 rows
+                const int xin_rows = xs ? a_rows + 11 : 0;
+                const size_t smem_tc = 128 + wb + (size_t)nstrip * rows_alloc * 16 + (size_t)xin_rows * C * 2;
+                if (n_mb > afa::kAcMaxBlocks || n_mb * npad > 512 || smem_tc > 110 * 1024) continue;
+                c = Cfg{lsub, a_rows, tt, n_mb, rows_alloc, xin_rows, smem_tc, true};
+                break;
+            }
+            return c;
+        };
+        Cfg cfg = pick(false);
+        bool xs = false;
+        if (xs_ok) {
+            const Cfg cx = pick(true);
+            if (cx.ok && (!cfg.ok || 5 * cx.tt >= 4 * cfg.tt)) { cfg = cx; xs = true; }
+        }
+        if (cfg.ok) {
             afa::ActConvTcArgs ta;
-            a.Lsub = lsub; a.a_rows = a_rows; a.TT = tt; a.a_stride = 8; a.w_stride = 8;
-            a.n_tiles = (int32_t)((T + tt - 1) / tt);
+            a.Lsub = cfg.lsub; a.a_rows = cfg.a_rows; a.TT = cfg.tt; a.a_stride = 8; a.w_stride = 8;
+            a.n_tiles = (int32_t)((T + cfg.tt - 1) / cfg.tt);
             ta.a = a;
-            ta.rows_alloc = rows_alloc;
-            ta.n_mb = n_mb;
+            ta.rows_alloc = cfg.rows_alloc;
+            ta.n_mb = cfg.n_mb;
+            ta.xin_rows = cfg.xin_rows;
             int cols = 32;
-            while (cols < n_mb * npad) cols *= 2;
+            while (cols < cfg.n_mb * npad) cols *= 2;
             ta.tmem_cols = cols;
             const int64_t grid_tc = (int64_t)a.n_tiles * batch;
             if (grid_tc >= (1ll << 31)) return fail(AFA_ERR_TOO_LARGE, "too many tiles");
-            return res ? launch_actconv_tc<true>(ta, smem_tc, (uint32_t)grid_tc, st) : launch_actconv_tc<false>(ta, smem_tc, (uint32_t)grid_tc, st);
+            if (xs) return launch_actconv_tc_xs(ta, cfg.smem, (uint32_t)grid_tc, st);
+            return res ? launch_actconv_tc<true>(ta, cfg.smem, (uint32_t)grid_tc, st) : launch_actconv_tc<false>(ta, cfg.smem, (uint32_t)grid_tc, st);
         }
     }
+    // legacy mma.sync path: row-major tiles, rows padded by 8 elements (conflict-free ldmatrix)
     a.a_stride = cpad + 8;
     a.w_stride = cpad + 8;
-    // sub-segment length 12 n + 2: as long as two CTAs still fit in shared memory (about 100 KB each), shorter
-    // for short rows so that a launch keeps enough tiles
     const size_t w_bytes = (size_t)kernel_size * C * a.w_stride * 2;
     int n = 7;
     while (n > 2 && w_bytes + (size_t)a.n_sub * (12 * n + 2) * a.a_stride * 2 > 100 * 1024) --n;

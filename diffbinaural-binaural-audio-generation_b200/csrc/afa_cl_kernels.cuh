@@ -93,6 +93,7 @@ template <typename T> struct ClRaw;
 template <> struct ClRaw<float> {
     using raw_t = float;
     static __device__ __forceinline__ raw_t load(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ raw_t load_smem(const float* p) { return *p; }
     static __device__ __forceinline__ float cvt(raw_t v) {
         float o;
         asm volatile("mov.b32 %0, %1;" : "=f"(o) : "f"(v));
@@ -103,6 +104,11 @@ template <> struct ClRaw<__nv_bfloat16> {
     using raw_t = uint32_t;
     static __device__ __forceinline__ raw_t load(const __nv_bfloat16* p) {
         return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p));
+    }
+    static __device__ __forceinline__ raw_t load_smem(const __nv_bfloat16* p) {       // p points into shared memory
+        uint32_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+        return v;
     }
     static __device__ __forceinline__ float cvt(raw_t v) {
         uint32_t o;
@@ -155,7 +161,7 @@ struct TileSink {
 // SINK 0: store y;  SINK 1: feed conv_post (tail kernel; all 32 lanes walk in lockstep);  SINK 2: write the
 // activated sample as bf16 into a shared-memory tile (zero outside the row: the convolution's zero padding).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE, bool RES, int SINK>
+template <typename T, int MODE, bool RES, int SINK, bool XSM = false>
 __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __restrict__ pr, T* __restrict__ ps,
                                         T* __restrict__ py, const int Cs, const int t0, const int L, const int Tlen,
                                         const float a, const float ib, const float bias, const FwdTaps& tp,
@@ -174,7 +180,7 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
             const T* q = RES ? pr + (int64_t)tb * Cs : nullptr;
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                xq[i] = raw::load(p);
+                xq[i] = XSM ? raw::load_smem(p) : raw::load(p);      // XSM: x was staged in shared memory by a bulk copy
                 p += Cs;
                 if (RES) { rq[i] = raw::load(q); q += Cs; }
             }
@@ -190,7 +196,7 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
 #pragma unroll
             for (int i = 0; i < S; ++i) {
                 const int64_t o = (int64_t)min(max(tb + i, 0), Tlen - 1) * Cs;
-                xq[i] = raw::load(px + o);
+                xq[i] = XSM ? raw::load_smem(px + o) : raw::load(px + o);
                 if (RES) rq[i] = raw::load(pr + o);
             }
         }
@@ -219,7 +225,7 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
     if (MODE != 0) {
         auto xval = [&](int t) -> float {
             const int64_t o = (int64_t)min(max(t, 0), Tlen - 1) * Cs;
-            float v = cl_load(px + o);
+            float v = XSM ? raw::cvt(raw::load_smem(px + o)) : cl_load(px + o);
             if (RES) v += cl_load(pr + o);
             return v + bias;
         };

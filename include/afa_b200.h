@@ -178,6 +178,7 @@ int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
  * (odd, one of the compiled values), threads = CTA size.  0 keeps the built-in choice.
  * which=2: channels-last forward, segment length = 12 * chunks + 2 samples.
  * which=3: tensor path of the fused activation+convolution: chunks = 1 tcgen05 (default), 0 legacy mma.sync.
+ * which=4: its input staging: chunks = 1 bulk-copy the tile's input rows into shared memory (default), 0 global loads.
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
  * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects.
  */

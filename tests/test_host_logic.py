@@ -51,7 +51,7 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.afa_activation1d_fwd(vp(16), vp(32), vp(64), vp(64), taps, taps, -1, 1, 8, 0, 0, None) == -1
     assert lib.afa_activation1d_fwd(vp(18), vp(32), vp(64), vp(64), taps, taps, 1, 1, 8, 0, 0, None) == -5  # 2-byte aligned fp32
     assert lib.afa_activation1d_fwd(vp(16), vp(32), vp(64), vp(64), taps, taps, 1 << 20, 1 << 12, 1 << 20, 0, 0, None) == -3
-    assert lib.afa_set_tuning(0, 4, 0) == -1 and lib.afa_set_tuning(4, 0, 0) == -1 and lib.afa_set_tuning(3, 2, 0) == -1
+    assert lib.afa_set_tuning(0, 4, 0) == -1 and lib.afa_set_tuning(5, 0, 0) == -1 and lib.afa_set_tuning(3, 2, 0) == -1
     assert lib.afa_set_tuning(0, 9, 0) == 0 and lib.afa_set_tuning(0, 0, 0) == 0
     assert lib.afa_set_tuning(2, 4, 0) == 0 and lib.afa_set_tuning(2, 0, 0) == 0 and lib.afa_set_tuning(2, -1, 0) == -1
     # channels-last AMP entry points: argument checks come before any CUDA call

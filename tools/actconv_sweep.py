@@ -15,6 +15,7 @@ B = int(os.environ.get("SWEEP_B", "8"))
 h = F_afa.host_taps(kaiser_sinc_filter1d(0.25, 0.3, 12))
 dt = torch.bfloat16
 _lib.set_tuning(3, int(os.environ.get('TC_PATH', '1')))
+_lib.set_tuning(4, int(os.environ.get('TC_XS', '1')))
 
 
 def timeit(fn, n=10):

@@ -25,6 +25,7 @@ for C in (8, 16, 24, 32, 48, 64):
             tag = f"C={C} k={k} d={d} T={T} B={B} res={with_res}"
             try:
                 _lib.set_tuning(3, int(os.environ.get('TC_PATH', '1')))
+                _lib.set_tuning(4, int(os.environ.get('TC_XS', '1')))
                 y = FC.amp_act_conv_cl(x, T, alpha, beta, h, h, True, w, k, d, bias=bias, **kw)
                 torch.cuda.synchronize()
                 _lib.set_tuning(3, 0)
