@@ -407,6 +407,76 @@ def run_cl_step(dev, clips: int, t_mel: int, steps: int = 5):
             "kernels": "afa_cl_fwd_kernel<bf16,false> x72, <bf16,true> x36, afa_mean_kernel x6, afa_cl_tail_kernel x1"}
 
 
+def run_mel_step(dev, batch: int = 32, segment: int = 8192, reps: int = 20):
+    """Training-side neighbour: the log-mel work of one BASELINE config 5 step -- the single-scale
+    mel of a [batch, segment] waveform (train_binaural_mel.py:711-720) and the seven-scale log mels of estimate and target
+    (loss.py:185-200) -- as fused afa_logmel_fwd launches, next to the reference's torch-op chains on the same GPU.
+    CUDA events; tensors are L2-resident by nature (1 MB of audio per batch)."""
+    import torch
+
+    from afa_b200 import mel as P
+    sr = 22050
+    hann = {w: torch.hann_window(w, device=dev) for w in (32, 64, 128, 256, 512, 1024, 2048)}
+
+    def chain_single(w, basis):       # the op sequence of meldataset.py:95-118 (torch ops on this GPU: the baseline beside the kernel)
+        p = torch.nn.functional.pad(w.unsqueeze(1), (384, 384), mode="reflect").squeeze(1)
+        spec = torch.stft(p, 1024, hop_length=256, win_length=1024, window=hann[1024], center=False, pad_mode="reflect",
+                          normalized=False, onesided=True, return_complex=True)
+        spec = torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1) + 1e-9)
+        return torch.log(torch.clamp(torch.matmul(basis, spec), min=1e-5))
+
+    def chain_scale(wav, basis, n):   # loss.py:110-167 + :195-197 for one scale
+        B, C, T = wav.shape
+        stft = torch.stft(wav.reshape(-1, T), n_fft=n, hop_length=n // 4, window=hann[n], return_complex=True, center=True)
+        mag = torch.abs(stft).reshape(B, C, stft.shape[1], stft.shape[2])
+        mels = (mag.transpose(2, -1) @ basis.T).transpose(-1, 2)
+        return torch.log(mels.clamp(min=1e-5)) / torch.log(torch.tensor(10.0))
+
+    torch.manual_seed(1234)
+    y = (0.3 * torch.randn(batch, segment, device=dev)).clamp(-1, 1)
+    yh = (y + 0.05 * torch.randn_like(y)).clamp(-1, 1)
+    plan1 = P.MelPlan(1024, torch.hann_window(1024, dtype=torch.float64), P.slaney_mel_filterbank(sr, 1024, 80), dev)
+    msl = P.MultiScaleMelSpectrogramLoss(sr)
+    bases = [torch.from_numpy(P.slaney_mel_filterbank(sr, w, nm)).to(dev) for w, nm in zip(msl.window_lengths, msl.n_mels)]
+    basis1 = torch.from_numpy(P.slaney_mel_filterbank(sr, 1024, 80)).to(dev)
+    y3, yh3 = y.unsqueeze(1), yh.unsqueeze(1)
+
+    def ours_single():
+        return P.logmel(yh, plan1, 256, 384)
+
+    def ours_multi():
+        return [(msl.log_mels(yh3, s), msl.log_mels(y3, s)) for s in range(7)]
+
+    def torch_single():
+        return chain_single(yh, basis1)
+
+    def torch_multi():
+        return [(chain_scale(yh3, bases[s], msl.window_lengths[s]), chain_scale(y3, bases[s], msl.window_lengths[s]))
+                for s in range(7)]
+
+    def timed(fn):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    with torch.no_grad():
+        err = float((ours_single() - torch_single()).abs().max())
+    frames = sum(2 * batch * P.num_frames(segment, w, w // 4, w // 2) for w in msl.window_lengths)
+    out = {"shape": [batch, segment], "single_scale_us": round(timed(ours_single), 2), "single_scale_torch_ops_us": round(timed(torch_single), 2),
+           "multi_scale_14_launches_us": round(timed(ours_multi), 2), "multi_scale_torch_ops_us": round(timed(torch_multi), 2),
+           "multi_scale_frames": frames, "max_abs_diff_vs_torch_ops_log_mel": err,
+           "what": "eager launches incl. host overhead, CUDA events; forward only (the adjoint kernel is not built yet)"}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -533,6 +603,13 @@ def run_gpu(args):
         except Exception as exc:  # noqa: BLE001
             channels_last = {"error": repr(exc)[:200]}
 
+    mel = None
+    if not args.no_vocoder and rank == 0 and world == 1:
+        try:
+            mel = run_mel_step(dev)
+        except Exception as exc:  # noqa: BLE001
+            mel = {"error": repr(exc)[:200]}
+
     if world > 1 and wl is not None:
         # the only collective: gather one checksum per rank (stands in for gathering finished waveforms)
         chk = torch.stack([s["ys"][0].float().abs().mean() for s in wl.stages]).sum().reshape(1)
@@ -563,6 +640,7 @@ def run_gpu(args):
             "audio_sec_per_sec_activation_only": round(world * args.clips * 10.0 / (ms_per_step * 1e-3), 2),
             "vocoder": vocoder,
             "channels_last_amp_kernels": channels_last,
+            "log_mel": mel,
         }
         print(json.dumps(line))
     if world > 1:

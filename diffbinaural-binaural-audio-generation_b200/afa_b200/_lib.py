@@ -23,6 +23,8 @@ EXPORTED_SYMBOLS = (
     "afa_tail_fwd_cl",
     "afa_amp_act_conv_supported",
     "afa_amp_act_conv_fwd_cl",
+    "afa_logmel_num_frames",
+    "afa_logmel_fwd",
     "afa_set_tuning",
     "afa_kernel_info",
     "afa_kernel_info_shape",
@@ -75,6 +77,12 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_amp_act_conv_fwd_cl.restype = i32
         lib.afa_amp_act_conv_fwd_cl.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, fp, fp, vp, i32, i32,
                                                 i64, i64, i64, i32, i32, vp]
+        ip = ctypes.POINTER(ctypes.c_int32)
+        lib.afa_logmel_num_frames.restype = i64
+        lib.afa_logmel_num_frames.argtypes = [i64, i32, i32, i32]
+        lib.afa_logmel_fwd.restype = i32
+        lib.afa_logmel_fwd.argtypes = [fp, fp, i64, i64, i64, i32, i32, i32, i32, fp, fp, i32, ip, ip, ip, fp,
+                                       f32, f32, f32, i32, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32

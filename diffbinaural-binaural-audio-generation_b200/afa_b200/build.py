@@ -17,13 +17,20 @@ def library_path() -> str:
     return os.path.join(_HERE, LIB_NAME)
 
 
+_COMMON = [os.path.join(_INCLUDE, "afa_b200.h"), os.path.join(_CSRC, "afa_internal.h")]
+# translation unit -> the headers only it includes (an object is rebuilt when its unit, its headers or _COMMON change)
+_UNITS = {
+    "afa_capi.cu": ["afa_kernels.cuh", "afa_cl_kernels.cuh", "afa_actconv_kernels.cuh"],
+    "afa_mel.cu": [],
+}
+
+
 def _sources():
-    return [os.path.join(_CSRC, "afa_capi.cu")]
+    return [os.path.join(_CSRC, u) for u in _UNITS]
 
 
 def _deps():
-    return _sources() + [os.path.join(_CSRC, "afa_kernels.cuh"), os.path.join(_CSRC, "afa_cl_kernels.cuh"), os.path.join(_CSRC, "afa_actconv_kernels.cuh"),
-                         os.path.join(_INCLUDE, "afa_b200.h")]
+    return _sources() + [os.path.join(_CSRC, h) for hs in _UNITS.values() for h in hs] + _COMMON
 
 
 def _nvcc() -> str:
@@ -41,18 +48,27 @@ def build_library(force: bool = False, verbose: bool = False, out: str | None = 
         t = os.path.getmtime(out)
         if all(os.path.getmtime(d) <= t for d in _deps()):
             return out
-    cmd = [
-        _nvcc(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-lineinfo", "-std=c++17",
-        "-Xptxas", "-v" if verbose else "-O3",
-        "-I", _INCLUDE, "-I", _CSRC,
-        "--shared", "-Xcompiler", "-fPIC",
-        "-o", out,
-    ] + [f"-D{d}" for d in defines] + _sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+    nvcc = _nvcc()
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+             "-Xptxas", "-v" if verbose else "-O3", "-I", _INCLUDE, "-I", _CSRC, "-Xcompiler", "-fPIC"] + [f"-D{d}" for d in defines]
+
+    def run(cmd):
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if verbose:
+            print(proc.stderr)
+
+    # one object per translation unit, cached next to the library (variants built elsewhere keep their own objects)
+    objdir = os.path.join(os.path.dirname(out), "_obj" if out == library_path() else "_obj_" + os.path.basename(out))
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for unit, headers in _UNITS.items():
+        src = os.path.join(_CSRC, unit)
+        obj = os.path.join(objdir, unit[:-3] + ".o")
+        deps = [src] + [os.path.join(_CSRC, h) for h in headers] + _COMMON
+        if force or defines or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
+            run([nvcc] + flags + ["-c", src, "-o", obj])
+        objs.append(obj)
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", out] + objs)
     return out

@@ -1,0 +1,226 @@
+"""Fused log-mel spectrogram on sm_100a behind the reference's own function signatures (forward).
+
+    mel_spectrogram(...)                 <->  BigVGAN/meldataset.py:51-123 (same arguments, same [B, n_mels, frames] result)
+    MultiScaleMelSpectrogramLoss(...)    <->  BigVGAN/loss.py:23-211 (same constructor; forward under no_grad, see below)
+
+One `afa_logmel_fwd` launch (csrc/afa_mel.cu) replaces pad -> torch.stft -> pow/sum/sqrt -> matmul -> clamp -> log.
+There is no CPU or eager fallback: CPU tensors raise.
+
+The filterbank comes from `librosa.filters.mel` in the reference (third-party, absent from this image); the
+`slaney_mel_filterbank` below follows librosa's published algorithm (htk=False, norm='slaney') and a caller that has
+its own basis (a checkpointed one, or librosa's) passes it as `mel_basis=`.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from ._lib import check, load_library  # noqa: F401  (check is re-exported for callers of the raw C ABI)
+
+AFA_MEL_PAD_REFLECT = 0
+AFA_MEL_PAD_ZERO = 1
+AFA_MEL_FLAG_RAW = 1
+
+
+def slaney_mel_filterbank(sr: float, n_fft: int, n_mels: int, fmin: float = 0.0, fmax=None) -> np.ndarray:
+    """float32 [n_mels, 1 + n_fft // 2]: triangular filters on Slaney's mel scale (linear to 1 kHz, then 27 steps per
+    factor 6.4), each normalised to unit area in Hz -- what `librosa_mel_fn(sr=, n_fft=, n_mels=, fmin=, fmax=)` gives
+    at meldataset.py:89-91 and loss.py:106-108."""
+    fmax = float(sr) / 2.0 if fmax is None else float(fmax)
+    step_hz, knee_hz, log_step = 200.0 / 3.0, 1000.0, math.log(6.4) / 27.0
+    knee_mel = knee_hz / step_hz
+
+    def to_mel(f):
+        return f / step_hz if f < knee_hz else knee_mel + math.log(f / knee_hz) / log_step
+
+    def to_hz(m):
+        return np.where(m < knee_mel, m * step_hz, knee_hz * np.exp(log_step * (m - knee_mel)))
+
+    edges = to_hz(np.linspace(to_mel(float(fmin)), to_mel(fmax), n_mels + 2))       # n_mels + 2 band edges in Hz
+    bins = np.linspace(0.0, float(sr) / 2.0, 1 + n_fft // 2)
+    rising = (bins[None, :] - edges[:-2, None]) / (edges[1:-1] - edges[:-2])[:, None]
+    falling = (edges[2:, None] - bins[None, :]) / (edges[2:] - edges[1:-1])[:, None]
+    tri = np.clip(np.minimum(rising, falling), 0.0, None)
+    return (tri * (2.0 / (edges[2:] - edges[:-2]))[:, None]).astype(np.float32)
+
+
+class MelPlan:
+    """Device-resident constants of one (n_fft, window, mel basis) configuration: window, FFT twiddles and the banded
+    form of the basis.  Built once per configuration and device, like the reference's mel_basis_cache /
+    hann_window_cache (meldataset.py:47-48, 86-93)."""
+
+    def __init__(self, n_fft: int, window: torch.Tensor, mel_basis, device):
+        if n_fft & (n_fft - 1) or not 32 <= n_fft <= 2048:
+            raise ValueError(f"n_fft must be a power of two in [32, 2048], got {n_fft} (no other STFT size is built)")
+        window = window.detach().to(torch.float64).cpu()
+        if window.numel() > n_fft:
+            raise ValueError("win_size must not exceed n_fft")
+        if window.numel() < n_fft:                      # torch.stft centres a short window inside n_fft
+            left = (n_fft - window.numel()) // 2
+            window = torch.nn.functional.pad(window, (left, n_fft - window.numel() - left))
+        basis = np.asarray(mel_basis.detach().cpu() if isinstance(mel_basis, torch.Tensor) else mel_basis, dtype=np.float32)
+        if basis.ndim != 2 or basis.shape[1] != n_fft // 2 + 1:
+            raise ValueError(f"mel basis must be [n_mels, {n_fft // 2 + 1}], got {basis.shape}")
+        starts, lens, offs, weights = banded(basis)
+        t = np.arange(n_fft // 2, dtype=np.float64) * (2.0 * np.pi / n_fft)
+        tw = np.stack([np.cos(t), -np.sin(t)], axis=1).astype(np.float32)
+        self.n_fft = n_fft
+        self.n_mels = int(basis.shape[0])
+        self.device = torch.device(device)
+        self.window = window.to(torch.float32).to(self.device)
+        self.twiddle = torch.from_numpy(tw).to(self.device)
+        self.band_start = torch.from_numpy(starts).to(self.device)
+        self.band_len = torch.from_numpy(lens).to(self.device)
+        self.band_off = torch.from_numpy(offs).to(self.device)
+        self.band_w = torch.from_numpy(weights).to(self.device)
+
+
+def banded(basis: np.ndarray):
+    """Dense [n_mels, n_freq] -> (first bin, run length, offset, packed weights): every row's non-zero support as one
+    contiguous run (interior zeros, if any, stay in the run, so the contraction is exact)."""
+    n_mels = basis.shape[0]
+    starts = np.zeros(n_mels, dtype=np.int32)
+    lens = np.zeros(n_mels, dtype=np.int32)
+    offs = np.zeros(n_mels, dtype=np.int32)
+    packed = []
+    total = 0
+    for m in range(n_mels):
+        nz = np.flatnonzero(basis[m])
+        if nz.size:
+            starts[m], lens[m] = nz[0], nz[-1] - nz[0] + 1
+            packed.append(basis[m, nz[0]:nz[-1] + 1])
+        offs[m] = total
+        total += int(lens[m])
+    weights = np.concatenate(packed).astype(np.float32) if packed else np.zeros(1, dtype=np.float32)
+    return starts, lens, offs, np.ascontiguousarray(weights)
+
+
+def num_frames(T: int, n_fft: int, hop: int, pad: int) -> int:
+    return int(load_library().afa_logmel_num_frames(T, n_fft, hop, pad))
+
+
+def logmel(wav: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad_mode: int = AFA_MEL_PAD_REFLECT, mag_eps: float = 1e-9,
+           clamp_eps: float = 1e-5, log_scale: float = 1.0, raw: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[rows, T] float32 CUDA -> [rows, n_mels, n_frames] float32: one launch of afa_logmel_fwd on the current stream."""
+    if not wav.is_cuda:
+        raise RuntimeError("afa_b200.mel: the fused log-mel kernel needs a CUDA tensor (there is no CPU fallback)")
+    if wav.dtype != torch.float32 or wav.dim() != 2:
+        raise TypeError(f"afa_b200.mel: expected a float32 [rows, T] tensor, got {wav.dtype} {tuple(wav.shape)}")
+    if wav.device != plan.device:
+        raise RuntimeError(f"afa_b200.mel: plan lives on {plan.device}, waveform on {wav.device}")
+    if wav.stride(1) != 1:
+        wav = wav.contiguous()
+    rows, T = wav.shape
+    if pad_mode == AFA_MEL_PAD_REFLECT and pad >= T:
+        raise RuntimeError(f"Padding size should be less than the corresponding input dimension, but got: padding ({pad}, {pad}) "
+                           f"at dimension 1 of input {tuple(wav.shape)}")   # F.pad's message for the same input
+    nf = num_frames(T, plan.n_fft, hop, pad)
+    if out is None:
+        out = torch.empty(rows, plan.n_mels, nf, device=wav.device, dtype=torch.float32)
+    elif tuple(out.shape) != (rows, plan.n_mels, nf) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("afa_b200.mel: `out` must be a contiguous float32 [rows, n_mels, n_frames] tensor")
+    lib = load_library()
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+
+    def f(t):
+        return ctypes.cast(t.data_ptr(), fp)
+
+    def i(t):
+        return ctypes.cast(t.data_ptr(), ip)
+
+    with torch.cuda.device(wav.device):
+        rc = lib.afa_logmel_fwd(f(wav), f(out), rows, T, wav.stride(0) if rows > 1 else T, plan.n_fft, hop, pad, pad_mode,
+                                f(plan.window), f(plan.twiddle), plan.n_mels, i(plan.band_start), i(plan.band_len),
+                                i(plan.band_off), f(plan.band_w), mag_eps, clamp_eps, log_scale,
+                                AFA_MEL_FLAG_RAW if raw else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    check(rc, "afa_logmel_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# the reference's public functions
+# --------------------------------------------------------------------------------------
+mel_plan_cache: dict = {}
+
+
+def mel_spectrogram(y: torch.Tensor, n_fft: int, num_mels: int, sampling_rate: int, hop_size: int, win_size: int, fmin: int,
+                    fmax: int = None, center: bool = False, *, mel_basis=None, check_range: bool = True) -> torch.Tensor:
+    """Drop-in for BigVGAN/meldataset.py:51-123: log(clamp(mel_basis @ |STFT(y)|, 1e-5)).
+
+    y: [B, T] (reflect-padded by (n_fft - hop_size) // 2, :98-101) or [T] (zero-padded, :96-97; the result then has
+    no batch dimension, as torch.stft returns for 1-D input).  `check_range=False` skips the reference's two
+    out-of-[-1, 1] warnings (:78-81), which cost a device synchronisation each."""
+    if center:
+        raise NotImplementedError("center=True is not used by the reference (meldataset.py:110 passes center=False)")
+    if check_range:
+        lo, hi = torch.aminmax(y)
+        if lo < -1.0:
+            print(f"[WARNING] Min value of input waveform signal is {lo}")
+        if hi > 1.0:
+            print(f"[WARNING] Max value of input waveform signal is {hi}")
+    key = f"{n_fft}_{num_mels}_{sampling_rate}_{hop_size}_{win_size}_{fmin}_{fmax}_{y.device}" if mel_basis is None else None
+    plan = mel_plan_cache.get(key) if key else None
+    if plan is None:
+        basis = slaney_mel_filterbank(sampling_rate, n_fft, num_mels, fmin, fmax) if mel_basis is None else mel_basis
+        plan = MelPlan(n_fft, torch.hann_window(win_size, dtype=torch.float64), basis, y.device)
+        if key:
+            mel_plan_cache[key] = plan
+    pad = (n_fft - hop_size) // 2
+    if y.dim() == 1:
+        return logmel(y.unsqueeze(0), plan, hop_size, pad, AFA_MEL_PAD_ZERO)[0]
+    if y.dim() != 2:
+        raise RuntimeError(f"mel_spectrogram expects a [B, T] or [T] waveform, got {tuple(y.shape)}")
+    return logmel(y, plan, hop_size, pad, AFA_MEL_PAD_REFLECT)
+
+
+class MultiScaleMelSpectrogramLoss(torch.nn.Module):
+    """BigVGAN/loss.py:23-211 with the fused kernel: seven (window, n_mels) scales, log10 of the clamped mels, L1.
+
+    Forward only in this round: the kernel has no backward yet, so an input that requires grad raises instead of
+    silently cutting the graph (training keeps the reference's torch-op loss until the adjoint kernel lands)."""
+
+    def __init__(self, sampling_rate: int, n_mels=(5, 10, 20, 40, 80, 160, 320), window_lengths=(32, 64, 128, 256, 512, 1024, 2048),
+                 loss_fn=None, clamp_eps: float = 1e-5, mag_weight: float = 0.0, log_weight: float = 1.0, pow: float = 1.0,
+                 weight: float = 1.0, match_stride: bool = False, mel_fmin=(0, 0, 0, 0, 0, 0, 0),
+                 mel_fmax=(None, None, None, None, None, None, None), window_type: str = "hann"):
+        super().__init__()
+        if match_stride or window_type != "hann" or pow != 1.0:
+            raise NotImplementedError("only the configuration the reference trains with is built "
+                                      "(match_stride=False, hann, pow=1.0; train_binaural_mel.py:458-460)")
+        self.sampling_rate = sampling_rate
+        self.n_mels = list(n_mels)
+        self.window_lengths = list(window_lengths)
+        self.loss_fn = loss_fn if loss_fn is not None else torch.nn.L1Loss()
+        self.clamp_eps, self.mag_weight, self.log_weight, self.weight = clamp_eps, mag_weight, log_weight, weight
+        self.mel_fmin, self.mel_fmax = list(mel_fmin), list(mel_fmax)
+        self._plans: dict = {}
+
+    def _plan(self, scale: int, device) -> MelPlan:
+        key = (scale, str(device))
+        if key not in self._plans:
+            w, nm = self.window_lengths[scale], self.n_mels[scale]
+            basis = slaney_mel_filterbank(self.sampling_rate, w, nm, self.mel_fmin[scale], self.mel_fmax[scale])
+            self._plans[key] = MelPlan(w, torch.hann_window(w, dtype=torch.float64), basis, device)
+        return self._plans[key]
+
+    def log_mels(self, wav: torch.Tensor, scale: int) -> torch.Tensor:
+        """[B, C, T] -> [B, C, n_mels, frames]: log10(clamp(mel, clamp_eps)) of one scale (loss.py:195-200)."""
+        B, C, T = wav.shape
+        w = self.window_lengths[scale]
+        out = logmel(wav.reshape(B * C, T), self._plan(scale, wav.device), w // 4, w // 2, AFA_MEL_PAD_REFLECT, mag_eps=0.0,
+                     clamp_eps=self.clamp_eps, log_scale=1.0 / math.log(10.0))
+        return out.view(B, C, out.shape[1], out.shape[2])
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+            raise NotImplementedError("afa_b200.mel.MultiScaleMelSpectrogramLoss has no backward yet: call it under torch.no_grad() "
+                                      "(validation), or keep the reference loss for the training step")
+        losses = []
+        for s in range(len(self.window_lengths)):
+            lx, ly = self.log_mels(x, s), self.log_mels(y, s)
+            losses.append(self.log_weight * self.loss_fn(lx, ly))
+            losses.append(self.mag_weight * self.loss_fn(lx, ly))     # the reference compares the log mels in both terms (:206-207)
+        return sum(losses)

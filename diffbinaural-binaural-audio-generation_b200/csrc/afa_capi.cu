@@ -8,6 +8,7 @@
 #include <atomic>
 
 #include "afa_b200.h"
+#include "afa_internal.h"
 #include "afa_kernels.cuh"
 #include "afa_cl_kernels.cuh"
 #include "afa_actconv_kernels.cuh"
@@ -243,6 +244,18 @@ size_t kernel_smem(int which) {
 }
 
 }  // namespace
+
+namespace afa_internal {
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_error(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace afa_internal
 
 extern "C" {
 

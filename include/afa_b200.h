@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 120            /* 0.1.2: + AMP-block entry points on channels-last activations, fused activation -> convolution */
+#define AFA_VERSION 130            /* 0.1.3: + fused log-mel spectrogram (training-side neighbour of the path) */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
@@ -171,6 +171,36 @@ int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
                             const void *w_kcc, int kernel_size, int dilation,
                             int64_t batch, int64_t channels, int64_t T,
                             int dtype, int flags, void *stream);
+
+/*
+ * Fused log-mel spectrogram (forward): one launch for
+ *   reflect/zero pad -> STFT (n_fft-point, hop, window) -> sqrt(re^2 + im^2 + mag_eps) -> mel_basis @ magnitudes
+ *   -> log(max(., clamp_eps)) * log_scale
+ *   <->  mel_spectrogram                                      BigVGAN/meldataset.py:51-123
+ *        (pad = (n_fft - hop) / 2, center=False, mag_eps = 1e-9, clamp_eps = 1e-5, log_scale = 1; called at
+ *         BigVGAN/train_binaural_mel.py:386, 640, 711 and BigVGAN/inference.py)
+ *   <->  MultiScaleMelSpectrogramLoss.mel_spectrogram + log10  BigVGAN/loss.py:110-167, 195-200
+ *        (center=True => pad = n_fft / 2, mag_eps = 0, clamp_eps = 1e-5, log_scale = 1 / ln 10)
+ * wav:  float32 device array [rows][row_pitch], T valid samples per row.
+ * out:  float32 device array [rows][n_mels][n_frames], n_frames = afa_logmel_num_frames(T, n_fft, hop, pad).
+ * n_fft: power of two in [32, 2048].  window: float32 device [n_fft] (a shorter window is zero-padded to n_fft
+ *   and centred by the caller, as torch.stft does).  twiddle: float32 device [n_fft / 2][2] = (cos, -sin)(2 pi t / n_fft).
+ * The mel basis is passed in banded form, built by the caller from the dense [n_mels][n_fft / 2 + 1] matrix the
+ * reference caches (meldataset.py:89-93): row m is non-zero on bins [band_start[m], band_start[m] + band_len[m])
+ * and its weights there are band_w[band_off[m] ...] (all device arrays; int32 / float32).
+ * pad_mode: AFA_MEL_PAD_REFLECT (2-D input in the reference) or AFA_MEL_PAD_ZERO (its 1-D input branch, :96-97).
+ * flags: AFA_MEL_FLAG_RAW writes the mel magnitudes without clamp / log.
+ */
+#define AFA_MEL_PAD_REFLECT 0
+#define AFA_MEL_PAD_ZERO 1
+#define AFA_MEL_FLAG_RAW 1
+int64_t afa_logmel_num_frames(int64_t T, int n_fft, int hop, int pad);
+int afa_logmel_fwd(const float *wav, float *out, int64_t rows, int64_t T, int64_t row_pitch,
+                   int n_fft, int hop, int pad, int pad_mode,
+                   const float *window, const float *twiddle,
+                   int n_mels, const int32_t *band_start, const int32_t *band_len, const int32_t *band_off,
+                   const float *band_w,
+                   float mag_eps, float clamp_eps, float log_scale, int flags, void *stream);
 
 /*
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).

@@ -70,3 +70,28 @@ def activation1d_torch_grads(x, gy, alpha, beta, logscale: bool, taps_up, taps_d
     y = activation1d_torch(x, alpha, beta_, logscale, taps_up, taps_down)
     y.backward(gy)
     return x.grad, alpha.grad, (None if beta_ is None else beta_.grad)
+
+
+# --------------------------------------------------------------------------------------
+# log-mel spectrogram: the reference's torch-op chains, restated
+# --------------------------------------------------------------------------------------
+def mel_spectrogram_torch(y, mel_basis, n_fft: int, hop_size: int, win_size: int):
+    """meldataset.py:95-118 for a [B, T] waveform (reflect pad, hann, center=False); mel_basis [n_mels, n_fft/2+1]
+    is what the reference caches at :89-92."""
+    pad = (n_fft - hop_size) // 2
+    y = F.pad(y.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    spec = torch.stft(y, n_fft, hop_length=hop_size, win_length=win_size, window=torch.hann_window(win_size).to(y.device),
+                      center=False, pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    spec = torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1) + 1e-9)
+    return torch.log(torch.clamp(torch.matmul(mel_basis, spec), min=1e-5))
+
+
+def msmsl_logmels_torch(wav, mel_basis, window_length: int, clamp_eps: float = 1e-5):
+    """loss.py:110-167 + :195-197 for one scale (match_stride=False): [B, C, T] -> log10 mels [B, C, n_mels, frames]."""
+    B, C, T = wav.shape
+    window = torch.hann_window(window_length, periodic=True, dtype=torch.float64).float().to(wav.device)
+    stft = torch.stft(wav.reshape(-1, T), n_fft=window_length, hop_length=window_length // 4, window=window,
+                      return_complex=True, center=True)
+    mag = torch.abs(stft).reshape(B, C, stft.shape[1], stft.shape[2])
+    mels = (mag.transpose(2, -1) @ mel_basis.T).transpose(-1, 2)
+    return torch.log(mels.clamp(min=clamp_eps)) / torch.log(torch.tensor(10.0))

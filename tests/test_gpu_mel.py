@@ -1,0 +1,198 @@
+"""GPU parity of the fused log-mel kernel (afa_logmel_fwd, through the C ABI / afa_b200.mel) against the vectors the
+reference's own `mel_spectrogram` / `MultiScaleMelSpectrogramLoss` produced (tests/golden/mel_golden.npz), the float64
+oracle, and size-independent properties at BASELINE config 5's batch.
+
+Tolerances.  Linear mel magnitudes: E = max|m - ref| / max|ref| <= 1e-5 (SURVEY.md 8d's fp32 budget; torch's own
+fp32 chain sits at ~1e-7 from the float64 oracle).  Log mels: |diff| <= 1e-4 absolute on broadband inputs (a log
+turns the relative error of a bin into an absolute one; the fixtures are broadband so no bin sits at the noise floor).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle as M
+from oracle import torch_path as TP
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda:0"
+SR = 22050
+TOL_LIN = 1e-5
+TOL_LOG = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mel_golden():
+    return dict(np.load(os.path.join(REPO, "tests", "golden", "mel_golden.npz")))
+
+
+def _P():
+    from afa_b200 import mel as P
+
+    return P
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_mel_spectrogram_matches_reference_vectors(mel_golden):
+    P = _P()
+    g = mel_golden
+    y = _dev(g["y"])
+    out = P.mel_spectrogram(y, 1024, 80, SR, 256, 1024, 0, None)
+    assert out.shape == (3, 80, 32) and out.dtype == torch.float32
+    assert np.abs(out.cpu().numpy() - g["mel_2d"]).max() <= TOL_LOG
+    assert np.abs(out.cpu().numpy() - M.mel_spectrogram(g["y"], 1024, 80, SR, 256, 1024, 0, None)).max() <= TOL_LOG
+    one = P.mel_spectrogram(y[0], 1024, 80, SR, 256, 1024, 0, None)           # 1-D branch: zero padding, no batch dim
+    assert one.shape == (80, 32)
+    assert np.abs(one.cpu().numpy() - g["mel_1d"]).max() <= TOL_LOG
+    short = P.mel_spectrogram(y[:, :1500], 1024, 80, SR, 256, 1024, 0, None)  # pitched rows, T % hop != 0
+    assert short.shape == (3, 80, 5)
+    assert np.abs(short.cpu().numpy() - g["mel_short"]).max() <= TOL_LOG
+
+
+def test_basis_argument_and_fmax(mel_golden):
+    """A caller-supplied basis (e.g. librosa's own, or a checkpointed one) is used as given."""
+    P = _P()
+    g = mel_golden
+    y = _dev(g["y"])
+    basis = g["basis_80_1024_fmax8000"]
+    a = P.mel_spectrogram(y, 1024, 80, SR, 256, 1024, 0, 8000)
+    b = P.mel_spectrogram(y, 1024, 80, SR, 256, 1024, 0, None, mel_basis=basis)
+    ref = M.mel_spectrogram(g["y"], 1024, 80, SR, 256, 1024, 0, 8000, mel_basis=basis)
+    assert np.abs(b.cpu().numpy() - ref).max() <= TOL_LOG
+    assert np.abs(a.cpu().numpy() - ref).max() <= TOL_LOG
+
+
+def test_every_multiscale_window_matches_reference_vectors(mel_golden):
+    """All seven STFT sizes the kernel is instantiated for (32 ... 2048), raw mel magnitudes."""
+    P = _P()
+    g = mel_golden
+    x = _dev(g["msl_x"])
+    B, C, T = x.shape
+    for w, nm in zip(M.MSMSL_WINDOWS, M.MSMSL_N_MELS):
+        plan = P.MelPlan(w, torch.hann_window(w, dtype=torch.float64), g[f"basis_{nm}_{w}"], DEV)
+        raw = P.logmel(x.reshape(B * C, T), plan, w // 4, w // 2, mag_eps=0.0, raw=True).view(B, C, nm, -1).cpu().numpy()
+        ref = g[f"msl_mels_{w}"]
+        assert raw.shape == ref.shape, w
+        assert np.abs(raw - ref).max() <= TOL_LIN * np.abs(ref).max(), w
+        ora = M.msmsl_mels(g["msl_x"], SR, nm, w)
+        assert np.abs(raw - ora).max() <= TOL_LIN * np.abs(ora).max(), w
+
+
+def test_multiscale_loss_matches_reference(mel_golden):
+    P = _P()
+    g = mel_golden
+    loss = P.MultiScaleMelSpectrogramLoss(SR).to(DEV)
+    with torch.no_grad():
+        v = float(loss(_dev(g["msl_x"]), _dev(g["msl_y"])))
+    assert v == pytest.approx(float(g["msl_loss"]), rel=1e-4)
+    xr = _dev(g["msl_x"]).requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        loss(xr, _dev(g["msl_y"]))
+
+
+def test_training_batch_against_oracle_and_torch_chain():
+    """BASELINE config 5's batch (32 segments of 8192 samples): fused kernel vs float64 oracle vs the torch-op chain
+    of the reference on the same device."""
+    P = _P()
+    torch.manual_seed(1234)
+    y = (0.3 * torch.randn(32, 8192, device=DEV)).clamp(-1, 1)
+    out = P.mel_spectrogram(y, 1024, 80, SR, 256, 1024, 0, None, check_range=False)
+    ref = M.mel_spectrogram(y.cpu().numpy(), 1024, 80, SR, 256, 1024, 0, None)
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL_LOG
+    basis = torch.from_numpy(M.slaney_mel_filterbank(SR, 1024, 80, 0, None)).to(DEV)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        chain = TP.mel_spectrogram_torch(y, basis, 1024, 256, 1024)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert (out - chain).abs().max().item() <= TOL_LOG
+    e_ours = np.abs(out.cpu().numpy() - ref).max()
+    e_torch = np.abs(chain.cpu().numpy() - ref).max()
+    print(f"log-mel vs float64 oracle: fused {e_ours:.2e}, torch chain {e_torch:.2e}")
+
+
+def test_size_independent_properties_at_clip_length():
+    """10 s clips (220 416 samples, 861 frames): homogeneity (bit-exact under a power-of-two gain, mag_eps = 0) and
+    shift-by-one-hop equivariance of the interior frames (bit-exact: the same samples meet the same arithmetic)."""
+    P = _P()
+    torch.manual_seed(7)
+    T, hop, n_fft = 220416, 256, 1024
+    y = 0.2 * torch.randn(4, T, device=DEV)
+    plan = P.MelPlan(n_fft, torch.hann_window(n_fft, dtype=torch.float64), M.slaney_mel_filterbank(SR, n_fft, 80), DEV)
+    pad = (n_fft - hop) // 2
+    a = P.logmel(y, plan, hop, pad, mag_eps=0.0, raw=True)
+    assert a.shape == (4, 80, 861)
+    b = P.logmel(y * 4.0, plan, hop, pad, mag_eps=0.0, raw=True)
+    assert torch.equal(b, a * 4.0)
+    shifted = torch.roll(y, -hop, dims=1)
+    c = P.logmel(shifted, plan, hop, pad, mag_eps=0.0, raw=True)
+    assert torch.equal(c[:, :, 2:-4], a[:, :, 3:-3])
+    # frames of a row do not depend on the other rows or on the launch's frame tiling
+    d = P.logmel(y[1:2, : 100 * hop], plan, hop, pad, mag_eps=0.0, raw=True)
+    assert torch.equal(d[0, :, :95], a[1, :, :95])
+    assert torch.isfinite(a).all()
+
+
+def test_edge_cases_and_errors():
+    P = _P()
+    from afa_b200._lib import AfaError
+
+    plan = P.MelPlan(64, torch.hann_window(64, dtype=torch.float64), M.slaney_mel_filterbank(SR, 64, 10), DEV)
+    empty = P.logmel(torch.zeros(0, 4096, device=DEV), plan, 16, 32)
+    assert empty.shape == (0, 10, 257)
+    too_short = P.logmel(torch.zeros(2, 40, device=DEV), plan, 16, 0)            # T < n_fft without padding: no frames
+    assert too_short.shape == (2, 10, 0)
+    with pytest.raises(RuntimeError, match="Padding size"):
+        P.logmel(torch.zeros(2, 20, device=DEV), plan, 16, 32)
+    with pytest.raises(TypeError):
+        P.logmel(torch.zeros(2, 4096, device=DEV, dtype=torch.bfloat16), plan, 16, 32)
+    silence = P.logmel(torch.zeros(2, 4096, device=DEV), plan, 16, 32)           # clamp floor, as the reference gives
+    assert torch.allclose(silence, torch.full_like(silence, math.log(1e-5)))
+    # argument checks of the C ABI itself
+    import ctypes
+
+    from afa_b200._lib import load_library
+
+    lib = load_library()
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    x = torch.zeros(1, 4096, device=DEV)
+    o = torch.zeros(1, 10, 300, device=DEV)
+    c = lambda t, ty: ctypes.cast(t.data_ptr(), ty)  # noqa: E731
+    rc = lib.afa_logmel_fwd(c(x, fp), c(o, fp), 1, 4096, 4096, 48, 16, 0, 0, c(plan.window, fp), c(plan.twiddle, fp), 10,
+                            c(plan.band_start, ip), c(plan.band_len, ip), c(plan.band_off, ip), c(plan.band_w, fp),
+                            0.0, 1e-5, 1.0, 0, None)
+    assert rc < 0 and b"power of two" in lib.afa_last_error()
+    with pytest.raises(AfaError):
+        P.check(rc, "afa_logmel_fwd")
+
+
+def test_cuda_graph_capture_and_side_stream():
+    """No allocation, no synchronisation inside the launch: capturable, and it runs on the caller's stream."""
+    P = _P()
+    torch.manual_seed(3)
+    y = 0.3 * torch.randn(8, 8192, device=DEV)
+    plan = P.MelPlan(1024, torch.hann_window(1024, dtype=torch.float64), M.slaney_mel_filterbank(SR, 1024, 80), DEV)
+    eager = P.logmel(y, plan, 256, 384)
+    out = torch.empty_like(eager)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        P.logmel(y, plan, 256, 384, out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    assert torch.equal(out, eager)
+    out.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        P.logmel(y, plan, 256, 384, out=out)
+    y.mul_(0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, P.logmel(y, plan, 256, 384))

@@ -1,0 +1,104 @@
+"""The log-mel oracle (oracle/mel_oracle.py) against vectors produced by the reference's own `mel_spectrogram` and
+`MultiScaleMelSpectrogramLoss` (tests/golden/mel_golden.npz <- tests/golden/make_golden_mel.py), the Slaney
+filterbank restatements (oracle and product) against the independent implementation stored in the same fixture,
+and the host-side logic of afa_b200/mel.py that needs no GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mel_oracle as M
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SR = 22050
+
+
+@pytest.fixture(scope="module")
+def mel_golden():
+    return dict(np.load(os.path.join(REPO, "tests", "golden", "mel_golden.npz")))
+
+
+def _basis_keys(g):
+    for k in g:
+        if k.startswith("basis_"):
+            parts = k.split("_")
+            yield k, int(parts[1]), int(parts[2]), (8000 if k.endswith("fmax8000") else None)
+
+
+def test_filterbank_restatements_match_independent_implementation(mel_golden):
+    from afa_b200.mel import slaney_mel_filterbank
+
+    n = 0
+    for k, n_mels, n_fft, fmax in _basis_keys(mel_golden):
+        ref = mel_golden[k]
+        scale = np.abs(ref).max()
+        assert np.abs(M.slaney_mel_filterbank(SR, n_fft, n_mels, 0, fmax) - ref).max() <= 1e-7 * scale, k
+        assert np.abs(slaney_mel_filterbank(SR, n_fft, n_mels, 0, fmax) - ref).max() <= 1e-6 * scale, k
+        n += 1
+    assert n == 9
+
+
+def test_filterbank_known_properties():
+    """Slaney normalisation: every filter integrates to ~1 over Hz; supports are contiguous and ordered."""
+    fb = M.slaney_mel_filterbank(SR, 1024, 80, 0, None).astype(np.float64)
+    df = SR / 1024
+    area = fb.sum(axis=1) * df
+    assert np.all(np.abs(area[10:] - 1.0) < 0.05)            # the narrow low bands sample their triangle coarsely
+    peaks = fb.argmax(axis=1)
+    assert np.all(np.diff(peaks) > 0)
+    assert M.hz_to_mel(1000.0) == pytest.approx(15.0) and M.mel_to_hz(15.0) == pytest.approx(1000.0)
+    assert M.mel_to_hz(M.hz_to_mel(np.array([50.0, 999.0, 4000.0, 11025.0]))) == pytest.approx([50.0, 999.0, 4000.0, 11025.0])
+
+
+def test_mel_spectrogram_matches_reference(mel_golden):
+    g = mel_golden
+    y = g["y"]
+    assert np.abs(M.mel_spectrogram(y, 1024, 80, SR, 256, 1024, 0, None) - g["mel_2d"]).max() <= 5e-6
+    assert np.abs(M.mel_spectrogram(y[0], 1024, 80, SR, 256, 1024, 0, None)[0] - g["mel_1d"]).max() <= 5e-6
+    short = M.mel_spectrogram(y[:, :1500], 1024, 80, SR, 256, 1024, 0, None)
+    assert short.shape == g["mel_short"].shape == (3, 80, 5)
+    assert np.abs(short - g["mel_short"]).max() <= 5e-6
+    # frames: segment_size / hop (the training invariant, train_binaural_mel.py segment 8192 -> 32 frames)
+    assert g["mel_2d"].shape == (3, 80, 8192 // 256)
+
+
+def test_multiscale_mels_and_loss_match_reference(mel_golden):
+    g = mel_golden
+    for w, nm in zip(M.MSMSL_WINDOWS, M.MSMSL_N_MELS):
+        ref = g[f"msl_mels_{w}"]
+        mine = M.msmsl_mels(g["msl_x"], SR, nm, w)
+        assert mine.shape == ref.shape
+        assert np.abs(mine - ref).max() <= 1e-6 * np.abs(ref).max(), w
+    assert M.msmsl_loss(g["msl_x"], g["msl_y"], SR) == pytest.approx(float(g["msl_loss"]), rel=1e-6)
+
+
+def test_banded_form_is_exact(mel_golden):
+    from afa_b200.mel import banded
+
+    for k, n_mels, n_fft, fmax in _basis_keys(mel_golden):
+        basis = mel_golden[k]
+        starts, lens, offs, w = banded(basis)
+        dense = np.zeros_like(basis)
+        for m in range(n_mels):
+            dense[m, starts[m]:starts[m] + lens[m]] = w[offs[m]:offs[m] + lens[m]]
+        assert np.array_equal(dense, basis), k
+        assert lens.sum() <= w.size
+
+
+def test_num_frames_and_argument_errors_without_gpu():
+    """Host-side entry points answer without a device; compute entry points refuse CPU tensors (no fallback)."""
+    import torch
+
+    from afa_b200 import mel as P
+
+    assert P.num_frames(8192, 1024, 256, 384) == 32          # center=False, pad (n_fft - hop) / 2
+    assert P.num_frames(1500, 1024, 256, 384) == 5
+    assert P.num_frames(4096, 2048, 512, 1024) == 9          # center=True
+    assert P.num_frames(100, 1024, 256, 0) == 0
+    with pytest.raises(ValueError):
+        P.MelPlan(1000, torch.hann_window(1000), np.zeros((80, 501), np.float32), "cpu")
+    plan = P.MelPlan(64, torch.hann_window(64), M.slaney_mel_filterbank(SR, 64, 10), "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.logmel(torch.zeros(2, 4096), plan, 16, 32)
+    with pytest.raises(NotImplementedError):
+        P.MultiScaleMelSpectrogramLoss(SR, match_stride=True)
