@@ -454,6 +454,20 @@ def run_mel_step(dev, batch: int = 32, segment: int = 8192, reps: int = 20):
         return [(chain_scale(yh3, bases[s], msl.window_lengths[s]), chain_scale(y3, bases[s], msl.window_lengths[s]))
                 for s in range(7)]
 
+    l1 = torch.nn.functional.l1_loss
+
+    def ours_loss_step():             # the loss_mel term of the step: forward + backward to d loss / d estimate
+        x = yh3.detach().requires_grad_(True)
+        with torch.enable_grad():
+            msl(x, y3).backward()
+        return x.grad
+
+    def torch_loss_step():
+        x = yh3.detach().requires_grad_(True)
+        with torch.enable_grad():
+            sum(l1(chain_scale(x, bases[s], msl.window_lengths[s]), chain_scale(y3, bases[s], msl.window_lengths[s])) for s in range(7)).backward()
+        return x.grad
+
     def timed(fn):
         with torch.no_grad():
             for _ in range(3):
@@ -473,7 +487,8 @@ def run_mel_step(dev, batch: int = 32, segment: int = 8192, reps: int = 20):
     out = {"shape": [batch, segment], "single_scale_us": round(timed(ours_single), 2), "single_scale_torch_ops_us": round(timed(torch_single), 2),
            "multi_scale_14_launches_us": round(timed(ours_multi), 2), "multi_scale_torch_ops_us": round(timed(torch_multi), 2),
            "multi_scale_frames": frames, "max_abs_diff_vs_torch_ops_log_mel": err,
-           "what": "eager launches incl. host overhead, CUDA events; forward only (the adjoint kernel is not built yet)"}
+           "multi_scale_loss_fwd_bwd_us": round(timed(ours_loss_step), 2), "multi_scale_loss_fwd_bwd_torch_ops_us": round(timed(torch_loss_step), 2),
+           "what": "eager launches incl. host overhead, CUDA events; loss step = 14 afa_logmel_fwd + 7 afa_logmel_bwd (2 kernels each) + torch L1"}
     return out
 
 

@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = (
     "afa_amp_act_conv_fwd_cl",
     "afa_logmel_num_frames",
     "afa_logmel_fwd",
+    "afa_logmel_bwd_workspace_bytes",
+    "afa_logmel_bwd",
     "afa_set_tuning",
     "afa_kernel_info",
     "afa_kernel_info_shape",
@@ -83,6 +85,11 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_logmel_fwd.restype = i32
         lib.afa_logmel_fwd.argtypes = [fp, fp, i64, i64, i64, i32, i32, i32, i32, fp, fp, i32, ip, ip, ip, fp,
                                        f32, f32, f32, i32, vp]
+        lib.afa_logmel_bwd_workspace_bytes.restype = ctypes.c_size_t
+        lib.afa_logmel_bwd_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
+        lib.afa_logmel_bwd.restype = i32
+        lib.afa_logmel_bwd.argtypes = [fp, fp, fp, i64, i64, i64, i64, i32, i32, i32, i32, fp, fp, i32, ip, ip, ip, fp, ip, ip,
+                                       f32, f32, f32, i32, vp, ctypes.c_size_t, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32

@@ -1,9 +1,11 @@
-"""Fused log-mel spectrogram on sm_100a behind the reference's own function signatures (forward).
+"""Fused log-mel spectrogram on sm_100a behind the reference's own function signatures.
 
     mel_spectrogram(...)                 <->  BigVGAN/meldataset.py:51-123 (same arguments, same [B, n_mels, frames] result)
-    MultiScaleMelSpectrogramLoss(...)    <->  BigVGAN/loss.py:23-211 (same constructor; forward under no_grad, see below)
+    MultiScaleMelSpectrogramLoss(...)    <->  BigVGAN/loss.py:23-211 (same constructor, same scalar loss)
 
-One `afa_logmel_fwd` launch (csrc/afa_mel.cu) replaces pad -> torch.stft -> pow/sum/sqrt -> matmul -> clamp -> log.
+One `afa_logmel_fwd` launch (csrc/afa_mel.cu) replaces pad -> torch.stft -> pow/sum/sqrt -> matmul -> clamp -> log;
+`afa_logmel_bwd` (two launches) is its adjoint, wired in as a torch.autograd.Function so that both functions are
+differentiable with respect to the waveform, as the training step needs (train_binaural_mel.py:711-787).
 There is no CPU or eager fallback: CPU tensors raise.
 
 The filterbank comes from `librosa.filters.mel` in the reference (third-party, absent from this image); the
@@ -76,6 +78,9 @@ class MelPlan:
         self.band_len = torch.from_numpy(lens).to(self.device)
         self.band_off = torch.from_numpy(offs).to(self.device)
         self.band_w = torch.from_numpy(weights).to(self.device)
+        mlo, mhi = bin_cover(starts, lens, n_fft // 2 + 1)
+        self.bin_mlo = torch.from_numpy(mlo).to(self.device)
+        self.bin_mhi = torch.from_numpy(mhi).to(self.device)
 
 
 def banded(basis: np.ndarray):
@@ -98,46 +103,120 @@ def banded(basis: np.ndarray):
     return starts, lens, offs, np.ascontiguousarray(weights)
 
 
+def bin_cover(starts: np.ndarray, lens: np.ndarray, n_freq: int):
+    """For every bin k: [mlo, mhi) bounding the filters whose run contains k (the backward kernel walks this range and
+    checks membership, so any basis is handled; for a mel basis the range is 1-3 filters)."""
+    mlo = np.zeros(n_freq, dtype=np.int32)
+    mhi = np.zeros(n_freq, dtype=np.int32)
+    first = np.full(n_freq, -1, dtype=np.int64)
+    last = np.full(n_freq, -1, dtype=np.int64)
+    for m in range(len(starts)):
+        a, b = int(starts[m]), int(starts[m] + lens[m])
+        if b > a:
+            seg = first[a:b]
+            seg[seg < 0] = m
+            last[a:b] = m
+    has = first >= 0
+    mlo[has] = first[has]
+    mhi[has] = last[has] + 1
+    return mlo, mhi
+
+
 def num_frames(T: int, n_fft: int, hop: int, pad: int) -> int:
     return int(load_library().afa_logmel_num_frames(T, n_fft, hop, pad))
 
 
-def logmel(wav: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad_mode: int = AFA_MEL_PAD_REFLECT, mag_eps: float = 1e-9,
-           clamp_eps: float = 1e-5, log_scale: float = 1.0, raw: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
-    """[rows, T] float32 CUDA -> [rows, n_mels, n_frames] float32: one launch of afa_logmel_fwd on the current stream."""
+def _fp(t):
+    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+
+
+def _ip(t):
+    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_int32))
+
+
+def _check_wav(wav: torch.Tensor, plan: MelPlan, pad: int, pad_mode: int) -> torch.Tensor:
     if not wav.is_cuda:
         raise RuntimeError("afa_b200.mel: the fused log-mel kernel needs a CUDA tensor (there is no CPU fallback)")
     if wav.dtype != torch.float32 or wav.dim() != 2:
         raise TypeError(f"afa_b200.mel: expected a float32 [rows, T] tensor, got {wav.dtype} {tuple(wav.shape)}")
     if wav.device != plan.device:
         raise RuntimeError(f"afa_b200.mel: plan lives on {plan.device}, waveform on {wav.device}")
-    if wav.stride(1) != 1:
+    if wav.stride(1) != 1 or (wav.shape[0] > 1 and wav.stride(0) < wav.shape[1]):
         wav = wav.contiguous()
-    rows, T = wav.shape
-    if pad_mode == AFA_MEL_PAD_REFLECT and pad >= T:
+    if pad_mode == AFA_MEL_PAD_REFLECT and pad >= wav.shape[1]:
         raise RuntimeError(f"Padding size should be less than the corresponding input dimension, but got: padding ({pad}, {pad}) "
                            f"at dimension 1 of input {tuple(wav.shape)}")   # F.pad's message for the same input
+    return wav
+
+
+def logmel_forward_raw(wav: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad_mode: int, mag_eps: float, clamp_eps: float,
+                       log_scale: float, raw: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """One launch of afa_logmel_fwd on the current stream (no autograd)."""
+    wav = _check_wav(wav, plan, pad, pad_mode)
+    rows, T = wav.shape
     nf = num_frames(T, plan.n_fft, hop, pad)
     if out is None:
         out = torch.empty(rows, plan.n_mels, nf, device=wav.device, dtype=torch.float32)
     elif tuple(out.shape) != (rows, plan.n_mels, nf) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("afa_b200.mel: `out` must be a contiguous float32 [rows, n_mels, n_frames] tensor")
-    lib = load_library()
-    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
-
-    def f(t):
-        return ctypes.cast(t.data_ptr(), fp)
-
-    def i(t):
-        return ctypes.cast(t.data_ptr(), ip)
-
     with torch.cuda.device(wav.device):
-        rc = lib.afa_logmel_fwd(f(wav), f(out), rows, T, wav.stride(0) if rows > 1 else T, plan.n_fft, hop, pad, pad_mode,
-                                f(plan.window), f(plan.twiddle), plan.n_mels, i(plan.band_start), i(plan.band_len),
-                                i(plan.band_off), f(plan.band_w), mag_eps, clamp_eps, log_scale,
-                                AFA_MEL_FLAG_RAW if raw else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = load_library().afa_logmel_fwd(
+            _fp(wav), _fp(out), rows, T, wav.stride(0) if rows > 1 else T, plan.n_fft, hop, pad, pad_mode,
+            _fp(plan.window), _fp(plan.twiddle), plan.n_mels, _ip(plan.band_start), _ip(plan.band_len), _ip(plan.band_off),
+            _fp(plan.band_w), mag_eps, clamp_eps, log_scale, AFA_MEL_FLAG_RAW if raw else 0,
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     check(rc, "afa_logmel_fwd")
     return out
+
+
+def logmel_backward_raw(wav: torch.Tensor, gout: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad_mode: int, mag_eps: float,
+                        clamp_eps: float, log_scale: float, raw: bool) -> torch.Tensor:
+    """d loss / d wav ([rows, T]) from gout = d loss / d out: afa_logmel_bwd (two launches) on the current stream."""
+    wav = _check_wav(wav, plan, pad, pad_mode)
+    rows, T = wav.shape
+    nf = num_frames(T, plan.n_fft, hop, pad)
+    if tuple(gout.shape) != (rows, plan.n_mels, nf):
+        raise ValueError(f"afa_b200.mel: gradient of shape {tuple(gout.shape)}, expected {(rows, plan.n_mels, nf)}")
+    gout = gout.to(torch.float32).contiguous()
+    gwav = torch.empty(rows, T, device=wav.device, dtype=torch.float32)
+    lib = load_library()
+    nbytes = int(lib.afa_logmel_bwd_workspace_bytes(rows, T, plan.n_fft, hop, pad))
+    ws = torch.empty(max(nbytes // 4, 2), device=wav.device, dtype=torch.float32)
+    with torch.cuda.device(wav.device):
+        rc = lib.afa_logmel_bwd(
+            _fp(wav), _fp(gout), _fp(gwav), rows, T, wav.stride(0) if rows > 1 else T, T, plan.n_fft, hop, pad, pad_mode,
+            _fp(plan.window), _fp(plan.twiddle), plan.n_mels, _ip(plan.band_start), _ip(plan.band_len), _ip(plan.band_off),
+            _fp(plan.band_w), _ip(plan.bin_mlo), _ip(plan.bin_mhi), mag_eps, clamp_eps, log_scale,
+            AFA_MEL_FLAG_RAW if raw else 0, ctypes.c_void_p(ws.data_ptr()), ws.numel() * 4,
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    check(rc, "afa_logmel_bwd")
+    return gwav
+
+
+class _LogMelFn(torch.autograd.Function):
+    """Saves only the waveform; the backward recomputes the spectrum inside afa_logmel_bwd."""
+
+    @staticmethod
+    def forward(ctx, wav, plan, hop, pad, pad_mode, mag_eps, clamp_eps, log_scale, raw):
+        ctx.save_for_backward(wav)
+        ctx.cfg = (plan, hop, pad, pad_mode, mag_eps, clamp_eps, log_scale, raw)
+        return logmel_forward_raw(wav, plan, hop, pad, pad_mode, mag_eps, clamp_eps, log_scale, raw)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (wav,) = ctx.saved_tensors
+        return (logmel_backward_raw(wav, gout, *ctx.cfg),) + (None,) * 8
+
+
+def logmel(wav: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad_mode: int = AFA_MEL_PAD_REFLECT, mag_eps: float = 1e-9,
+           clamp_eps: float = 1e-5, log_scale: float = 1.0, raw: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[rows, T] float32 CUDA -> [rows, n_mels, n_frames] float32; differentiable with respect to `wav`
+    (pass `out=` only outside autograd, e.g. under CUDA-graph capture with preallocated buffers)."""
+    if out is None and torch.is_grad_enabled() and wav.requires_grad:
+        return _LogMelFn.apply(wav, plan, hop, pad, pad_mode, mag_eps, clamp_eps, log_scale, raw)
+    if out is not None and torch.is_grad_enabled() and wav.requires_grad:
+        raise RuntimeError("afa_b200.mel.logmel: `out=` cannot be combined with autograd")
+    return logmel_forward_raw(wav.detach(), plan, hop, pad, pad_mode, mag_eps, clamp_eps, log_scale, raw, out)
 
 
 # --------------------------------------------------------------------------------------
@@ -177,10 +256,8 @@ def mel_spectrogram(y: torch.Tensor, n_fft: int, num_mels: int, sampling_rate: i
 
 
 class MultiScaleMelSpectrogramLoss(torch.nn.Module):
-    """BigVGAN/loss.py:23-211 with the fused kernel: seven (window, n_mels) scales, log10 of the clamped mels, L1.
-
-    Forward only in this round: the kernel has no backward yet, so an input that requires grad raises instead of
-    silently cutting the graph (training keeps the reference's torch-op loss until the adjoint kernel lands)."""
+    """BigVGAN/loss.py:23-211 with the fused kernels: seven (window, n_mels) scales, log10 of the clamped mels, L1.
+    Differentiable with respect to both waveforms (the L1 and the sum stay torch ops on the small log-mel tensors)."""
 
     def __init__(self, sampling_rate: int, n_mels=(5, 10, 20, 40, 80, 160, 320), window_lengths=(32, 64, 128, 256, 512, 1024, 2048),
                  loss_fn=None, clamp_eps: float = 1e-5, mag_weight: float = 0.0, log_weight: float = 1.0, pow: float = 1.0,
@@ -215,9 +292,6 @@ class MultiScaleMelSpectrogramLoss(torch.nn.Module):
         return out.view(B, C, out.shape[1], out.shape[2])
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
-            raise NotImplementedError("afa_b200.mel.MultiScaleMelSpectrogramLoss has no backward yet: call it under torch.no_grad() "
-                                      "(validation), or keep the reference loss for the training step")
         losses = []
         for s in range(len(self.window_lengths)):
             lx, ly = self.log_mels(x, s), self.log_mels(y, s)

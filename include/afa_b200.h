@@ -173,7 +173,7 @@ int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
                             int dtype, int flags, void *stream);
 
 /*
- * Fused log-mel spectrogram (forward): one launch for
+ * Fused log-mel spectrogram: one launch for
  *   reflect/zero pad -> STFT (n_fft-point, hop, window) -> sqrt(re^2 + im^2 + mag_eps) -> mel_basis @ magnitudes
  *   -> log(max(., clamp_eps)) * log_scale
  *   <->  mel_spectrogram                                      BigVGAN/meldataset.py:51-123
@@ -201,6 +201,26 @@ int afa_logmel_fwd(const float *wav, float *out, int64_t rows, int64_t T, int64_
                    int n_mels, const int32_t *band_start, const int32_t *band_len, const int32_t *band_off,
                    const float *band_w,
                    float mag_eps, float clamp_eps, float log_scale, int flags, void *stream);
+
+/*
+ * Its adjoint: d loss / d wav from gout = d loss / d out ([rows][n_mels][n_frames], float32), i.e. what autograd
+ * computes through the same op chain when BigVGAN/train_binaural_mel.py:787 calls loss_gen_all.backward() with
+ * loss_mel = fn_mel_loss_multiscale(y, y_g_hat) (:759) or the single-scale L1 on mel_spectrogram(y_g_hat) (:711-720, :762).
+ * Only the waveform is needed from the forward (the spectrum is recomputed).  gwav ([rows][gwav_pitch], T valid
+ * samples per row) is overwritten, not accumulated into.  The clamp passes the gradient where mel >= clamp_eps and
+ * the magnitude has gradient 0 at 0 (torch.clamp / torch.abs).  bin_mlo / bin_mhi (int32 device [n_fft / 2 + 1]):
+ * the filters whose support contains bin k all lie in [bin_mlo[k], bin_mhi[k]).
+ * workspace: device scratch of afa_logmel_bwd_workspace_bytes() bytes (8-byte aligned) holding the windowed frame
+ * gradients between the two kernels; the overlap-add is a fixed-order gather, so gwav is bitwise reproducible.
+ */
+size_t afa_logmel_bwd_workspace_bytes(int64_t rows, int64_t T, int n_fft, int hop, int pad);
+int afa_logmel_bwd(const float *wav, const float *gout, float *gwav, int64_t rows, int64_t T, int64_t row_pitch,
+                   int64_t gwav_pitch, int n_fft, int hop, int pad, int pad_mode,
+                   const float *window, const float *twiddle,
+                   int n_mels, const int32_t *band_start, const int32_t *band_len, const int32_t *band_off,
+                   const float *band_w, const int32_t *bin_mlo, const int32_t *bin_mhi,
+                   float mag_eps, float clamp_eps, float log_scale, int flags,
+                   void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).

@@ -124,6 +124,64 @@ def msmsl_mels(wav: np.ndarray, sampling_rate: int, n_mels: int, window_length: 
     return mel.reshape(B, C, n_mels, -1)
 
 
+def logmel_backward(y: np.ndarray, gout: np.ndarray, mel_basis: np.ndarray, n_fft: int, hop: int, pad: int, pad_mode: str,
+                    mag_eps: float, clamp_eps: float, log_scale: float, raw: bool = False) -> np.ndarray:
+    """d <out, gout> / d y for out = log(max(basis @ sqrt(|STFT(y)|^2 + mag_eps), clamp_eps)) * log_scale (or the raw mels):
+    the derivative autograd takes through meldataset.py:95-118 / loss.py:131-167, 195-197, stated op by op in reverse.
+    torch.clamp passes the gradient where its input >= min; torch.abs has gradient 0 at 0.  y [rows, T], gout
+    [rows, n_mels, n_frames] -> [rows, T] float64."""
+    y = np.asarray(y, dtype=np.float64)
+    rows, T = y.shape
+    window = hann_periodic(n_fft)
+    yp = pad_rows(y, pad, pad_mode)
+    Tp = yp.shape[1]
+    n_frames = 1 + (Tp - n_fft) // hop
+    idx = np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]
+    spec = np.fft.rfft(yp[:, idx] * window[None, None, :], axis=-1)                  # [rows, frames, bins]
+    mag = np.sqrt(spec.real ** 2 + spec.imag ** 2 + mag_eps)
+    basis = mel_basis.astype(np.float64)
+    g = np.transpose(np.asarray(gout, dtype=np.float64), (0, 2, 1))                  # [rows, frames, mels]
+    if not raw:
+        mel = mag @ basis.T
+        g = np.where(mel >= clamp_eps, g * log_scale / np.maximum(mel, 1e-300), 0.0)
+    gmag = g @ basis                                                                 # [rows, frames, bins]
+    scale = np.where(mag > 0, gmag / np.where(mag > 0, mag, 1.0), 0.0)
+    G = scale * spec                                                                 # d / d re + i d / d im
+    # adjoint of rfft: g[n] = Re sum_{k=0..N/2} G_k e^{+2 pi i k n / N} = N * irfft(H), H_0 = Re G_0, H_{N/2} = Re G_{N/2}, else G_k / 2
+    H = G * 0.5
+    H[..., 0] = G[..., 0].real
+    H[..., -1] = G[..., -1].real
+    gframes = np.fft.irfft(H, n=n_fft, axis=-1) * n_fft * window[None, None, :]
+    gp = np.zeros((rows, Tp))
+    for r in range(rows):
+        np.add.at(gp[r], idx, gframes[r])
+    if pad == 0:
+        return gp
+    gy = gp[:, pad:pad + T].copy()
+    if pad_mode == "reflect":                                                        # padded[pad - j] = y[j], padded[pad + T - 1 + j] = y[T - 1 - j]
+        j = np.arange(1, pad + 1)
+        gy[:, j] += gp[:, pad - j]
+        gy[:, T - 1 - j] += gp[:, pad + T - 1 + j]
+    return gy
+
+
+def msmsl_loss_backward(x: np.ndarray, y: np.ndarray, sampling_rate: int, n_mels=None, window_lengths=None,
+                        clamp_eps: float = 1e-5, log_weight: float = 1.0, mag_weight: float = 0.0) -> np.ndarray:
+    """d msmsl_loss / d x ([B, C, T]): L1 mean's subgradient sign(lx - ly) / numel through every scale."""
+    n_mels = MSMSL_N_MELS if n_mels is None else n_mels
+    window_lengths = MSMSL_WINDOWS if window_lengths is None else window_lengths
+    B, C, T = x.shape
+    gx = np.zeros((B * C, T))
+    for nm, w in zip(n_mels, window_lengths):
+        basis = slaney_mel_filterbank(sampling_rate, w, nm, 0.0, None)
+        lx = np.log(np.maximum(msmsl_mels(x, sampling_rate, nm, w), clamp_eps)) / math.log(10.0)
+        ly = np.log(np.maximum(msmsl_mels(y, sampling_rate, nm, w), clamp_eps)) / math.log(10.0)
+        gout = (log_weight + mag_weight) * np.sign(lx - ly) / lx.size
+        gx += logmel_backward(x.reshape(B * C, T), gout.reshape(B * C, nm, -1), basis, w, w // 4, w // 2, "reflect", 0.0,
+                              clamp_eps, 1.0 / math.log(10.0))
+    return gx.reshape(B, C, T)
+
+
 MSMSL_N_MELS = (5, 10, 20, 40, 80, 160, 320)          # loss.py:56
 MSMSL_WINDOWS = (32, 64, 128, 256, 512, 1024, 2048)   # loss.py:57
 

@@ -86,6 +86,19 @@ def main():
     for nm, w in zip(msl.n_mels, [s.window_length for s in msl.stft_params]):
         out[f"msl_mels_{w}"] = msl.mel_spectrogram(xh, nm, 0, None, w, w // 4, False, "hann").numpy()
         out[f"basis_{nm}_{w}"] = librosa_mel_standin(sr, w, nm, 0, None)
+    # backward (autograd through the reference's own op chains, float32): d/dy of <mel_spectrogram(y), G> for the reflect and
+    # the zero-pad branch, and d/dx of the seven-scale loss (what loss_mel.backward() propagates, train_binaural_mel.py:759-787)
+    G = torch.randn(3, num_mels, 32)
+    yg = y.clone().requires_grad_(True)
+    (meldataset.mel_spectrogram(yg, n_fft, num_mels, sr, hop, win, fmin, fmax) * G).sum().backward()
+    out["bwd_G"] = G.numpy()
+    out["bwd_gy_2d"] = yg.grad.numpy()
+    y1 = y[0].clone().requires_grad_(True)
+    (meldataset.mel_spectrogram(y1, n_fft, num_mels, sr, hop, win, fmin, fmax) * G[0]).sum().backward()
+    out["bwd_gy_1d"] = y1.grad.numpy()
+    xg = xh.clone().requires_grad_(True)
+    msl(xg, x).backward()
+    out["msl_gx"] = xg.grad.numpy()
     path = os.path.join(HERE, "mel_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: getattr(v, "shape", None) for k, v in out.items()})

@@ -102,3 +102,48 @@ def test_num_frames_and_argument_errors_without_gpu():
         P.logmel(torch.zeros(2, 4096), plan, 16, 32)
     with pytest.raises(NotImplementedError):
         P.MultiScaleMelSpectrogramLoss(SR, match_stride=True)
+
+
+def test_backward_oracle_matches_reference_autograd(mel_golden):
+    """The reverse-mode restatement against gradients autograd took through the reference's own functions."""
+    g = mel_golden
+    b = M.slaney_mel_filterbank(SR, 1024, 80)
+    gy = M.logmel_backward(g["y"], g["bwd_G"], b, 1024, 256, 384, "reflect", 1e-9, 1e-5, 1.0)
+    assert np.abs(gy - g["bwd_gy_2d"]).max() <= 1e-5 * np.abs(g["bwd_gy_2d"]).max()
+    gy1 = M.logmel_backward(g["y"][:1], g["bwd_G"][:1], b, 1024, 256, 384, "constant", 1e-9, 1e-5, 1.0)
+    assert np.abs(gy1[0] - g["bwd_gy_1d"]).max() <= 1e-5 * np.abs(g["bwd_gy_1d"]).max()
+    # the L1 of the loss is not smooth: where |log mel(x) - log mel(y)| is at float32 rounding level the reference's
+    # sign() and the float64 one differ, each flip moving the gradient by 2 / numel of that scale -- hence the budget
+    gx = M.msmsl_loss_backward(g["msl_x"], g["msl_y"], SR)
+    assert np.abs(gx - g["msl_gx"]).max() <= 1e-2 * np.abs(g["msl_gx"]).max()
+
+
+def test_backward_oracle_is_the_derivative_of_the_forward_oracle():
+    """Directional finite difference in float64 (independent of any fixture)."""
+    rng = np.random.default_rng(0)
+    y = 0.3 * rng.standard_normal((2, 700))
+    G = rng.standard_normal((2, 10, M.stft_mag(y, 64, 16, M.hann_periodic(64), 32, "reflect", 0.0).shape[2]))
+    basis = M.slaney_mel_filterbank(SR, 64, 10)
+    d = rng.standard_normal(y.shape)
+
+    def f(v):
+        mel = np.einsum("mk,rkf->rmf", basis.astype(np.float64), M.stft_mag(v, 64, 16, M.hann_periodic(64), 32, "reflect", 1e-9))
+        return float((np.log(np.maximum(mel, 1e-5)) * G).sum())
+
+    gy = M.logmel_backward(y, G, basis, 64, 16, 32, "reflect", 1e-9, 1e-5, 1.0)
+    h = 1e-6
+    fd = (f(y + h * d) - f(y - h * d)) / (2 * h)
+    assert fd == pytest.approx(float((gy * d).sum()), rel=1e-6)
+
+
+def test_bin_cover_bounds_every_filter(mel_golden):
+    from afa_b200.mel import banded, bin_cover
+
+    for k, n_mels, n_fft, fmax in _basis_keys(mel_golden):
+        basis = mel_golden[k]
+        starts, lens, _, _ = banded(basis)
+        lo, hi = bin_cover(starts, lens, basis.shape[1])
+        for b in range(basis.shape[1]):
+            ms = np.flatnonzero(basis[:, b])
+            if ms.size:
+                assert lo[b] <= ms[0] and ms[-1] < hi[b], (k, b)
