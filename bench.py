@@ -732,13 +732,49 @@ def run_train_mode(args):
                                 capturable=bool(args.graph_step))
         return gen, model, opt
 
-    def time_steps(model, gen, opt, steps, warmup):
+    def make_loss(fused: bool):
+        """`--mel-loss`: the reference's generator-side mel term, loss_mel = MultiScaleMelSpectrogramLoss(y, y_g_hat) * 60
+        (train_binaural_mel.py:759, lambda_melloss = 60) plus the single-scale mel of the estimate it computes every step
+        (:711-720), on a synthetic target -- through the fused kernels (fused=True) or the reference's torch-op chain."""
+        if not args.mel_loss:
+            return lambda y: y.abs().mean()
+        from afa_b200 import mel as P
+
+        torch.manual_seed(4321)
+        target = (0.3 * torch.randn(B, 1, t_mel * 256, device=dev)).clamp(-1, 1)
+        if fused:
+            msl = P.MultiScaleMelSpectrogramLoss(22050)
+
+            def loss_of(y):
+                P.mel_spectrogram(y.detach().squeeze(1), 1024, 80, 22050, 256, 1024, 0, None, check_range=False)
+                return msl(target, y) * 60.0
+            return loss_of
+        wins, nms = (32, 64, 128, 256, 512, 1024, 2048), (5, 10, 20, 40, 80, 160, 320)
+        bases = [torch.from_numpy(P.slaney_mel_filterbank(22050, w, nm)).to(dev) for w, nm in zip(wins, nms)]
+        basis1 = torch.from_numpy(P.slaney_mel_filterbank(22050, 1024, 80)).to(dev)
+        hann = {w: torch.hann_window(w, device=dev) for w in wins}
+        log10 = torch.log(torch.tensor(10.0))
+
+        def logmels(wav, basis, n):       # loss.py:110-167 + :195-197
+            stft = torch.stft(wav.reshape(-1, wav.shape[-1]), n_fft=n, hop_length=n // 4, window=hann[n], return_complex=True, center=True)
+            mels = (torch.abs(stft).transpose(1, 2) @ basis.T).transpose(1, 2)
+            return torch.log(mels.clamp(min=1e-5)) / log10
+
+        def loss_of(y):
+            yp = torch.nn.functional.pad(y.detach(), (384, 384), mode="reflect").squeeze(1)       # meldataset.py:95-118
+            spec = torch.stft(yp, 1024, hop_length=256, win_length=1024, window=hann[1024], center=False, return_complex=True)
+            torch.log(torch.clamp(basis1 @ torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1) + 1e-9), min=1e-5))
+            return sum(torch.nn.functional.l1_loss(logmels(target, b, w), logmels(y, b, w)) for b, w in zip(bases, wins)) * 60.0
+        return loss_of
+
+    def time_steps(model, gen, opt, steps, warmup, fused=True):
         mel = torch.rand(B, 80, t_mel, device=dev) * 14.5 - 12.0
+        loss_of = make_loss(fused)
 
         def one():
             opt.zero_grad(set_to_none=True)
             y = model(mel)
-            loss = y.abs().mean()
+            loss = loss_of(y)
             loss.backward()
             torch.nn.utils.clip_grad_norm_(gen.parameters(), 500.0)     # config clip_grad_norm, train_binaural_mel.py:788-790
             opt.step()
@@ -758,7 +794,7 @@ def run_train_mode(args):
             opt.zero_grad(set_to_none=False)
             with torch.cuda.graph(graph):
                 y = model(mel)
-                static_loss = y.abs().mean()
+                static_loss = loss_of(y)
                 static_loss.backward()
                 torch.nn.utils.clip_grad_norm_(gen.parameters(), 500.0)
                 opt.step()
@@ -824,7 +860,7 @@ def run_train_mode(args):
                                              self.downsample.lowpass.filter)
 
         gen_t, model_t, opt_t = build(TorchOpActivation1d)
-        ms_t, loss_t, _ = time_steps(model_t, gen_t, opt_t, max(1, args.steps), 3)
+        ms_t, loss_t, _ = time_steps(model_t, gen_t, opt_t, max(1, args.steps), 3, fused=False)
         base = {"ms_per_step": round(ms_t, 3), "loss": loss_t, "what": "same step, reference torch-op Activation1d on the same GPU"}
     if rank == 0:
         samples = world * B * t_mel * 256
@@ -834,7 +870,9 @@ def run_train_mode(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (f"BASELINE config 5: BigVGAN generator (bigvgan_binaural_22khz_80band_256x, random init) forward + "
                                     f"backward + clip_grad_norm + AdamW, batch {B} per GPU, segment {t_mel * 256} samples (T_mel={t_mel}), "
-                                    f"synthetic scalar loss; fused Activation1d forward and backward ([B, C, T] kernels)"),
+                                    + ("multi-scale mel loss x 60 + single-scale mel of the estimate (fused log-mel kernels, forward + adjoint)"
+                                       if args.mel_loss else "synthetic scalar loss")
+                                    + "; fused Activation1d forward and backward ([B, C, T] kernels)"),
                        "parallelism": f"DDP dp{world}" if world > 1 else "single GPU",
                        "cuda_graph_step": bool(args.graph_step and world == 1)},
             "audio_sec_per_sec_trained": round(samples / 22050.0 / (ms * 1e-3), 1),
@@ -948,6 +986,7 @@ def main():
                     help="vocoder: BASELINE config 4 (--total-clips clips sharded over the ranks, strong scaling); "
                          "train: BASELINE config 5 (generator forward + backward step, --batch per GPU, segment 8192)")
     ap.add_argument("--batch", type=int, default=32, help="--mode train: items per GPU (config batch_size)")
+    ap.add_argument("--mel-loss", action="store_true", help="--mode train: the reference's multi-scale mel loss x 60 instead of the synthetic scalar loss")
     ap.add_argument("--graph-step", action="store_true", help="--mode train, one GPU: capture the whole step in a CUDA graph")
     ap.add_argument("--total-clips", type=int, default=64)
     ap.add_argument("--cpu-repeats", type=int, default=3)

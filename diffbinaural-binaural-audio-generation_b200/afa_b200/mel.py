@@ -49,6 +49,14 @@ def slaney_mel_filterbank(sr: float, n_fft: int, n_mels: int, fmin: float = 0.0,
     return (tri * (2.0 / (edges[2:] - edges[:-2]))[:, None]).astype(np.float32)
 
 
+def _fp(t):
+    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+
+
+def _ip(t):
+    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_int32))
+
+
 class MelPlan:
     """Device-resident constants of one (n_fft, window, mel basis) configuration: window, FFT twiddles and the banded
     form of the basis.  Built once per configuration and device, like the reference's mel_basis_cache /
@@ -81,6 +89,11 @@ class MelPlan:
         mlo, mhi = bin_cover(starts, lens, n_fft // 2 + 1)
         self.bin_mlo = torch.from_numpy(mlo).to(self.device)
         self.bin_mhi = torch.from_numpy(mhi).to(self.device)
+        # the constant tail of every launch's argument list, cast once (a launch is a few microseconds of GPU time:
+        # per-call ctypes casts would cost more than the kernel)
+        self._c_basis = (_fp(self.window), _fp(self.twiddle), self.n_mels, _ip(self.band_start), _ip(self.band_len),
+                         _ip(self.band_off), _fp(self.band_w))
+        self._c_cover = (_ip(self.bin_mlo), _ip(self.bin_mhi))
 
 
 def banded(basis: np.ndarray):
@@ -123,15 +136,25 @@ def bin_cover(starts: np.ndarray, lens: np.ndarray, n_freq: int):
 
 
 def num_frames(T: int, n_fft: int, hop: int, pad: int) -> int:
-    return int(load_library().afa_logmel_num_frames(T, n_fft, hop, pad))
+    """Frames of a T-sample row: what afa_logmel_num_frames() returns (tests check the two agree)."""
+    if T <= 0 or n_fft <= 0 or hop <= 0 or pad < 0 or T + 2 * pad < n_fft:
+        return 0
+    return 1 + (T + 2 * pad - n_fft) // hop
 
 
-def _fp(t):
-    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+class _on_device:
+    """torch.cuda.device(), entered only when the tensor's device is not already current."""
 
+    def __init__(self, device):
+        self.ctx = None if device.index == torch.cuda.current_device() else torch.cuda.device(device)
 
-def _ip(t):
-    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_int32))
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def _check_wav(wav: torch.Tensor, plan: MelPlan, pad: int, pad_mode: int) -> torch.Tensor:
@@ -159,11 +182,10 @@ def logmel_forward_raw(wav: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad
         out = torch.empty(rows, plan.n_mels, nf, device=wav.device, dtype=torch.float32)
     elif tuple(out.shape) != (rows, plan.n_mels, nf) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("afa_b200.mel: `out` must be a contiguous float32 [rows, n_mels, n_frames] tensor")
-    with torch.cuda.device(wav.device):
+    with _on_device(wav.device):
         rc = load_library().afa_logmel_fwd(
             _fp(wav), _fp(out), rows, T, wav.stride(0) if rows > 1 else T, plan.n_fft, hop, pad, pad_mode,
-            _fp(plan.window), _fp(plan.twiddle), plan.n_mels, _ip(plan.band_start), _ip(plan.band_len), _ip(plan.band_off),
-            _fp(plan.band_w), mag_eps, clamp_eps, log_scale, AFA_MEL_FLAG_RAW if raw else 0,
+            *plan._c_basis, mag_eps, clamp_eps, log_scale, AFA_MEL_FLAG_RAW if raw else 0,
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     check(rc, "afa_logmel_fwd")
     return out
@@ -182,11 +204,10 @@ def logmel_backward_raw(wav: torch.Tensor, gout: torch.Tensor, plan: MelPlan, ho
     lib = load_library()
     nbytes = int(lib.afa_logmel_bwd_workspace_bytes(rows, T, plan.n_fft, hop, pad))
     ws = torch.empty(max(nbytes // 4, 2), device=wav.device, dtype=torch.float32)
-    with torch.cuda.device(wav.device):
+    with _on_device(wav.device):
         rc = lib.afa_logmel_bwd(
             _fp(wav), _fp(gout), _fp(gwav), rows, T, wav.stride(0) if rows > 1 else T, T, plan.n_fft, hop, pad, pad_mode,
-            _fp(plan.window), _fp(plan.twiddle), plan.n_mels, _ip(plan.band_start), _ip(plan.band_len), _ip(plan.band_off),
-            _fp(plan.band_w), _ip(plan.bin_mlo), _ip(plan.bin_mhi), mag_eps, clamp_eps, log_scale,
+            *plan._c_basis, *plan._c_cover, mag_eps, clamp_eps, log_scale,
             AFA_MEL_FLAG_RAW if raw else 0, ctypes.c_void_p(ws.data_ptr()), ws.numel() * 4,
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     check(rc, "afa_logmel_bwd")

@@ -95,6 +95,12 @@ def test_num_frames_and_argument_errors_without_gpu():
     assert P.num_frames(1500, 1024, 256, 384) == 5
     assert P.num_frames(4096, 2048, 512, 1024) == 9          # center=True
     assert P.num_frames(100, 1024, 256, 0) == 0
+    from afa_b200._lib import load_library
+
+    lib = load_library()
+    for T in (1, 40, 63, 64, 65, 1500, 8192, 220416):
+        for n, hop, pad in ((64, 16, 0), (64, 16, 32), (1024, 256, 384), (2048, 512, 1024)):
+            assert P.num_frames(T, n, hop, pad) == lib.afa_logmel_num_frames(T, n, hop, pad), (T, n, hop, pad)
     with pytest.raises(ValueError):
         P.MelPlan(1000, torch.hann_window(1000), np.zeros((80, 501), np.float32), "cpu")
     plan = P.MelPlan(64, torch.hann_window(64), M.slaney_mel_filterbank(SR, 64, 10), "cpu")
