@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "afa_logmel_fwd",
     "afa_logmel_bwd_workspace_bytes",
     "afa_logmel_bwd",
+    "afa_l1_partial_sums",
     "afa_set_tuning",
     "afa_kernel_info",
     "afa_kernel_info_shape",
@@ -89,7 +90,9 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_logmel_bwd_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
         lib.afa_logmel_bwd.restype = i32
         lib.afa_logmel_bwd.argtypes = [fp, fp, fp, i64, i64, i64, i64, i32, i32, i32, i32, fp, fp, i32, ip, ip, ip, fp, ip, ip,
-                                       f32, f32, f32, i32, vp, ctypes.c_size_t, vp]
+                                       f32, f32, f32, i32, fp, f32, fp, vp, ctypes.c_size_t, vp]
+        lib.afa_l1_partial_sums.restype = i32
+        lib.afa_l1_partial_sums.argtypes = [fp, fp, i64, fp, i32, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32

@@ -25,6 +25,9 @@ from ._lib import check, load_library  # noqa: F401  (check is re-exported for c
 AFA_MEL_PAD_REFLECT = 0
 AFA_MEL_PAD_ZERO = 1
 AFA_MEL_FLAG_RAW = 1
+AFA_MEL_FLAG_L1_SIGN = 2
+AFA_MEL_FLAG_ACCUMULATE = 4
+L1_PARTIALS = 256          # per-CTA partial sums of one L1 (finished by one torch reduction over all scales)
 
 
 def slaney_mel_filterbank(sr: float, n_fft: int, n_mels: int, fmin: float = 0.0, fmax=None) -> np.ndarray:
@@ -192,26 +195,60 @@ def logmel_forward_raw(wav: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad
 
 
 def logmel_backward_raw(wav: torch.Tensor, gout: torch.Tensor, plan: MelPlan, hop: int, pad: int, pad_mode: int, mag_eps: float,
-                        clamp_eps: float, log_scale: float, raw: bool) -> torch.Tensor:
-    """d loss / d wav ([rows, T]) from gout = d loss / d out: afa_logmel_bwd (two launches) on the current stream."""
+                        clamp_eps: float, log_scale: float, raw: bool, *, l1_other: torch.Tensor | None = None, l1_coef: float = 0.0,
+                        l1_scale: torch.Tensor | None = None, accumulate_into: torch.Tensor | None = None) -> torch.Tensor:
+    """d loss / d wav ([rows, T]) from gout = d loss / d out: afa_logmel_bwd (two launches) on the current stream.
+
+    With `l1_other`, `gout` / `l1_other` are the two log-mel tensors of an L1 loss and the output gradient is
+    sign(gout - l1_other) * l1_coef * l1_scale (a device scalar), formed inside the kernel (AFA_MEL_FLAG_L1_SIGN).
+    `accumulate_into`: add to this [rows, T] tensor instead of writing a new one (AFA_MEL_FLAG_ACCUMULATE)."""
     wav = _check_wav(wav, plan, pad, pad_mode)
     rows, T = wav.shape
     nf = num_frames(T, plan.n_fft, hop, pad)
     if tuple(gout.shape) != (rows, plan.n_mels, nf):
         raise ValueError(f"afa_b200.mel: gradient of shape {tuple(gout.shape)}, expected {(rows, plan.n_mels, nf)}")
     gout = gout.to(torch.float32).contiguous()
-    gwav = torch.empty(rows, T, device=wav.device, dtype=torch.float32)
+    flags = AFA_MEL_FLAG_RAW if raw else 0
+    other_p, scale_p = None, None
+    if l1_other is not None:
+        if l1_other.shape != gout.shape or l1_other.dtype != torch.float32 or not l1_other.is_contiguous():
+            raise ValueError("afa_b200.mel: l1_other must match gout (contiguous float32)")
+        flags |= AFA_MEL_FLAG_L1_SIGN
+        other_p = _fp(l1_other)
+        if l1_scale is not None:
+            l1_scale = l1_scale.to(device=wav.device, dtype=torch.float32).reshape(1).contiguous()
+            scale_p = _fp(l1_scale)
+    if accumulate_into is None:
+        gwav = torch.empty(rows, T, device=wav.device, dtype=torch.float32)
+    else:
+        gwav = accumulate_into
+        if tuple(gwav.shape) != (rows, T) or gwav.dtype != torch.float32 or not gwav.is_contiguous():
+            raise ValueError("afa_b200.mel: accumulate_into must be a contiguous float32 [rows, T] tensor")
+        flags |= AFA_MEL_FLAG_ACCUMULATE
     lib = load_library()
-    nbytes = int(lib.afa_logmel_bwd_workspace_bytes(rows, T, plan.n_fft, hop, pad))
+    nbytes = rows * nf * plan.n_fft * 4                     # == afa_logmel_bwd_workspace_bytes(rows, T, n_fft, hop, pad)
     ws = torch.empty(max(nbytes // 4, 2), device=wav.device, dtype=torch.float32)
     with _on_device(wav.device):
         rc = lib.afa_logmel_bwd(
             _fp(wav), _fp(gout), _fp(gwav), rows, T, wav.stride(0) if rows > 1 else T, T, plan.n_fft, hop, pad, pad_mode,
-            *plan._c_basis, *plan._c_cover, mag_eps, clamp_eps, log_scale,
-            AFA_MEL_FLAG_RAW if raw else 0, ctypes.c_void_p(ws.data_ptr()), ws.numel() * 4,
+            *plan._c_basis, *plan._c_cover, mag_eps, clamp_eps, log_scale, flags, other_p, l1_coef, scale_p,
+            ctypes.c_void_p(ws.data_ptr()), ws.numel() * 4,
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     check(rc, "afa_logmel_bwd")
     return gwav
+
+
+def l1_partial_sums(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[:] = per-CTA partial sums of |a - b| (afa_l1_partial_sums; `out` is a contiguous float32 CUDA vector)."""
+    if a.shape != b.shape or a.dtype != torch.float32 or b.dtype != torch.float32 or not (a.is_contiguous() and b.is_contiguous()):
+        raise ValueError("afa_b200.mel.l1_partial_sums: two contiguous float32 tensors of one shape expected")
+    if not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.dim() != 1:
+        raise ValueError("afa_b200.mel.l1_partial_sums: `out` must be a contiguous float32 CUDA vector")
+    with _on_device(a.device):
+        rc = load_library().afa_l1_partial_sums(_fp(a), _fp(b), a.numel(), _fp(out), out.numel(),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    check(rc, "afa_l1_partial_sums")
+    return out
 
 
 class _LogMelFn(torch.autograd.Function):
@@ -276,6 +313,51 @@ def mel_spectrogram(y: torch.Tensor, n_fft: int, num_mels: int, sampling_rate: i
     return logmel(y, plan, hop_size, pad, AFA_MEL_PAD_REFLECT)
 
 
+class _MultiScaleL1Fn(torch.autograd.Function):
+    """sum over scales of weight * mean |log10 mel(x) - log10 mel(y)| with the L1 inside the kernels: per scale two
+    afa_logmel_fwd launches and one afa_l1_partial_sums forward, one afa_logmel_bwd (sign formed in-kernel, waveform
+    gradients of the scales accumulated in place) per differentiated input backward."""
+
+    @staticmethod
+    def forward(ctx, x, y, module):
+        B, C, T = x.shape
+        x2, y2 = x.reshape(B * C, T), y.reshape(B * C, T)
+        n_scales = len(module.window_lengths)
+        partials = torch.empty(n_scales, L1_PARTIALS, device=x.device, dtype=torch.float32)
+        coefs, saved = [], []
+        for s in range(n_scales):
+            w = module.window_lengths[s]
+            cfg = (module._plan(s, x.device), w // 4, w // 2, AFA_MEL_PAD_REFLECT, 0.0, module.clamp_eps, 1.0 / math.log(10.0), False)
+            lx, ly = logmel_forward_raw(x2, *cfg), logmel_forward_raw(y2, *cfg)
+            l1_partial_sums(lx, ly, partials[s])
+            coefs.append((module.log_weight + module.mag_weight) / max(lx.numel(), 1))   # both terms compare the log mels (loss.py:206-207)
+            saved += [lx, ly]
+        ctx.module, ctx.coefs, ctx.shape = module, coefs, (B, C, T)
+        ctx.save_for_backward(x2, y2, *saved)
+        key = (str(x.device), B * C, T)
+        if key not in module._coefs:                            # built once per shape: no host-to-device copy in the step (graph capture)
+            module._coefs[key] = torch.tensor(coefs, device=x.device, dtype=torch.float32)
+        return (partials.sum(dim=1) * module._coefs[key]).sum()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        x2, y2, *saved = ctx.saved_tensors
+        module, (B, C, T) = ctx.module, ctx.shape
+        grads = []
+        for which, wav in ((0, x2), (1, y2)):
+            if not ctx.needs_input_grad[which]:
+                grads.append(None)
+                continue
+            g = None
+            for s, w in enumerate(module.window_lengths):
+                lx, ly = saved[2 * s], saved[2 * s + 1]
+                a, b = (lx, ly) if which == 0 else (ly, lx)
+                cfg = (module._plan(s, wav.device), w // 4, w // 2, AFA_MEL_PAD_REFLECT, 0.0, module.clamp_eps, 1.0 / math.log(10.0), False)
+                g = logmel_backward_raw(wav, a, *cfg, l1_other=b, l1_coef=ctx.coefs[s], l1_scale=gloss, accumulate_into=g)
+            grads.append(g.view(B, C, T))
+        return grads[0], grads[1], None
+
+
 class MultiScaleMelSpectrogramLoss(torch.nn.Module):
     """BigVGAN/loss.py:23-211 with the fused kernels: seven (window, n_mels) scales, log10 of the clamped mels, L1.
     Differentiable with respect to both waveforms (the L1 and the sum stay torch ops on the small log-mel tensors)."""
@@ -295,6 +377,7 @@ class MultiScaleMelSpectrogramLoss(torch.nn.Module):
         self.clamp_eps, self.mag_weight, self.log_weight, self.weight = clamp_eps, mag_weight, log_weight, weight
         self.mel_fmin, self.mel_fmax = list(mel_fmin), list(mel_fmax)
         self._plans: dict = {}
+        self._coefs: dict = {}
 
     def _plan(self, scale: int, device) -> MelPlan:
         key = (scale, str(device))
@@ -313,6 +396,9 @@ class MultiScaleMelSpectrogramLoss(torch.nn.Module):
         return out.view(B, C, out.shape[1], out.shape[2])
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if type(self.loss_fn) is torch.nn.L1Loss and self.loss_fn.reduction == "mean" and x.shape == y.shape and x.dim() == 3 \
+                and x.dtype == y.dtype == torch.float32:
+            return _MultiScaleL1Fn.apply(x, y, self)          # the default loss_fn: L1 fused into the kernels
         losses = []
         for s in range(len(self.window_lengths)):
             lx, ly = self.log_mels(x, s), self.log_mels(y, s)

@@ -57,6 +57,10 @@ struct MelArgs {
     float* frames;             // workspace [rows][n_frames][N]: windowed frame gradients
     const int32_t* bin_mlo;    // [N/2 + 1] the filters covering bin k lie in [bin_mlo[k], bin_mhi[k])
     const int32_t* bin_mhi;
+    const float* gother;       // AFA_MEL_FLAG_L1_SIGN: gout / gother are the two log-mel tensors of an L1 loss and the
+    const float* gscale_dev;   //   output gradient is sign(gout - gother) * gcoef * (*gscale_dev)  (null pointer: 1)
+    float gcoef;
+    int l1_sign;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -250,11 +254,22 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
     for (int64_t row = blockIdx.y; row < p.rows; row += gridDim.y) {
         const float* x = p.wav + row * p.row_pitch;
         const float* g = p.gout + row * (int64_t)p.n_mels * p.n_frames;
+        const float* g2 = p.l1_sign ? p.gother + row * (int64_t)p.n_mels * p.n_frames : nullptr;
+        const float l1c = p.l1_sign ? p.gcoef * (p.gscale_dev ? __ldg(p.gscale_dev) : 1.f) : 0.f;
         __syncthreads();                                     // tw / win staged; gtile free again
         for (int i = tid; i < (p.n_mels << fshift); i += NT) {
             const int m = i >> fshift;
             const int fi = i & (fpc - 1);
-            gtile[i] = fi < nf ? __ldg(g + (int64_t)m * p.n_frames + f0 + fi) : 0.f;
+            float v = 0.f;
+            if (fi < nf) {
+                const int64_t at = (int64_t)m * p.n_frames + f0 + fi;
+                v = __ldg(g + at);
+                if (p.l1_sign) {                             // d |a - b| / d a = sign(a - b), 0 at 0 (torch.sign)
+                    const float d = v - __ldg(g2 + at);
+                    v = d > 0.f ? l1c : (d < 0.f ? -l1c : 0.f);
+                }
+            }
+            gtile[i] = v;
         }
         for (int fi = 0; fi < nf; ++fi) {
             const int64_t s0 = (f0 + fi) * (int64_t)p.hop - p.pad;
@@ -331,6 +346,7 @@ struct OlaArgs {
     float* gwav;
     int64_t rows, T, gwav_pitch, n_frames;
     int n_fft, hop, pad, pad_mode;
+    int accumulate;            // AFA_MEL_FLAG_ACCUMULATE: gwav += instead of gwav =
 };
 
 __device__ __forceinline__ float ola_position(const OlaArgs& p, const float* fr, int64_t pos) {
@@ -354,7 +370,29 @@ __global__ void __launch_bounds__(256) afa_logmel_bwd_ola_kernel(const OlaArgs p
             const int64_t r = p.T - 1 - t;
             if (r >= 1 && r <= p.pad) s += ola_position(p, fr, p.pad + 2 * (p.T - 1) - t);
         }
-        p.gwav[row * p.gwav_pitch + t] = s;
+        float* o = p.gwav + row * p.gwav_pitch + t;
+        *o = p.accumulate ? *o + s : s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sum |a - b| as n_partial per-CTA partial sums in a fixed order (the caller finishes the few hundred values):
+// the L1 of two log-mel tensors without materialising a - b, |.| and the reduction tree as separate launches
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) afa_l1_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                              float* __restrict__ partial) {
+    __shared__ float warp_sums[8];
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += fabsf(__ldg(a + i) - __ldg(b + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += warp_sums[w];
+        partial[blockIdx.x] = t;
     }
 }
 
@@ -386,6 +424,17 @@ int launch_bwd(MelArgs a, const OlaArgs& o, int64_t rows, cudaStream_t stream) {
 }
 
 }  // namespace afa_mel
+
+extern "C" int afa_l1_partial_sums(const float* a, const float* b, int64_t n, float* partial, int n_partial, void* stream) {
+    if (n < 0 || n_partial <= 0 || n_partial > 65535)
+        return afa_internal::set_error(AFA_ERR_BAD_ARG, "afa_l1_partial_sums: bad sizes (n %lld, n_partial %d)", (long long)n, n_partial);
+    if (!partial || (n > 0 && (!a || !b))) return afa_internal::set_error(AFA_ERR_BAD_ARG, "afa_l1_partial_sums: null pointer");
+    afa_mel::afa_l1_partial_kernel<<<n_partial, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, n, partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return afa_internal::cuda_error(e, "afa_l1_partial_kernel launch");
+    afa_internal::count_launch();
+    return 0;
+}
 
 extern "C" int64_t afa_logmel_num_frames(int64_t T, int n_fft, int hop, int pad) {
     if (T <= 0 || n_fft <= 0 || hop <= 0 || pad < 0) return 0;
@@ -420,6 +469,7 @@ extern "C" int afa_logmel_fwd(const float* wav, float* out, int64_t rows, int64_
     a.mag_eps = mag_eps; a.clamp_eps = clamp_eps; a.log_scale = log_scale; a.raw = (flags & AFA_MEL_FLAG_RAW) ? 1 : 0;
     a.rows = rows;
     a.gout = nullptr; a.frames = nullptr; a.bin_mlo = nullptr; a.bin_mhi = nullptr;
+    a.gother = nullptr; a.gscale_dev = nullptr; a.gcoef = 0.f; a.l1_sign = 0;
     if (rows == 0 || a.n_frames == 0) return 0;     // nothing to do: empty batches / rows shorter than one frame are legal
     if (!wav || !out || !window || !twiddle || !band_start || !band_len || !band_off || !band_w)
         return afa_internal::set_error(AFA_ERR_BAD_ARG, "afa_logmel_fwd: null pointer");
@@ -446,6 +496,7 @@ extern "C" int afa_logmel_bwd(const float* wav, const float* gout, float* gwav, 
                               int n_mels, const int32_t* band_start, const int32_t* band_len, const int32_t* band_off,
                               const float* band_w, const int32_t* bin_mlo, const int32_t* bin_mhi,
                               float mag_eps, float clamp_eps, float log_scale, int flags,
+                              const float* gother, float gcoef, const float* gscale_dev,
                               void* workspace, size_t workspace_bytes, void* stream) {
     using namespace afa_mel;
     if (rows < 0 || T <= 0 || row_pitch < T || gwav_pitch < T || hop <= 0 || pad < 0 || n_mels <= 0 || n_mels > 1024)
@@ -469,19 +520,24 @@ extern "C" int afa_logmel_bwd(const float* wav, const float* gout, float* gwav, 
     a.n_mels = n_mels; a.hop = hop; a.pad = pad; a.pad_mode = pad_mode;
     a.mag_eps = mag_eps; a.clamp_eps = clamp_eps; a.log_scale = log_scale; a.raw = (flags & AFA_MEL_FLAG_RAW) ? 1 : 0;
     a.gout = gout; a.frames = reinterpret_cast<float*>(workspace); a.bin_mlo = bin_mlo; a.bin_mhi = bin_mhi;
+    a.l1_sign = (flags & AFA_MEL_FLAG_L1_SIGN) ? 1 : 0;
+    a.gother = gother; a.gcoef = gcoef; a.gscale_dev = gscale_dev;
+    const int accumulate = (flags & AFA_MEL_FLAG_ACCUMULATE) ? 1 : 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (a.n_frames == 0) {                          // no frame read the waveform: the gradient is zero
+        if (accumulate) return 0;
         cudaError_t e = cudaMemset2DAsync(gwav, (size_t)gwav_pitch * sizeof(float), 0, (size_t)T * sizeof(float), (size_t)rows, s);
         return e == cudaSuccess ? 0 : afa_internal::cuda_error(e, "cudaMemset2DAsync(gwav)");
     }
     if (!gout || !window || !twiddle || !band_start || !band_len || !band_off || !band_w || !bin_mlo || !bin_mhi || !workspace)
         return afa_internal::set_error(AFA_ERR_BAD_ARG, "afa_logmel_bwd: null pointer");
+    if (a.l1_sign && !gother) return afa_internal::set_error(AFA_ERR_BAD_ARG, "afa_logmel_bwd: AFA_MEL_FLAG_L1_SIGN needs the second log-mel tensor");
     const size_t need = afa_logmel_bwd_workspace_bytes(rows, T, n_fft, hop, pad);
     if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 7))
         return afa_internal::set_error(AFA_ERR_WORKSPACE, "afa_logmel_bwd: workspace of %zu bytes (8-byte aligned) needed, %zu given", need, workspace_bytes);
     OlaArgs o;
     o.frames = a.frames; o.gwav = gwav; o.rows = rows; o.T = T; o.gwav_pitch = gwav_pitch; o.n_frames = a.n_frames;
-    o.n_fft = n_fft; o.hop = hop; o.pad = pad; o.pad_mode = pad_mode;
+    o.n_fft = n_fft; o.hop = hop; o.pad = pad; o.pad_mode = pad_mode; o.accumulate = accumulate;
     switch (log2n) {
         case 5: return launch_bwd<5>(a, o, rows, s);
         case 6: return launch_bwd<6>(a, o, rows, s);

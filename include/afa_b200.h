@@ -194,6 +194,8 @@ int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
 #define AFA_MEL_PAD_REFLECT 0
 #define AFA_MEL_PAD_ZERO 1
 #define AFA_MEL_FLAG_RAW 1
+#define AFA_MEL_FLAG_L1_SIGN 2       /* afa_logmel_bwd: the output gradient is sign(gout - gother) * gcoef * (*gscale_dev) */
+#define AFA_MEL_FLAG_ACCUMULATE 4    /* afa_logmel_bwd: gwav += instead of gwav = (summing the scales of the loss) */
 int64_t afa_logmel_num_frames(int64_t T, int n_fft, int hop, int pad);
 int afa_logmel_fwd(const float *wav, float *out, int64_t rows, int64_t T, int64_t row_pitch,
                    int n_fft, int hop, int pad, int pad_mode,
@@ -210,6 +212,7 @@ int afa_logmel_fwd(const float *wav, float *out, int64_t rows, int64_t T, int64_
  * samples per row) is overwritten, not accumulated into.  The clamp passes the gradient where mel >= clamp_eps and
  * the magnitude has gradient 0 at 0 (torch.clamp / torch.abs).  bin_mlo / bin_mhi (int32 device [n_fft / 2 + 1]):
  * the filters whose support contains bin k all lie in [bin_mlo[k], bin_mhi[k]).
+ * gother / gcoef / gscale_dev: see AFA_MEL_FLAG_L1_SIGN below (NULL, 0, NULL otherwise).
  * workspace: device scratch of afa_logmel_bwd_workspace_bytes() bytes (8-byte aligned) holding the windowed frame
  * gradients between the two kernels; the overlap-add is a fixed-order gather, so gwav is bitwise reproducible.
  */
@@ -220,7 +223,18 @@ int afa_logmel_bwd(const float *wav, const float *gout, float *gwav, int64_t row
                    int n_mels, const int32_t *band_start, const int32_t *band_len, const int32_t *band_off,
                    const float *band_w, const int32_t *bin_mlo, const int32_t *bin_mhi,
                    float mag_eps, float clamp_eps, float log_scale, int flags,
+                   const float *gother, float gcoef, const float *gscale_dev,
                    void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * The L1 of the loss (loss.py:203-207: loss_fn = nn.L1Loss() on the two log-mel tensors) without its torch launches.
+ * Forward: afa_l1_partial_sums writes n_partial per-CTA sums of |a - b| (fixed order; the caller adds them and divides
+ * by n).  Backward: with AFA_MEL_FLAG_L1_SIGN, afa_logmel_bwd takes the two saved log-mel tensors as gout / gother and
+ * uses sign(gout - gother) * gcoef * (*gscale_dev) as the output gradient (gscale_dev: device scalar holding the
+ * upstream d / d loss, NULL = 1), so sign / scale never exist as tensors; AFA_MEL_FLAG_ACCUMULATE adds this scale's
+ * waveform gradient to gwav.
+ */
+int afa_l1_partial_sums(const float *a, const float *b, int64_t n, float *partial, int n_partial, void *stream);
 
 /*
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).

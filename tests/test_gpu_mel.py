@@ -147,6 +147,48 @@ def test_size_independent_properties_at_clip_length():
 TOL_GRAD = 1e-4
 
 
+def test_fused_l1_path_equals_generic_autograd_path(mel_golden):
+    """The default loss (nn.L1Loss) runs with the L1 inside the kernels (afa_l1_partial_sums forward, sign formed in
+    afa_logmel_bwd, scales accumulated in place); any other loss_fn takes the per-scale autograd path.  Same log mels,
+    same signs -> same loss and the same gradients for BOTH waveforms, up to summation order."""
+    P = _P()
+    g = mel_golden
+    fused = P.MultiScaleMelSpectrogramLoss(SR)
+    generic = P.MultiScaleMelSpectrogramLoss(SR, loss_fn=lambda a, b: (a - b).abs().mean())
+    res = []
+    for loss in (fused, generic):
+        x = _dev(g["msl_x"]).requires_grad_(True)
+        y = _dev(g["msl_y"]).requires_grad_(True)
+        v = loss(x, y)
+        (v * 60.0).backward()                                   # lambda_melloss: the upstream gradient is not 1
+        res.append((float(v), x.grad.clone(), y.grad.clone()))
+    assert res[0][0] == pytest.approx(res[1][0], rel=1e-5)
+    assert res[0][0] == pytest.approx(float(g["msl_loss"]), rel=1e-4)
+    for a, b in ((res[0][1], res[1][1]), (res[0][2], res[1][2])):
+        assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item()
+    assert np.abs(res[0][1].cpu().numpy() - g["msl_gx"] * 60.0).max() <= 1e-2 * np.abs(g["msl_gx"] * 60.0).max()
+    # only the estimate differentiated (the training step): the target's gradient is not computed
+    x = _dev(g["msl_x"]).requires_grad_(True)
+    fused(x, _dev(g["msl_y"])).backward()
+    assert torch.equal(x.grad * 60.0, res[0][1]) or (x.grad * 60.0 - res[0][1]).abs().max().item() <= 1e-6 * res[0][1].abs().max().item()
+
+
+def test_l1_partial_sums():
+    P = _P()
+    torch.manual_seed(2)
+    for n in (1, 255, 4097, 32 * 80 * 32, 1_000_003):
+        a, b = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+        out = torch.full((P.L1_PARTIALS,), float("nan"), device=DEV)
+        P.l1_partial_sums(a, b, out)
+        ref = (a.double() - b.double()).abs().sum().item()
+        assert out.double().sum().item() == pytest.approx(ref, rel=1e-5), n
+        again = torch.empty_like(out)
+        P.l1_partial_sums(a, b, again)
+        assert torch.equal(out, again)
+    with pytest.raises(ValueError):
+        P.l1_partial_sums(torch.zeros(4, device=DEV), torch.zeros(5, device=DEV), torch.zeros(8, device=DEV))
+
+
 def test_backward_matches_reference_autograd_vectors(mel_golden):
     """d <mel_spectrogram(y), G> / d y through afa_logmel_bwd vs autograd through the reference's own op chain."""
     P = _P()
