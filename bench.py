@@ -487,9 +487,15 @@ def run_mel_step(dev, batch: int = 32, segment: int = 8192, reps: int = 20):
     with torch.no_grad():
         err = float((ours_single() - torch_single()).abs().max())
     frames = sum(2 * batch * P.num_frames(segment, w, w // 4, w // 2) for w in msl.window_lengths)
+    # inference side (get_mel_spectrogram at BigVGAN/inference_binaural.py:131-132: mel of whole clips): 16 ten-second rows = 8 binaural clips
+    clips = (0.3 * torch.randn(16, 220416, device=dev)).clamp(-1, 1)
+    clip_us = timed(lambda: P.logmel(clips, plan1, 256, 384))
+    clip_torch_us = timed(lambda: chain_single(clips, basis1))
     out = {"shape": [batch, segment], "single_scale_us": round(timed(ours_single), 2), "single_scale_torch_ops_us": round(timed(torch_single), 2),
            "multi_scale_14_launches_us": round(timed(ours_multi), 2), "multi_scale_torch_ops_us": round(timed(torch_multi), 2),
            "multi_scale_frames": frames, "max_abs_diff_vs_torch_ops_log_mel": err,
+           "clips_16x220416_us": round(clip_us, 2), "clips_16x220416_torch_ops_us": round(clip_torch_us, 2),
+           "clips_algorithmic_gbps": round(16 * (220416 + 80 * 861) * 4 / (clip_us * 1e-6) / 1e9, 1),
            "multi_scale_loss_fwd_bwd_us": round(timed(ours_loss_step), 2), "multi_scale_loss_fwd_bwd_torch_ops_us": round(timed(torch_loss_step), 2),
            "what": "eager calls incl. host overhead, CUDA events, best of 3 x 20; loss step = forward + backward to d loss / d estimate: 14 afa_logmel_fwd + 7 afa_l1_partial_sums + 7 afa_logmel_bwd (2 kernels each); device time per step under ncu: 0.6 ms in ~50 launches vs 1.6 ms in 330 for the torch-op chain (profiles/r01_mel_loss_step_launches_*.txt)"}
     return out

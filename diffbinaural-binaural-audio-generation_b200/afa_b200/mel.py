@@ -1,6 +1,7 @@
 """Fused log-mel spectrogram on sm_100a behind the reference's own function signatures.
 
     mel_spectrogram(...)                 <->  BigVGAN/meldataset.py:51-123 (same arguments, same [B, n_mels, frames] result)
+    get_mel_spectrogram(wav, h)          <->  BigVGAN/meldataset.py:126-146
     MultiScaleMelSpectrogramLoss(...)    <->  BigVGAN/loss.py:23-211 (same constructor, same scalar loss)
 
 One `afa_logmel_fwd` launch (csrc/afa_mel.cu) replaces pad -> torch.stft -> pow/sum/sqrt -> matmul -> clamp -> log;
@@ -311,6 +312,12 @@ def mel_spectrogram(y: torch.Tensor, n_fft: int, num_mels: int, sampling_rate: i
     if y.dim() != 2:
         raise RuntimeError(f"mel_spectrogram expects a [B, T] or [T] waveform, got {tuple(y.shape)}")
     return logmel(y, plan, hop_size, pad, AFA_MEL_PAD_REFLECT)
+
+
+def get_mel_spectrogram(wav: torch.Tensor, h) -> torch.Tensor:
+    """Drop-in for BigVGAN/meldataset.py:126-146 (called per channel at BigVGAN/inference_binaural.py:131-132):
+    `h` carries n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax."""
+    return mel_spectrogram(wav, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax)
 
 
 class _MultiScaleL1Fn(torch.autograd.Function):

@@ -178,7 +178,7 @@ int afa_amp_act_conv_fwd_cl(const void *x, int64_t x_bstride,
  *   -> log(max(., clamp_eps)) * log_scale
  *   <->  mel_spectrogram                                      BigVGAN/meldataset.py:51-123
  *        (pad = (n_fft - hop) / 2, center=False, mag_eps = 1e-9, clamp_eps = 1e-5, log_scale = 1; called at
- *         BigVGAN/train_binaural_mel.py:386, 640, 711 and BigVGAN/inference.py)
+ *         BigVGAN/train_binaural_mel.py:386, 640, 711 and, via get_mel_spectrogram, BigVGAN/inference_binaural.py:131-132)
  *   <->  MultiScaleMelSpectrogramLoss.mel_spectrogram + log10  BigVGAN/loss.py:110-167, 195-200
  *        (center=True => pad = n_fft / 2, mag_eps = 0, clamp_eps = 1e-5, log_scale = 1 / ln 10)
  * wav:  float32 device array [rows][row_pitch], T valid samples per row.

@@ -51,6 +51,10 @@ def test_mel_spectrogram_matches_reference_vectors(mel_golden):
     one = P.mel_spectrogram(y[0], 1024, 80, SR, 256, 1024, 0, None)           # 1-D branch: zero padding, no batch dim
     assert one.shape == (80, 32)
     assert np.abs(one.cpu().numpy() - g["mel_1d"]).max() <= TOL_LOG
+    from types import SimpleNamespace
+
+    h = SimpleNamespace(n_fft=1024, num_mels=80, sampling_rate=SR, hop_size=256, win_size=1024, fmin=0, fmax=None)
+    assert torch.equal(P.get_mel_spectrogram(y, h), out)
     short = P.mel_spectrogram(y[:, :1500], 1024, 80, SR, 256, 1024, 0, None)  # pitched rows, T % hop != 0
     assert short.shape == (3, 80, 5)
     assert np.abs(short.cpu().numpy() - g["mel_short"]).max() <= TOL_LOG
