@@ -209,7 +209,7 @@ int afa_logmel_fwd(const float *wav, float *out, int64_t rows, int64_t T, int64_
  * computes through the same op chain when BigVGAN/train_binaural_mel.py:787 calls loss_gen_all.backward() with
  * loss_mel = fn_mel_loss_multiscale(y, y_g_hat) (:759) or the single-scale L1 on mel_spectrogram(y_g_hat) (:711-720, :762).
  * Only the waveform is needed from the forward (the spectrum is recomputed).  gwav ([rows][gwav_pitch], T valid
- * samples per row) is overwritten, not accumulated into.  The clamp passes the gradient where mel >= clamp_eps and
+ * samples per row) is overwritten (added to under AFA_MEL_FLAG_ACCUMULATE).  The clamp passes the gradient where mel >= clamp_eps and
  * the magnitude has gradient 0 at 0 (torch.clamp / torch.abs).  bin_mlo / bin_mhi (int32 device [n_fft / 2 + 1]):
  * the filters whose support contains bin k all lie in [bin_mlo[k], bin_mhi[k]).
  * gother / gcoef / gscale_dev: see AFA_MEL_FLAG_L1_SIGN below (NULL, 0, NULL otherwise).

@@ -16,7 +16,8 @@ norm='slaney').  `slaney_mel_filterbank` restates librosa's published algorithm 
 linear below 1 kHz, log above; triangles in Hz; area normalisation 2 / (f[m+2] - f[m])); tests/test_oracle_mel.py
 pins it on an independent implementation of the same published algorithm that IS installed
 (`transformers.audio_utils.mel_filter_bank(norm='slaney', mel_scale='slaney')`, the one Whisper's feature extractor
-uses in place of librosa) through tests/golden/mel_golden.npz.  The STFT / magnitude / log part is pinned on outputs
+uses in place of librosa) through tests/golden/mel_golden.npz.  Against librosa's own array the filterbank is therefore
+PARITY UNPINNED (librosa cannot be installed here); a caller who has librosa passes its basis in (`mel_basis=`).  The STFT / magnitude / log part is pinned on outputs
 of the reference's own `mel_spectrogram` and `MultiScaleMelSpectrogramLoss`, run unmodified by
 tests/golden/make_golden_mel.py with that filterbank standing in for librosa's.
 
