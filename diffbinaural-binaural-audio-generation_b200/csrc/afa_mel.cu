@@ -8,9 +8,10 @@
 //
 // Per CTA: up to 8 consecutive STFT frames of one waveform row.  Each frame is windowed while it is gathered from
 // global memory (replicated / reflected borders resolved by index arithmetic, no padded copy), packed as N/2 complex
-// points, transformed by a radix-2 Stockham FFT in shared memory (twiddles and window staged once per CTA), unpacked
-// to the N/2+1 one-sided bins as magnitudes, contracted with the mel filterbank in its banded form (each triangular
-// filter touches a contiguous run of bins) and written as full 32-byte sectors of the [rows, n_mels, n_frames] output.
+// points, transformed by a radix-4 (+ one radix-2 stage for odd log2) Stockham FFT in shared memory (twiddles staged
+// once per CTA, the window read through L1), unpacked to the N/2+1 one-sided bins as magnitudes, contracted with the
+// mel filterbank in its banded form (each triangular filter touches a contiguous run of bins; one thread per filter)
+// and written as full 32-byte sectors of the [rows, n_mels, n_frames] output.
 // Nothing of length n_frames * n_fft ever reaches HBM.
 //
 // Backward (d loss / d waveform, what `loss_mel.backward()` asks of the chain at BigVGAN/train_binaural_mel.py:759-787):
@@ -69,9 +70,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 
 // gather + window + pack one frame: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1]  (borders by index arithmetic)
 template <int M, int NT>
-__device__ __forceinline__ void gather_frame(const MelArgs& p, const float* x, int64_t s0, const float* win, float2* z, int tid) {
+__device__ __forceinline__ void gather_frame(const MelArgs& p, const float* x, int64_t s0, float2* z, int tid) {
+    const float2* win2 = reinterpret_cast<const float2*>(p.window);       // read-only, L1-resident, coalesced: no staging
     for (int n = tid; n < M; n += NT) {
         float v[2];
+        const float2 wn = __ldg(win2 + n);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             int64_t idx = s0 + 2 * n + h;
@@ -84,35 +87,59 @@ __device__ __forceinline__ void gather_frame(const MelArgs& p, const float* x, i
             } else {
                 s = 0.f;
             }
-            v[h] = s * win[2 * n + h];
+            v[h] = s * (h ? wn.y : wn.x);
         }
         z[n] = make_float2(v[0], v[1]);
     }
 }
 
-// M-point complex FFT (M = 2^(LOG2N-1)), radix-2 Stockham autosort, ping-pong between the two buffers; the caller
-// has synchronised after filling buf0; returns the buffer that holds the transform (synchronised).
+// M-point complex FFT (M = 2^(LOG2N-1)), Stockham autosort in shared memory, ping-pong between the two buffers:
+// radix-4 stages (half the barriers and shared-memory round trips of radix-2) and one closing radix-2 stage when
+// log2(M) is odd.  The caller has synchronised after filling buf0; returns the buffer holding the transform (synchronised).
 template <int LOG2N, int NT>
 __device__ __forceinline__ float2* fft_stockham(float2* buf0, float2* buf1, const float2* tw, int tid) {
-    constexpr int M = 1 << (LOG2N - 1);
+    constexpr int LOG2M = LOG2N - 1;
+    constexpr int M = 1 << LOG2M;
     float2* src = buf0;
     float2* dst = buf1;
 #pragma unroll
-    for (int ls = 0; ls < LOG2N - 1; ++ls) {
+    for (int ls = 0; ls + 2 <= LOG2M; ls += 2) {
         const int Ns = 1 << ls;
-        for (int j = tid; j < M / 2; j += NT) {
+        for (int j = tid; j < M / 4; j += NT) {
             const int k = j & (Ns - 1);
-            const float2 w = tw[k << (LOG2N - 1 - ls)];      // exp(-2 pi i k / (2 Ns))
-            const float2 a = src[j];
-            const float2 b = cmul(src[j + M / 2], w);
-            const int j0 = ((j - k) << 1) + k;
-            dst[j0] = make_float2(a.x + b.x, a.y + b.y);
-            dst[j0 + Ns] = make_float2(a.x - b.x, a.y - b.y);
+            const int t1 = k << (LOG2M - 1 - ls);              // exp(-2 pi i k r / (4 Ns)): r = 1, 2 from the table, r = 3 as their product
+            const float2 w1 = tw[t1];
+            const float2 w2 = tw[2 * t1];
+            const float2 w3 = cmul(w1, w2);
+            const float2 v0 = src[j];
+            const float2 v1 = cmul(src[j + M / 4], w1);
+            const float2 v2 = cmul(src[j + M / 2], w2);
+            const float2 v3 = cmul(src[j + 3 * (M / 4)], w3);
+            const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+            const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+            const int j0 = ((j - k) << 2) + k;
+            dst[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+            dst[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);          // d02 - i d13
+            dst[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+            dst[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);      // d02 + i d13
         }
         __syncthreads();
         float2* t = src;
         src = dst;
         dst = t;
+    }
+    if (LOG2M & 1) {
+        constexpr int Ns = M / 2;
+        for (int j = tid; j < M / 2; j += NT) {
+            const int k = j & (Ns - 1);
+            const float2 a = src[j];
+            const float2 b = cmul(src[j + M / 2], tw[2 * k]);  // exp(-2 pi i k / M)
+            const int j0 = ((j - k) << 1) + k;
+            dst[j0] = make_float2(a.x + b.x, a.y + b.y);
+            dst[j0 + Ns] = make_float2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+        return dst;
     }
     return src;
 }
@@ -132,6 +159,18 @@ __device__ __forceinline__ float2 unpack_bin(const float2* Z, const float2* tw, 
     return make_float2(e.x + t.y, e.y - t.x);
 }
 
+// mel[m] = sum_q w[q] * val(b0 + q) over the filter's run, one thread per filter (a warp per filter with a shuffle
+// tree was measured: 3.3x the instructions for runs of 2 ... 40 bins, 142 -> 245 us at clip length).
+template <typename F>
+__device__ __forceinline__ float band_sum(const MelArgs& p, int m, F val) {
+    const int b0 = __ldg(p.band_start + m);
+    const int bl = __ldg(p.band_len + m);
+    const float* w = p.band_w + __ldg(p.band_off + m);
+    float s = 0.f;
+    for (int q = 0; q < bl; ++q) s = fmaf(__ldg(w + q), val(b0 + q), s);
+    return s;
+}
+
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT) afa_logmel_kernel(const MelArgs p) {
     constexpr int N = 1 << LOG2N;
@@ -140,25 +179,22 @@ __global__ void __launch_bounds__(NT) afa_logmel_kernel(const MelArgs p) {
     float2* buf0 = reinterpret_cast<float2*>(smem_raw);
     float2* buf1 = buf0 + M;
     float2* tw = buf1 + M;
-    float* win = reinterpret_cast<float*>(tw + M);
-    float* mag = win + N;                 // [M + 1]
-    float* melout = mag + (M + 1);        // [n_mels][frames per CTA]
+    float* mag = reinterpret_cast<float*>(tw + M);   // [M + 1]
+    float* melout = mag + (M + 1);                   // [n_mels][frames per CTA]
 
     const int tid = threadIdx.x;
     const int fshift = p.fshift;
     const int fpc = 1 << fshift;
     const int64_t f0 = (int64_t)blockIdx.x << fshift;
 
-    for (int i = tid; i < M; i += NT) tw[i] = p.twiddle[i];
-    for (int i = tid; i < N; i += NT) win[i] = p.window[i];
-    __syncthreads();
+    for (int i = tid; i < M; i += NT) tw[i] = p.twiddle[i];          // visible after the first frame's barrier
 
     const int nf = (int)min((int64_t)fpc, p.n_frames - f0);
     for (int64_t row = blockIdx.y; row < p.rows; row += gridDim.y) {   // gridDim.y == rows unless rows > 65535
         const float* x = p.wav + row * p.row_pitch;
         for (int fi = 0; fi < nf; ++fi) {
             const int64_t s0 = (f0 + fi) * (int64_t)p.hop - p.pad;
-            gather_frame<M, NT>(p, x, s0, win, buf0, tid);
+            gather_frame<M, NT>(p, x, s0, buf0, tid);
             __syncthreads();
             const float2* Z = fft_stockham<LOG2N, NT>(buf0, buf1, tw, tid);
 
@@ -171,11 +207,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_kernel(const MelArgs p) {
 
             // banded mel contraction + dynamic-range compression
             for (int m = tid; m < p.n_mels; m += NT) {
-                const int b0 = __ldg(p.band_start + m);
-                const int bl = __ldg(p.band_len + m);
-                const float* w = p.band_w + __ldg(p.band_off + m);
-                float s = 0.f;
-                for (int q = 0; q < bl; ++q) s = fmaf(__ldg(w + q), mag[b0 + q], s);
+                float s = band_sum(p, m, [&](int k) { return mag[k]; });
                 if (!p.raw) s = logf(fmaxf(s, p.clamp_eps)) * p.log_scale;
                 melout[(m << fshift) + fi] = s;
             }
@@ -209,9 +241,9 @@ template <int LOG2N>
 int launch(MelArgs a, int64_t rows, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
     constexpr int M = N / 2;
-    constexpr int NT = (M / 2 < 32) ? 32 : (M / 2 > 256 ? 256 : M / 2);
+    constexpr int NT = (M / 4 < 32) ? 32 : (M / 4 > 256 ? 256 : M / 4);    // one radix-4 butterfly per thread and stage
     a.fshift = pick_fshift(a.n_frames, rows);
-    const size_t smem = sizeof(float2) * 3 * M + sizeof(float) * (N + M + 1) + sizeof(float) * ((size_t)a.n_mels << a.fshift);
+    const size_t smem = sizeof(float2) * 3 * M + sizeof(float) * (M + 1) + sizeof(float) * ((size_t)a.n_mels << a.fshift);
     const int64_t gx = (a.n_frames + (1 << a.fshift) - 1) >> a.fshift;
     if (gx > 0x7fffffffLL) return afa_internal::set_error(AFA_ERR_TOO_LARGE, "afa_logmel_fwd: %lld frames per row exceed the grid", (long long)a.n_frames);
     const unsigned gy = (unsigned)(rows < 65535 ? rows : 65535);
@@ -239,8 +271,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
     float2* buf1 = buf0 + M;
     float2* tw = buf1 + M;
     float2* spec = tw + M;                                   // [M + 1] (re, im), later the Hermitian half H
-    float* win = reinterpret_cast<float*>(spec + (M + 1));   // [N]
-    float* gmel = win + N;                                   // [n_mels]
+    float* gmel = reinterpret_cast<float*>(spec + (M + 1));  // [n_mels]
     float* gtile = gmel + p.n_mels;                          // [n_mels][frames per CTA]
 
     const int tid = threadIdx.x;
@@ -248,7 +279,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
     const int fpc = 1 << fshift;
     const int64_t f0 = (int64_t)blockIdx.x << fshift;
     for (int i = tid; i < M; i += NT) tw[i] = p.twiddle[i];
-    for (int i = tid; i < N; i += NT) win[i] = p.window[i];
+    const float2* win2 = reinterpret_cast<const float2*>(p.window);
     const int nf = (int)min((int64_t)fpc, p.n_frames - f0);
 
     for (int64_t row = blockIdx.y; row < p.rows; row += gridDim.y) {
@@ -256,7 +287,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
         const float* g = p.gout + row * (int64_t)p.n_mels * p.n_frames;
         const float* g2 = p.l1_sign ? p.gother + row * (int64_t)p.n_mels * p.n_frames : nullptr;
         const float l1c = p.l1_sign ? p.gcoef * (p.gscale_dev ? __ldg(p.gscale_dev) : 1.f) : 0.f;
-        __syncthreads();                                     // tw / win staged; gtile free again
+        __syncthreads();                                     // tw staged; gtile free again
         for (int i = tid; i < (p.n_mels << fshift); i += NT) {
             const int m = i >> fshift;
             const int fi = i & (fpc - 1);
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
         }
         for (int fi = 0; fi < nf; ++fi) {
             const int64_t s0 = (f0 + fi) * (int64_t)p.hop - p.pad;
-            gather_frame<M, NT>(p, x, s0, win, buf0, tid);
+            gather_frame<M, NT>(p, x, s0, buf0, tid);
             __syncthreads();
             const float2* Z = fft_stockham<LOG2N, NT>(buf0, buf1, tw, tid);
             for (int k = tid; k <= M; k += NT) spec[k] = unpack_bin<M>(Z, tw, k);
@@ -283,14 +314,10 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
             for (int m = tid; m < p.n_mels; m += NT) {
                 float gm = gtile[(m << fshift) + fi];
                 if (!p.raw) {
-                    const int b0 = __ldg(p.band_start + m);
-                    const int bl = __ldg(p.band_len + m);
-                    const float* w = p.band_w + __ldg(p.band_off + m);
-                    float s = 0.f;
-                    for (int q = 0; q < bl; ++q) {
-                        const float2 c = spec[b0 + q];
-                        s = fmaf(__ldg(w + q), sqrtf(c.x * c.x + c.y * c.y + p.mag_eps), s);
-                    }
+                    const float s = band_sum(p, m, [&](int k) {
+                        const float2 c = spec[k];
+                        return sqrtf(c.x * c.x + c.y * c.y + p.mag_eps);
+                    });
                     gm = s >= p.clamp_eps ? gm * p.log_scale / s : 0.f;      // torch.clamp passes the gradient where x >= min
                 }
                 gmel[m] = gm;
@@ -330,7 +357,8 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
             float2* fr = reinterpret_cast<float2*>(p.frames + ((row * p.n_frames + f0 + fi) << LOG2N));
             for (int n = tid; n < M; n += NT) {
                 const float2 v = z[n];
-                fr[n] = make_float2(v.x * win[2 * n], -v.y * win[2 * n + 1]);
+                const float2 wn = __ldg(win2 + n);
+                fr[n] = make_float2(v.x * wn.x, -v.y * wn.y);
             }
             __syncthreads();   // buf0 / buf1 / spec / gmel are rewritten by the next frame
         }
@@ -400,9 +428,9 @@ template <int LOG2N>
 int launch_bwd(MelArgs a, const OlaArgs& o, int64_t rows, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
     constexpr int M = N / 2;
-    constexpr int NT = (M / 2 < 32) ? 32 : (M / 2 > 256 ? 256 : M / 2);
+    constexpr int NT = (M / 4 < 32) ? 32 : (M / 4 > 256 ? 256 : M / 4);
     a.fshift = pick_fshift(a.n_frames, rows);
-    const size_t smem = sizeof(float2) * (4 * M + 1) + sizeof(float) * N + sizeof(float) * (((size_t)a.n_mels << a.fshift) + a.n_mels);
+    const size_t smem = sizeof(float2) * (4 * M + 1) + sizeof(float) * (((size_t)a.n_mels << a.fshift) + a.n_mels);
     const int64_t gx = (a.n_frames + (1 << a.fshift) - 1) >> a.fshift;
     const int64_t ox = (a.T + 255) / 256;
     if (gx > 0x7fffffffLL || ox > 0x7fffffffLL) return afa_internal::set_error(AFA_ERR_TOO_LARGE, "afa_logmel_bwd: row too long for the grid");
