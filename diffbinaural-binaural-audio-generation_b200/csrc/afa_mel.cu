@@ -159,6 +159,17 @@ __device__ __forceinline__ float2 unpack_bin(const float2* Z, const float2* tw, 
     return make_float2(e.x + t.y, e.y - t.x);
 }
 
+// A frame keeps M/4 threads busy (one radix-4 butterfly each), so a CTA of NT threads carries G = NT / (M/4) frames at once:
+// 32 frames for the 32-point window, one for 1024 points and more.  All slots run in lockstep between CTA-wide barriers.
+template <int LOG2N, int NT>
+struct Slots {
+    static constexpr int M = 1 << (LOG2N - 1);
+    static constexpr int TPF = (M / 4 < NT) ? M / 4 : NT;
+    static constexpr int G = NT / TPF;
+    static constexpr int MS = G > 1 ? M + 1 : M;     // slot stride of the FFT buffers (float2): odd, so slots land on different banks
+};
+constexpr int kIdleLane = 1 << 30;                   // lane index of an idle slot: past every loop bound
+
 // mel[m] = sum_q w[q] * val(b0 + q) over the filter's run, one thread per filter (a warp per filter with a shuffle
 // tree was measured: 3.3x the instructions for runs of 2 ... 40 bins, 142 -> 245 us at clip length).
 template <typename F>
@@ -175,14 +186,19 @@ template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT) afa_logmel_kernel(const MelArgs p) {
     constexpr int N = 1 << LOG2N;
     constexpr int M = N / 2;
+    constexpr int TPF = Slots<LOG2N, NT>::TPF;       // threads per frame = radix-4 butterflies per stage
+    constexpr int G = Slots<LOG2N, NT>::G;           // frames in flight per CTA (small windows: up to 32)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
-    float2* buf1 = buf0 + M;
-    float2* tw = buf1 + M;
-    float* mag = reinterpret_cast<float*>(tw + M);   // [M + 1]
-    float* melout = mag + (M + 1);                   // [n_mels][frames per CTA]
-
     const int tid = threadIdx.x;
+    const int g = tid / TPF;
+    const int l = tid % TPF;
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    constexpr int MS = Slots<LOG2N, NT>::MS;
+    float2* buf0 = tw + M + g * MS;                  // [G][MS]
+    float2* buf1 = buf0 + G * MS;                    // [G][MS]
+    float* mag = reinterpret_cast<float*>(tw + M + 2 * G * MS) + g * (M + 1);      // [G][M + 1]
+    float* melout = reinterpret_cast<float*>(tw + M + 2 * G * MS) + G * (M + 1);  // [n_mels][frames per CTA]
+
     const int fshift = p.fshift;
     const int fpc = 1 << fshift;
     const int64_t f0 = (int64_t)blockIdx.x << fshift;
@@ -192,26 +208,28 @@ __global__ void __launch_bounds__(NT) afa_logmel_kernel(const MelArgs p) {
     const int nf = (int)min((int64_t)fpc, p.n_frames - f0);
     for (int64_t row = blockIdx.y; row < p.rows; row += gridDim.y) {   // gridDim.y == rows unless rows > 65535
         const float* x = p.wav + row * p.row_pitch;
-        for (int fi = 0; fi < nf; ++fi) {
+        for (int fb = 0; fb < nf; fb += G) {
+            const int fi = fb + g;                                     // this slot's frame; idle slots only keep the barriers
+            const int le = fi < nf ? l : kIdleLane;
             const int64_t s0 = (f0 + fi) * (int64_t)p.hop - p.pad;
-            gather_frame<M, NT>(p, x, s0, buf0, tid);
+            gather_frame<M, TPF>(p, x, s0, buf0, le);
             __syncthreads();
-            const float2* Z = fft_stockham<LOG2N, NT>(buf0, buf1, tw, tid);
+            const float2* Z = fft_stockham<LOG2N, TPF>(buf0, buf1, tw, le);
 
             // one-sided spectrum of the real frame from the packed transform, as magnitudes
-            for (int k = tid; k <= M; k += NT) {
+            for (int k = le; k <= M; k += TPF) {
                 const float2 c = unpack_bin<M>(Z, tw, k);
                 mag[k] = sqrtf(c.x * c.x + c.y * c.y + p.mag_eps);
             }
             __syncthreads();
 
             // banded mel contraction + dynamic-range compression
-            for (int m = tid; m < p.n_mels; m += NT) {
+            for (int m = le; m < p.n_mels; m += TPF) {
                 float s = band_sum(p, m, [&](int k) { return mag[k]; });
                 if (!p.raw) s = logf(fmaxf(s, p.clamp_eps)) * p.log_scale;
                 melout[(m << fshift) + fi] = s;
             }
-            __syncthreads();   // mag / buf0 are rewritten by the next frame
+            __syncthreads();   // mag / buf0 are rewritten by the next pass
         }
 
         float* o = p.out + row * (int64_t)p.n_mels * p.n_frames;
@@ -224,8 +242,8 @@ __global__ void __launch_bounds__(NT) afa_logmel_kernel(const MelArgs p) {
     }
 }
 
-// Frames per CTA: the largest of 8, 4, 2, 1 that still gives every SM several CTAs.
-int pick_fshift(int64_t n_frames, int64_t rows) {
+// Frames per CTA: a power of two, at most max(8, frames in flight per CTA), traded against the number of CTAs.
+int pick_fshift(int64_t n_frames, int64_t rows, int slots) {
     static int sms = 0;
     if (sms == 0) {
         int dev = 0, n = 0;
@@ -233,7 +251,10 @@ int pick_fshift(int64_t n_frames, int64_t rows) {
         else sms = 148;
     }
     int fs = 3;
-    while (fs > 0 && ((n_frames + (1 << fs) - 1) >> fs) * rows < 8LL * sms) --fs;
+    while ((1 << fs) < slots) ++fs;
+    // more frames than slots only deepen the serial loop: give them up until every SM has 8 CTAs; fewer frames than slots
+    // idle lanes: give those up only when the launch would not even put 2 CTAs on every SM
+    while (fs > 0 && ((n_frames + (1 << fs) - 1) >> fs) * rows < ((1 << fs) > slots ? 8LL : 2LL) * sms) --fs;
     return fs;
 }
 
@@ -241,9 +262,11 @@ template <int LOG2N>
 int launch(MelArgs a, int64_t rows, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
     constexpr int M = N / 2;
-    constexpr int NT = (M / 4 < 32) ? 32 : (M / 4 > 256 ? 256 : M / 4);    // one radix-4 butterfly per thread and stage
-    a.fshift = pick_fshift(a.n_frames, rows);
-    const size_t smem = sizeof(float2) * 3 * M + sizeof(float) * (M + 1) + sizeof(float) * ((size_t)a.n_mels << a.fshift);
+    constexpr int NT = (M / 4 < 128) ? 128 : (M / 4 > 256 ? 256 : M / 4);  // one radix-4 butterfly per thread and stage
+    constexpr int G = Slots<LOG2N, NT>::G;
+    a.fshift = pick_fshift(a.n_frames, rows, G);
+    constexpr int MS = Slots<LOG2N, NT>::MS;
+    const size_t smem = sizeof(float2) * (M + 2 * G * MS) + sizeof(float) * G * (M + 1) + sizeof(float) * ((size_t)a.n_mels << a.fshift);
     const int64_t gx = (a.n_frames + (1 << a.fshift) - 1) >> a.fshift;
     if (gx > 0x7fffffffLL) return afa_internal::set_error(AFA_ERR_TOO_LARGE, "afa_logmel_fwd: %lld frames per row exceed the grid", (long long)a.n_frames);
     const unsigned gy = (unsigned)(rows < 65535 ? rows : 65535);
@@ -266,15 +289,21 @@ template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs p) {
     constexpr int N = 1 << LOG2N;
     constexpr int M = N / 2;
+    constexpr int TPF = Slots<LOG2N, NT>::TPF;
+    constexpr int G = Slots<LOG2N, NT>::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
-    float2* buf1 = buf0 + M;
-    float2* tw = buf1 + M;
-    float2* spec = tw + M;                                   // [M + 1] (re, im), later the Hermitian half H
-    float* gmel = reinterpret_cast<float*>(spec + (M + 1));  // [n_mels]
-    float* gtile = gmel + p.n_mels;                          // [n_mels][frames per CTA]
-
     const int tid = threadIdx.x;
+    const int g = tid / TPF;
+    const int l = tid % TPF;
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    constexpr int MS = Slots<LOG2N, NT>::MS;
+    float2* buf0 = tw + M + g * MS;                          // [G][MS]
+    float2* buf1 = buf0 + G * MS;                            // [G][MS]
+    float2* spec = tw + M + 2 * G * MS + g * (M + 1);        // [G][M + 1] (re, im), later the Hermitian half H
+    float* fbase = reinterpret_cast<float*>(tw + M + 2 * G * MS + G * (M + 1));
+    float* gmel = fbase + g * p.n_mels;                      // [G][n_mels]
+    float* gtile = fbase + G * p.n_mels;                     // [n_mels][frames per CTA]
+
     const int fshift = p.fshift;
     const int fpc = 1 << fshift;
     const int64_t f0 = (int64_t)blockIdx.x << fshift;
@@ -284,7 +313,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
 
     for (int64_t row = blockIdx.y; row < p.rows; row += gridDim.y) {
         const float* x = p.wav + row * p.row_pitch;
-        const float* g = p.gout + row * (int64_t)p.n_mels * p.n_frames;
+        const float* go = p.gout + row * (int64_t)p.n_mels * p.n_frames;
         const float* g2 = p.l1_sign ? p.gother + row * (int64_t)p.n_mels * p.n_frames : nullptr;
         const float l1c = p.l1_sign ? p.gcoef * (p.gscale_dev ? __ldg(p.gscale_dev) : 1.f) : 0.f;
         __syncthreads();                                     // tw staged; gtile free again
@@ -294,7 +323,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
             float v = 0.f;
             if (fi < nf) {
                 const int64_t at = (int64_t)m * p.n_frames + f0 + fi;
-                v = __ldg(g + at);
+                v = __ldg(go + at);
                 if (p.l1_sign) {                             // d |a - b| / d a = sign(a - b), 0 at 0 (torch.sign)
                     const float d = v - __ldg(g2 + at);
                     v = d > 0.f ? l1c : (d < 0.f ? -l1c : 0.f);
@@ -302,16 +331,18 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
             }
             gtile[i] = v;
         }
-        for (int fi = 0; fi < nf; ++fi) {
+        for (int fb = 0; fb < nf; fb += G) {
+            const int fi = fb + g;
+            const int le = fi < nf ? l : kIdleLane;          // idle slots only keep the barriers
             const int64_t s0 = (f0 + fi) * (int64_t)p.hop - p.pad;
-            gather_frame<M, NT>(p, x, s0, buf0, tid);
+            gather_frame<M, TPF>(p, x, s0, buf0, le);
             __syncthreads();
-            const float2* Z = fft_stockham<LOG2N, NT>(buf0, buf1, tw, tid);
-            for (int k = tid; k <= M; k += NT) spec[k] = unpack_bin<M>(Z, tw, k);
+            const float2* Z = fft_stockham<LOG2N, TPF>(buf0, buf1, tw, le);
+            for (int k = le; k <= M; k += TPF) spec[k] = unpack_bin<M>(Z, tw, k);
             __syncthreads();
 
             // d loss / d mel[m]: the forward's mel value is recomputed, then log / clamp are differentiated
-            for (int m = tid; m < p.n_mels; m += NT) {
+            for (int m = le; m < p.n_mels; m += TPF) {
                 float gm = gtile[(m << fshift) + fi];
                 if (!p.raw) {
                     const float s = band_sum(p, m, [&](int k) {
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
 
             // transposed mel contraction, magnitude, and the Hermitian half of the real adjoint:
             // g[n] = Re sum_{k=0..M} G_k e^{+2 pi i k n / N} = sum_{k=0..N-1} H_k e^{...},  H_0 = Re G_0, H_M = Re G_M, H_k = G_k / 2
-            for (int k = tid; k <= M; k += NT) {
+            for (int k = le; k <= M; k += TPF) {
                 const float2 c = spec[k];
                 const float mag = sqrtf(c.x * c.x + c.y * c.y + p.mag_eps);
                 float gk = 0.f;
@@ -343,7 +374,7 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
 
             // packed half-size spectrum of the real sequence: Z_k = (H_k + conj H_{M-k}) + i (H_k - conj H_{M-k}) e^{+2 pi i k / N};
             // the inverse transform is taken as conj(FFT(conj Z))
-            for (int k = tid; k < M; k += NT) {
+            for (int k = le; k < M; k += TPF) {
                 const float2 hk = spec[k];
                 const float2 hm = spec[M - k];
                 const float2 e = make_float2(hk.x + hm.x, hk.y - hm.y);
@@ -353,9 +384,9 @@ __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs
                 buf0[k] = make_float2(e.x - o.y, -(e.y + o.x));
             }
             __syncthreads();
-            const float2* z = fft_stockham<LOG2N, NT>(buf0, buf1, tw, tid);
+            const float2* z = fft_stockham<LOG2N, TPF>(buf0, buf1, tw, le);
             float2* fr = reinterpret_cast<float2*>(p.frames + ((row * p.n_frames + f0 + fi) << LOG2N));
-            for (int n = tid; n < M; n += NT) {
+            for (int n = le; n < M; n += TPF) {
                 const float2 v = z[n];
                 const float2 wn = __ldg(win2 + n);
                 fr[n] = make_float2(v.x * wn.x, -v.y * wn.y);
@@ -428,9 +459,11 @@ template <int LOG2N>
 int launch_bwd(MelArgs a, const OlaArgs& o, int64_t rows, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
     constexpr int M = N / 2;
-    constexpr int NT = (M / 4 < 32) ? 32 : (M / 4 > 256 ? 256 : M / 4);
-    a.fshift = pick_fshift(a.n_frames, rows);
-    const size_t smem = sizeof(float2) * (4 * M + 1) + sizeof(float) * (((size_t)a.n_mels << a.fshift) + a.n_mels);
+    constexpr int NT = (M / 4 < 128) ? 128 : (M / 4 > 256 ? 256 : M / 4);
+    constexpr int G = Slots<LOG2N, NT>::G;
+    a.fshift = pick_fshift(a.n_frames, rows, G);
+    constexpr int MS = Slots<LOG2N, NT>::MS;
+    const size_t smem = sizeof(float2) * (M + 2 * G * MS + G * (M + 1)) + sizeof(float) * (((size_t)a.n_mels << a.fshift) + (size_t)G * a.n_mels);
     const int64_t gx = (a.n_frames + (1 << a.fshift) - 1) >> a.fshift;
     const int64_t ox = (a.T + 255) / 256;
     if (gx > 0x7fffffffLL || ox > 0x7fffffffLL) return afa_internal::set_error(AFA_ERR_TOO_LARGE, "afa_logmel_bwd: row too long for the grid");
