@@ -165,7 +165,7 @@ def test_fused_l1_path_equals_generic_autograd_path(mel_golden):
         y = _dev(g["msl_y"]).requires_grad_(True)
         v = loss(x, y)
         (v * 60.0).backward()                                   # lambda_melloss: the upstream gradient is not 1
-        res.append((float(v), x.grad.clone(), y.grad.clone()))
+        res.append((float(v.detach()), x.grad.clone(), y.grad.clone()))
     assert res[0][0] == pytest.approx(res[1][0], rel=1e-5)
     assert res[0][0] == pytest.approx(float(g["msl_loss"]), rel=1e-4)
     for a, b in ((res[0][1], res[1][1]), (res[0][2], res[1][2])):
