@@ -6,7 +6,8 @@
 // -> log(clamp(., 1e-5))) and of `MultiScaleMelSpectrogramLoss.mel_spectrogram` + its log10
 // (BigVGAN/loss.py:110-167, 195-200), which differ only in pad width, magnitude epsilon, clamp and log base.
 //
-// Per CTA: up to 8 consecutive STFT frames of one waveform row.  Each frame is windowed while it is gathered from
+// Per CTA: a run of consecutive STFT frames of one waveform row (several in flight at once for the small windows, see
+// Slots).  Each frame is windowed while it is gathered from
 // global memory (replicated / reflected borders resolved by index arithmetic, no padded copy), packed as N/2 complex
 // points, transformed by a radix-4 (+ one radix-2 stage for odd log2) Stockham FFT in shared memory (twiddles staged
 // once per CTA, the window read through L1), unpacked to the N/2+1 one-sided bins as magnitudes, contracted with the
@@ -28,8 +29,8 @@
 
 namespace afa_mel {
 
-// Frames per CTA: 8 = one 32-byte sector of every output row; fewer when the launch would otherwise leave SMs idle
-// (a training batch is ~1000 frames: latency-bound, not bandwidth-bound).  See pick_fshift().
+// Frames per CTA (1 << fshift): at least 8 = one 32-byte sector of every output row when the launch is large; fewer when
+// it would otherwise leave SMs idle (a training batch is ~1000 frames: latency-bound, not bandwidth-bound).  See pick_fshift().
 
 struct MelArgs {
     const float* wav;          // [rows][row_pitch]
@@ -283,7 +284,7 @@ int launch(MelArgs a, int64_t rows, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward, kernel 1: output gradient -> windowed frame gradients (one frame at a time, up to 8 per CTA)
+// backward, kernel 1: output gradient -> windowed frame gradients (same frame slots as the forward)
 // ---------------------------------------------------------------------------------------------------------------
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT) afa_logmel_bwd_frames_kernel(const MelArgs p) {
