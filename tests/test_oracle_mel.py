@@ -153,3 +153,27 @@ def test_bin_cover_bounds_every_filter(mel_golden):
             ms = np.flatnonzero(basis[:, b])
             if ms.size:
                 assert lo[b] <= ms[0] and ms[-1] < hi[b], (k, b)
+
+
+@pytest.mark.parametrize("T,n_fft,hop,n_mels", [(4096, 1024, 256, 80), (1500, 1024, 256, 80), (777, 256, 64, 40), (9000, 2048, 512, 128),
+                                               (300, 64, 16, 10), (4099, 512, 128, 80)])
+def test_oracle_matches_torch_chain_on_cpu(T, n_fft, hop, n_mels):
+    """The numpy restatement against the torch-op restatement of the same reference lines (oracle/torch_path.py), executed
+    on the CPU for shapes outside the committed fixture: ragged lengths, every pad / hop relation the reference can produce."""
+    import torch
+
+    from oracle import torch_path as TP
+
+    rng = np.random.default_rng(T + n_fft)
+    y = (0.3 * rng.standard_normal((2, T))).clip(-1, 1).astype(np.float32)
+    basis = M.slaney_mel_filterbank(SR, n_fft, n_mels)
+    ref = TP.mel_spectrogram_torch(torch.from_numpy(y).double(), torch.from_numpy(basis).double(), n_fft, hop, n_fft).numpy()
+    mine = M.mel_spectrogram(y, n_fft, n_mels, SR, hop, n_fft, 0, None, mel_basis=basis)
+    assert mine.shape == ref.shape
+    assert np.abs(mine - ref).max() <= 5e-6          # the torch chain's hann window is float32 (meldataset.py:93)
+    # the loss's variant (center=True, |.|, log10) for the same window
+    ref2 = TP.msmsl_logmels_torch(torch.from_numpy(y).double()[:, None, :], torch.from_numpy(basis).double(), n_fft).numpy()
+    mels = M.msmsl_mels(y[:, None, :].astype(np.float64), SR, n_mels, n_fft, mel_basis=basis)
+    mine2 = np.log(np.maximum(mels, 1e-5)) / np.log(10.0)
+    assert mine2.shape == ref2.shape
+    assert np.abs(mine2 - ref2).max() <= 5e-6       # float32 window; torch divides by a float32 log(10) tensor (loss.py:196)
