@@ -22,6 +22,7 @@ _COMMON = [os.path.join(_INCLUDE, "afa_b200.h"), os.path.join(_CSRC, "afa_intern
 _UNITS = {
     "afa_capi.cu": ["afa_kernels.cuh", "afa_cl_kernels.cuh", "afa_actconv_kernels.cuh"],
     "afa_mel.cu": [],
+    "afa_tc.cu": ["afa_tc_kernels.cuh"],
 }
 
 

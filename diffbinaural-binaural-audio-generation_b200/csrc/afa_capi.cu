@@ -24,6 +24,7 @@ std::atomic<long long> g_launches{0};
 int g_tune_chunks[3] = {0, 0, 0};   // [2]: channels-last walk, segment length in units of 12 samples
 int g_tune_threads[3] = {0, 0, 0};
 int g_actconv_xs = 1;     // fused activation+convolution, tcgen05 path: stage the input rows in shared memory (which=4)
+int g_tc_mode = 1, g_tc_ny = 0, g_tc_rlog2 = -1;   // tensor-core Activation1d (which = 5, 6)
 int g_actconv_path = 1;   // fused activation+convolution: 1 = tcgen05 (falls back to mma.sync when the tile does not fit), 0 = mma.sync
 
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
@@ -264,6 +265,20 @@ const char* afa_last_error(void) { return g_err; }
 int64_t afa_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int afa_set_tuning(int which, int chunks, int threads) {
+    if (which == 5) {   // tensor-core Activation1d (bf16): chunks = 0 off / 1 heuristic / 2 whenever eligible; threads = forced blocks per lane (0 = heuristic)
+        if (chunks < 0 || chunks > 2 || !(threads == 0 || threads == 4 || threads == 8 || threads == 12 || threads == 16))
+            return fail(AFA_ERR_BAD_ARG, "tensor-core path: mode 0..2, blocks per lane 0 / 4 / 8 / 12 / 16");
+        g_tc_mode = chunks;
+        g_tc_ny = threads;
+        afa_internal::tc_set_tuning(g_tc_mode, g_tc_ny, g_tc_rlog2);
+        return 0;
+    }
+    if (which == 6) {   // tensor-core Activation1d: log2 of the rows per CTA (3..7; -1 = heuristic)
+        if (chunks != -1 && (chunks < 3 || chunks > 7)) return fail(AFA_ERR_BAD_ARG, "log2(rows per CTA) must be 3..7 or -1");
+        g_tc_rlog2 = chunks;
+        afa_internal::tc_set_tuning(g_tc_mode, g_tc_ny, g_tc_rlog2);
+        return 0;
+    }
     if (which == 4) {   // fused activation+convolution, tcgen05 path: 1 = input rows staged by a bulk copy (default), 0 = global loads
         if (chunks != 0 && chunks != 1) return fail(AFA_ERR_BAD_ARG, "input staging must be 0 or 1");
         g_actconv_xs = chunks;
@@ -279,7 +294,7 @@ int afa_set_tuning(int which, int chunks, int threads) {
         g_tune_chunks[2] = chunks;
         return 0;
     }
-    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd) or 3 (fused conv tensor path)");
+    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd)");
     bool ok = chunks == 0;
 #define X(CH) ok = ok || chunks == CH;
     AFA_CHUNK_LIST(X)
@@ -300,6 +315,10 @@ int afa_activation1d_fwd(const void* x, void* y, const float* alpha, const float
     Plan pl;
     if (int rc = make_plan(0, x, y, nullptr, batch, channels, T, dtype, &pl)) return rc;
     if (pl.total_segs == 0) return 0;
+    // bf16 tensors with 16-byte aligned rows: both FIR filters run on the tensor cores (afa_tc_kernels.cuh)
+    if (afa_internal::tc_eligible(x, y, batch, channels, T, dtype))
+        return afa_internal::tc_fwd_launch(x, y, alpha, beta, taps_up12, taps_down12, batch, channels, T, flags,
+                                           (cudaStream_t)stream, 0, nullptr);
     afa::FwdArgs a;
     a.x = x;
     a.y = y;
@@ -359,6 +378,7 @@ int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]) {
 }
 
 int afa_kernel_info_shape(int which, int dtype, int64_t batch, int64_t channels, int64_t T, int32_t out[6]) {
+    if (out && which == 5) return afa_internal::tc_kernel_info(out);   // the tensor-core forward (one variant)
     if (!out || which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "bad argument");
     Plan pl;
     if (int rc = make_plan(which, nullptr, nullptr, nullptr, batch, channels, T, dtype, &pl)) return rc;

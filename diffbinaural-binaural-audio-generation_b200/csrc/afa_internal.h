@@ -2,9 +2,19 @@
 // the thread-local error string behind afa_last_error() and the launch counter behind afa_launch_count().
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace afa_internal {
 int set_error(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 int cuda_error(cudaError_t e, const char* what);
 void count_launch();
+
+// afa_tc.cu: Activation1d forward with both FIR filters on the tensor cores (bf16 I/O, 16-byte aligned rows)
+void tc_set_tuning(int enable, int ny, int rlog2);
+bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, int64_t T, int dtype);
+void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rgroups, int64_t* n_tstrips);
+int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta, const float* taps_up12,
+                  const float* taps_down12, int64_t batch, int64_t channels, int64_t T, int flags, cudaStream_t st,
+                  int debug, float* dbg);
+int tc_kernel_info(int32_t out[6]);
 }  // namespace afa_internal

@@ -1,0 +1,186 @@
+// afa_tc.cu -- host side of the tensor-core Activation1d kernels (afa_tc_kernels.cuh): eligibility, tile-shape
+// choice, tensor-map encoding (driver entry point fetched through the runtime: no link against libcuda), launch.
+// Called from afa_activation1d_fwd (afa_capi.cu) for bf16 tensors whose rows are 16-byte aligned.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "afa_b200.h"
+#include "afa_internal.h"
+#include "afa_tc_kernels.cuh"
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+int g_tc_enable = 1;      // afa_set_tuning(5, ...): 0 = never take the tensor-core path
+int g_tc_ny = 0;          // forced y blocks per lane (0 = heuristic)
+int g_tc_rlog2 = -1;      // forced log2(rows per CTA) (-1 = heuristic)
+
+// [rows, T] bf16 row-major, box = R rows x 64 samples, 128-byte swizzle, zero fill outside the tensor
+int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)T * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)R};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return 0;
+}
+
+uint16_t bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+// v ~= hi + lo with hi, lo bf16: 16 mantissa bits for the filter taps, both halves ride the same fp32 accumulation
+void split_bf16(float v, uint16_t* hi, uint16_t* lo) {
+    *hi = bf16_rne(v);
+    const uint32_t hb = (uint32_t)*hi << 16;
+    float hf;
+    memcpy(&hf, &hb, 4);
+    *lo = bf16_rne(v - hf);
+}
+
+}  // namespace
+
+namespace afa_internal {
+
+void tc_set_tuning(int enable, int ny, int rlog2) {
+    g_tc_enable = enable;
+    g_tc_ny = ny;
+    g_tc_rlog2 = rlog2;
+}
+
+// The tensor-core path takes bf16 tensors whose rows start on 16-byte boundaries (tensor-map TMA) and that are
+// large enough to fill the machine; everything else stays on the register-walk kernels of afa_kernels.cuh.
+bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, int64_t T, int dtype) {
+    if (!g_tc_enable || dtype != AFA_DTYPE_BF16) return false;
+    if (T < 64 || (T % 8) != 0 || T >= (1ll << 30)) return false;
+    if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return false;
+    const int64_t rows = batch * channels;
+    if (rows < 8 || rows >= (1ll << 30)) return false;
+    if (g_tc_enable == 1 && rows * T < (1ll << 20)) return false;   // tiny launches: fewer, simpler CTAs win
+    return encode_fn() != nullptr;
+}
+
+void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rgroups, int64_t* n_tstrips) {
+    int rlog2 = 3;
+    for (int cand = 7; cand >= 3; --cand) {
+        const int64_t R = 1ll << cand;
+        const int64_t padded = (rows + R - 1) / R * R;
+        if (padded * 10 <= rows * 11) { rlog2 = cand; break; }
+    }
+    if (g_tc_rlog2 >= 3 && g_tc_rlog2 <= 7) rlog2 = g_tc_rlog2;
+    const int64_t R = 1ll << rlog2, G = 128 / R;
+    const int64_t rg = (rows + R - 1) / R;
+    auto ctas = [&](int ny) { return rg * ((T + G * 16 * ny - 1) / (G * 16 * ny)); };
+    // blocks per lane: a CTA costs ~5 block-times of set-up / fill / drain plus one per block, and the grid runs in waves of
+    // 2 CTAs per SM (fitted to same-box sweeps, profiles/r02_tc_sweep.log): take the cheapest, the longer strip on ties
+    static int slots = 0;
+    if (!slots) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * (sms > 0 ? sms : 148);
+    }
+    int ny = 16;
+    int64_t best = -1;
+    for (int cand = 16; cand >= 4; cand -= 4) {
+        const int64_t cost = ((ctas(cand) + slots - 1) / slots) * (5 + cand);
+        if (best < 0 || cost < best) { best = cost; ny = cand; }
+    }
+    if (g_tc_ny == 4 || g_tc_ny == 8 || g_tc_ny == 12 || g_tc_ny == 16) ny = g_tc_ny;
+    *rlog2_out = rlog2;
+    *ny_out = ny;
+    *n_rgroups = rg;
+    *n_tstrips = (T + G * 16 * ny - 1) / (G * 16 * ny);
+}
+
+int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta, const float* taps_up12,
+                  const float* taps_down12, int64_t batch, int64_t channels, int64_t T, int flags, cudaStream_t st,
+                  int debug, float* dbg) {
+    const int64_t rows = batch * channels;
+    int rlog2, ny;
+    int64_t rg, ts;
+    tc_plan(rows, T, &rlog2, &ny, &rg, &ts);
+    if (rg * ts >= (1ll << 31)) return set_error(AFA_ERR_TOO_LARGE, "grid of %lld CTAs", (long long)(rg * ts));
+    CUtensorMap tmx, tmy;
+    if (int rc = make_map(&tmx, x, rows, T, 1 << rlog2)) return rc;
+    if (int rc = make_map(&tmy, y, rows, T, 1 << rlog2)) return rc;
+    afa_tc::Args a;
+    memset(&a, 0, sizeof(a));
+    a.x = static_cast<const __nv_bfloat16*>(x);
+    a.alpha = alpha;
+    a.beta = beta;
+    for (int i = 0; i < 12; ++i) {
+        split_bf16(2.0f * taps_up12[i], &a.up_hi[i], &a.up_lo[i]);      // ratio * conv_transpose taps        resample.py:33
+        split_bf16(taps_down12[i], &a.dn_hi[i], &a.dn_lo[i]);
+    }
+    a.rows = (int32_t)rows;
+    a.C = (int32_t)channels;
+    a.T = (int32_t)T;
+    a.flags = flags;
+    a.R_log2 = rlog2;
+    a.NY = ny;
+    a.n_tstrips = (int32_t)ts;
+    a.debug = debug;
+    a.dbg = dbg;
+    a.dbg_cta = (int32_t)(rg * ts / 2);
+    static thread_local bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, afa_tc::kSmemBytes);
+        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel)");
+        // two CTAs per SM need the largest shared-memory carveout (2 x 88 KB)
+        e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel, carveout)");
+        attr_set[dev] = true;
+    }
+    afa_tc::afa_tc_fwd_kernel<<<(unsigned)(rg * ts), afa_tc::kThreads, afa_tc::kSmemBytes, st>>>(tmx, tmy, a);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_error(e, "afa_tc_fwd_kernel launch");
+}
+
+int tc_kernel_info(int32_t out[6]) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, afa_tc::afa_tc_fwd_kernel);
+    if (e != cudaSuccess) return cuda_error(e, "cudaFuncGetAttributes(afa_tc_fwd_kernel)");
+    e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, afa_tc::kSmemBytes);
+    if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel)");
+    e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel, carveout)");
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, afa_tc::afa_tc_fwd_kernel, afa_tc::kThreads, afa_tc::kSmemBytes);
+    if (e != cudaSuccess) return cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    out[0] = fa.numRegs;
+    out[1] = (int32_t)(fa.sharedSizeBytes + afa_tc::kSmemBytes);
+    out[2] = afa_tc::kThreads;
+    out[3] = 16 * afa_tc::kNYMax;
+    out[4] = occ;
+    out[5] = 0;
+    return 0;
+}
+
+}  // namespace afa_internal

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 130            /* 0.1.3: + fused log-mel spectrogram (training-side neighbour of the path) */
+#define AFA_VERSION 140            /* 0.1.4: + tensor-core (tcgen05) forward for bf16 activations */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
@@ -243,8 +243,12 @@ int afa_l1_partial_sums(const float *a, const float *b, int64_t n, float *partia
  * which=2: channels-last forward, segment length = 12 * chunks + 2 samples.
  * which=3: tensor path of the fused activation+convolution: chunks = 1 tcgen05 (default), 0 legacy mma.sync.
  * which=4: its input staging: chunks = 1 bulk-copy the tile's input rows into shared memory (default), 0 global loads.
+ * which=5: tensor-core forward (bf16 tensors, T % 8 == 0, 16-byte aligned x and y: both FIR filters as banded-Toeplitz
+ *          tcgen05 products, csrc/afa_tc_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible;
+ *          threads = blocks of 16 outputs per TMEM lane (4 / 8 / 12 / 16; 0 = built-in choice).
+ * which=6: its rows per CTA as log2 (3..7; -1 = built-in choice).
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
- * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects.
+ * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects (which = 5: the tensor-core forward).
  */
 int afa_set_tuning(int which, int chunks, int threads);
 int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]);

@@ -372,3 +372,146 @@ def test_backward_is_run_to_run_deterministic():
             for _ in range(3):
                 again = Fn.activation1d_backward_raw(x, gy, a, b, taps, taps, True)
                 assert all(torch.equal(p, q) for p, q in zip(first, again))
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core forward (csrc/afa_tc_kernels.cuh): bf16 tensors with T % 8 == 0 and 16-byte aligned rows
+# ------------------------------------------------------------------------------------------------
+def _tc_forward(x, alpha, beta, logscale, mode, ny=0, rlog2=-1):
+    _, _lib, Fn, _, _ = _mods()
+    taps = Fn.host_taps(TP.make_taps())
+    _lib.set_tuning(5, mode, ny)
+    _lib.set_tuning(6, rlog2, 0)
+    try:
+        n0 = _lib.launch_count()
+        y = Fn.activation1d_forward_raw(x, alpha, beta, taps, taps, logscale)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == n0 + 1
+    finally:
+        _lib.set_tuning(5, 1, 0)
+        _lib.set_tuning(6, -1, 0)
+    return y
+
+
+TC_EDGE = [(1, 8, 64), (1, 8, 72), (2, 3, 128), (3, 5, 1000), (1, 24, 8), (2, 24, 256), (1, 128, 264), (1, 130, 512),
+           (2, 24, 2040), (5, 7, 4104), (1, 16, 16), (2, 12, 24), (1, 9, 40)]
+
+
+@pytest.mark.parametrize("kind,logscale", [("snakebeta", True), ("snake", True), ("snakebeta", False), ("snake", False)])
+def test_tensor_core_forward_edge_grid(kind, logscale):
+    """Rows that are no multiple of the CTA's row count, rows shorter than one CTA span, T = 8 ... around the 64-sample chunk
+    and 256-sample strip boundaries, every blocks-per-lane and rows-per-CTA variant, against the float64 oracle on the
+    bf16-rounded input (1e-2) and against the register-walk kernel (both round the same fp32 math to bf16: <= 2 bf16 ulps)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4321)
+    taps = TP.make_taps().reshape(-1).numpy().astype(np.float64)
+    for (B, C, T) in TC_EDGE:
+        if logscale:
+            alpha = (torch.randn(C, generator=g) * 0.5)
+            beta = (torch.randn(C, generator=g) * 0.5)
+        else:
+            alpha = (torch.rand(C, generator=g) * 2 + 0.25)
+            beta = (torch.rand(C, generator=g) * 2 + 0.25)
+        beta_ = beta if kind == "snakebeta" else None
+        x = torch.randn(B, C, T, generator=g).to(torch.bfloat16).to(dev)
+        y_ref = O.activation1d_forward(x.float().cpu().numpy(), alpha.numpy(), None if beta_ is None else beta_.numpy(), logscale, taps, taps)
+        a_d, b_d = alpha.to(dev), None if beta_ is None else beta_.to(dev)
+        y_walk = _tc_forward(x, a_d, b_d, logscale, 0)
+        for ny, rlog2 in ((0, -1), (4, 3), (8, 4), (12, 5), (16, 6), (4, 7), (16, 3)):
+            if T < 64 and ny == 0 and rlog2 == -1:
+                continue                                   # the built-in choice keeps such rows on the walk kernel
+            y = _tc_forward(x, a_d, b_d, logscale, 2, ny, rlog2)
+            tag = (B, C, T, ny, rlog2)
+            assert y.dtype == torch.bfloat16 and y.shape == (B, C, T)
+            assert torch.isfinite(y.float()).all(), tag
+            assert O.max_normalised_error(y.float().cpu().numpy(), y_ref) <= TOL_BF16, tag
+            assert (y.float() - y_walk.float()).abs().max().item() <= 4 * 2.0 ** -8 * max(1.0, float(np.abs(y_ref).max())), tag
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 220416), (16, 768, 3440), (16, 384, 13776), (32, 96, 2048), (2, 512, 8192), (16, 24, 220416)])
+def test_tensor_core_forward_model_sizes(shape):
+    """bf16 at the sizes the bench runs (the full-size test was fp32 only): against the torch-op oracle in
+    fp32 on the same device evaluated on the bf16 input, bitwise run-to-run determinism, and the DC identity."""
+    _, _lib, Fn, _, _ = _mods()
+    dev = torch.device("cuda:0")
+    B, C, T = shape
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    alpha = (torch.randn(C, generator=g) * 0.5).to(dev)
+    beta = (torch.randn(C, generator=g) * 0.5).to(dev)
+    x = torch.randn(B, C, T, generator=g).to(torch.bfloat16).to(dev)
+    taps_t = TP.make_taps().to(dev)
+    y = _tc_forward(x, alpha, beta, True, 2)
+    with torch.no_grad():
+        ref = TP.activation1d_torch(x.float(), alpha, beta, True, taps_t, taps_t)
+    err = (y.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= TOL_BF16, err
+    # error statistics, not only the maximum: the mean error must sit at bf16 output-rounding level
+    assert ((y.float() - ref).abs().mean() / ref.abs().mean()).item() <= 4e-3
+    for _ in range(2):
+        assert torch.equal(_tc_forward(x, alpha, beta, True, 2), y)
+    c = torch.linspace(-2, 2, C, device=dev).view(1, C, 1).expand(B, C, T).contiguous().to(torch.bfloat16)
+    yc = _tc_forward(c, alpha, beta, True, 2).float()
+    cf = c.float()
+    expect = cf + torch.sin(torch.exp(alpha).view(1, C, 1) * cf) ** 2 / (torch.exp(beta).view(1, C, 1) + 1e-9)
+    assert ((yc - expect).abs().max() / expect.abs().max()).item() <= TOL_BF16
+
+
+def test_tensor_core_forward_large_arguments_and_degenerate_parameters():
+    """|alpha * x| in the hundreds (x * 10, alpha up to e^1.5), and non-log-scale alpha in {0, -0.5} / beta -> 0
+    (raw parameters are only guarded by + 1e-9)."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    C, T = 8, 4096
+    taps = TP.make_taps().reshape(-1).numpy().astype(np.float64)
+    x = (torch.randn(2, C, T) * 10.0).to(torch.bfloat16).to(dev)
+    alpha = torch.tensor([1.5, 1.0, 0.5, 0.0, -0.5, 1.2, 0.3, -1.0])
+    beta = torch.tensor([0.0, 0.5, -0.5, 1.0, 0.2, -0.3, 1.5, 0.7])
+    y = _tc_forward(x, alpha.to(dev), beta.to(dev), True, 2)
+    ref = O.activation1d_forward(x.float().cpu().numpy(), alpha.numpy(), beta.numpy(), True, taps, taps)
+    assert O.max_normalised_error(y.float().cpu().numpy(), ref) <= TOL_BF16
+    x1 = torch.randn(2, C, T).to(torch.bfloat16).to(dev)
+    alpha = torch.tensor([0.0, -0.5, 1.0, 2.0, 0.5, -2.0, 0.1, 3.0])
+    beta = torch.tensor([1.0, 0.5, 1e-3, 2.0, -0.5, 0.25, 1e-2, 4.0])
+    for b_ in (beta, None):
+        y = _tc_forward(x1, alpha.to(dev), None if b_ is None else b_.to(dev), False, 2)
+        a_np, b_np = alpha.numpy(), None if b_ is None else b_.numpy()
+        ref = O.activation1d_forward(x1.float().cpu().numpy(), a_np, b_np, False, taps, taps)
+        # per channel: beta = 1e-3 scales the sin^2 term by 1000, so normalise each channel by its own maximum
+        yv, rv = y.float().cpu().numpy(), ref
+        for ch in range(C):
+            assert O.max_normalised_error(yv[:, ch], rv[:, ch]) <= TOL_BF16, (ch, b_ is None)
+
+
+def test_tensor_core_forward_graph_capture_guard_band_and_module_dispatch():
+    """CUDA-graph capture (tensor maps travel by value), no write outside y (sentinels), and the module picks the tensor-core
+    kernel by itself for large bf16 tensors (launch is one kernel either way; results within 2 ulps of the walk kernel)."""
+    _, _lib, Fn, _, _ = _mods()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(8)
+    taps = Fn.host_taps(TP.make_taps())
+    B, C, T = 3, 20, 5000 // 8 * 8
+    a = torch.randn(C, device=dev) * 0.5
+    b = torch.randn(C, device=dev) * 0.5
+    x = torch.randn(B, C, T, device=dev).to(torch.bfloat16)
+    n = B * C * T
+    big = torch.full((n + 256,), 12345.0, device=dev, dtype=torch.bfloat16)
+    y = big[128 : 128 + n].view(B, C, T)
+    _lib.set_tuning(5, 2, 0)
+    try:
+        Fn.activation1d_forward_raw(x, a, b, taps, taps, True, out=y)
+        torch.cuda.synchronize()
+        assert torch.all(big[:128] == 12345.0) and torch.all(big[128 + n :] == 12345.0)
+        y0 = y.clone()
+        sx = x.clone()
+        sy = torch.empty_like(x)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            Fn.activation1d_forward_raw(sx, a, b, taps, taps, True, out=sy)
+        sx.copy_(x)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(sy, y0)
+        info = _lib.kernel_info(5, 1, T)
+        assert info["registers"] > 0 and info["ctas_per_sm"] >= 1 and info["threads"] == 320
+    finally:
+        _lib.set_tuning(5, 1, 0)

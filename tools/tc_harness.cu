@@ -1,0 +1,270 @@
+// tc_harness.cu -- stand-alone bring-up / timing harness for the tensor-core Activation1d kernel (csrc/afa_tc_kernels.cuh).
+// Not product code and not a parity test (those live in tests/ and go through the C ABI): it compiles the kernel's
+// translation unit directly, checks the output (and, with --debug 1|2, the U / S blocks dumped from TMEM) against a
+// double-precision loop written from the reference's op definitions, and times L2-cold launches.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I <csrc> tools/tc_harness.cu -o tools/_build/tc_harness
+//   tc_harness B C T [--ny N] [--rlog2 R] [--debug D] [--iters I] [--flags F] [--check-rows N]
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "afa_tc.cu"
+
+namespace afa_internal {
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    return code;
+}
+int cuda_error(cudaError_t e, const char* what) {
+    fprintf(stderr, "%s: %s\n", what, cudaGetErrorString(e));
+    return (int)e;
+}
+void count_launch() {}
+}  // namespace afa_internal
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); exit(2); } } while (0)
+
+static const double kTaps[12] = {0.0020289646927267313, 0.009389465674757957, -0.0255434587597847, -0.057657383382320404,
+                                 0.12857258319854736, 0.44320979714393616, 0.44320979714393616, 0.12857258319854736,
+                                 -0.057657383382320404, -0.0255434587597847, 0.009389465674757957, 0.0020289646927267313};
+
+static float bf16_round(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+    u = r & 0xFFFF0000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static uint16_t bf16_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (uint16_t)(u >> 16);
+}
+static float bf16_to_f(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// one row: u (2T), s (2T), y (T) in double from bf16-exact x
+static void ref_row(const float* x, int T, double a, double ib, std::vector<double>& u, std::vector<double>& s, std::vector<double>& y) {
+    u.assign(2 * T, 0.0);
+    s.assign(2 * T, 0.0);
+    y.assign(T, 0.0);
+    for (int n = 0; n < 2 * T; ++n) {
+        double acc = 0;
+        // u[n] = 2 sum_i f[n + 5 - 2i] x[clamp(i)], i over the padded index range (resample.py:32-36)
+        for (int k = 0; k < 12; ++k) {
+            const int num = n + 5 - k;          // 2i
+            if (num & 1) continue;
+            const int i = num / 2 - 0;           // num may be negative and even
+            const int ii = (num >= 0) ? num / 2 : -((-num) / 2);
+            (void)i;
+            acc += 2.0 * kTaps[k] * (double)x[clampi(ii, 0, T - 1)];
+        }
+        u[n] = acc;
+        const double sn = sin(a * acc);
+        s[n] = acc + ib * sn * sn;
+    }
+    for (int t = 0; t < T; ++t) {
+        double acc = 0;
+        for (int k = 0; k < 12; ++k) acc += kTaps[k] * s[clampi(2 * t + k - 5, 0, 2 * T - 1)];
+        y[t] = acc;
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) {
+        fprintf(stderr, "usage: tc_harness B C T [--ny N] [--rlog2 R] [--debug D] [--iters I] [--flags F] [--check-rows N]\n");
+        return 1;
+    }
+    const int B = atoi(argv[1]), C = atoi(argv[2]), T = atoi(argv[3]);
+    int ny = 0, rlog2 = -1, debug = 0, iters = 0, flags = 1, check_rows = 64;
+    for (int i = 4; i + 1 < argc; i += 2) {
+        if (!strcmp(argv[i], "--ny")) ny = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--rlog2")) rlog2 = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--debug")) debug = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--flags")) flags = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--check-rows")) check_rows = atoi(argv[i + 1]);
+    }
+    afa_internal::tc_set_tuning(2, ny, rlog2);
+    const int64_t rows = (int64_t)B * C, N = rows * T;
+    int prl, pny;
+    int64_t rg, ts;
+    afa_internal::tc_plan(rows, T, &prl, &pny, &rg, &ts);
+    printf("shape B=%d C=%d T=%d rows=%lld | plan R=%d G=%d NY=%d ctas=%lld x %lld = %lld\n", B, C, T, (long long)rows, 1 << prl,
+           128 >> prl, pny, (long long)rg, (long long)ts, (long long)(rg * ts));
+    { int32_t info[6]; if (!afa_internal::tc_kernel_info(info)) printf("kernel: %d registers, %d B smem, %d threads, occupancy API: %d CTAs/SM\n", info[0], info[1], info[2], info[4]); }
+    if (!afa_internal::tc_eligible((void*)16, (void*)16, B, C, T, AFA_DTYPE_BF16)) {
+        printf("not eligible for the tensor-core path\n");
+        return 1;
+    }
+
+    std::vector<uint16_t> hx(N);
+    std::vector<float> hxf(N), halpha(C), hbeta(C);
+    uint64_t seed = 1234;
+    auto rnd = [&]() {  // uniform (0,1)
+        seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+        return ((seed >> 11) + 0.5) / 9007199254740992.0;
+    };
+    auto gauss = [&]() { return sqrt(-2.0 * log(rnd())) * cos(6.283185307179586 * rnd()); };
+    for (int64_t i = 0; i < N; ++i) {
+        const float v = bf16_round((float)gauss());
+        hxf[i] = v;
+        hx[i] = bf16_bits(v);
+    }
+    for (int c = 0; c < C; ++c) {
+        halpha[c] = (float)(0.5 * gauss());
+        hbeta[c] = (float)(0.5 * gauss());
+    }
+    float tu[12], td[12];
+    for (int i = 0; i < 12; ++i) tu[i] = td[i] = (float)kTaps[i];
+
+    // enough buffer sets to exceed the 126 MB L2 between reuses
+    const size_t bytes = (size_t)N * 2;
+    int nsets = iters > 0 ? (int)std::max<size_t>(2, (size_t)(400ull << 20) / (2 * bytes) + 1) : 1;
+    if (nsets > 64) nsets = 64;
+    std::vector<void*> dx(nsets), dy(nsets);
+    for (int s = 0; s < nsets; ++s) {
+        CK(cudaMalloc(&dx[s], bytes));
+        CK(cudaMalloc(&dy[s], bytes));
+        CK(cudaMemcpy(dx[s], hx.data(), bytes, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dy[s], 0xFF, bytes));
+    }
+    float *dalpha, *dbeta, *ddbg = nullptr;
+    CK(cudaMalloc(&dalpha, C * 4));
+    CK(cudaMalloc(&dbeta, C * 4));
+    CK(cudaMemcpy(dalpha, halpha.data(), C * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbeta, hbeta.data(), C * 4, cudaMemcpyHostToDevice));
+    const size_t dbg_per_cta = (size_t)128 * (afa_tc::kNYMax + 1) * 32;
+    if (debug) {
+        CK(cudaMalloc(&ddbg, (size_t)(rg * ts) * dbg_per_cta * 4));
+        CK(cudaMemset(ddbg, 0, (size_t)(rg * ts) * dbg_per_cta * 4));
+    }
+
+    if (debug >= 3) {   // warm the instruction cache / tensor maps first, then stamp a CTA in the middle of the grid
+        afa_internal::tc_fwd_launch(dx[0], dy[0], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
+        CK(cudaDeviceSynchronize());
+    }
+    int rc = afa_internal::tc_fwd_launch(dx[0], dy[0], dalpha, dbeta, tu, td, B, C, T, flags, 0, debug, ddbg);
+    if (rc) { printf("launch failed rc=%d\n", rc); return 2; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("KERNEL FAILED: %s\n", cudaGetErrorString(e)); return 3; }
+
+    std::vector<uint16_t> hy(N);
+    CK(cudaMemcpy(hy.data(), dy[0], bytes, cudaMemcpyDeviceToHost));
+    std::vector<float> hdbg;
+    if (debug) {
+        hdbg.resize((size_t)(rg * ts) * dbg_per_cta);
+        CK(cudaMemcpy(hdbg.data(), ddbg, hdbg.size() * 4, cudaMemcpyDeviceToHost));
+    }
+
+    if (debug >= 3) {
+        const uint32_t* st = reinterpret_cast<const uint32_t*>(hdbg.data());
+        uint32_t t0 = 0xffffffffu;
+        for (int i = 0; i < 3 * 32 * 8; ++i) if ((i / 8) % 32 < 30 && st[i] && st[i] < t0) t0 = st[i];
+        printf("first loop stamp at %d cycles after kernel entry\n", (int)(t0 - st[31 * 8]));
+        printf("timeline of CTA %lld (cycles since first stamp); MMA: wait-start, woke, issued | group g: wait-up, woke, U loaded, snake done, arrived, dn woke\n", (long long)(rg * ts / 2));
+        for (int j = 0; j <= pny + 1; ++j) {
+            printf("j=%2d MMA %6d %6d %6d (batch done %6d) | g%d %6d %6d %6d %6d %6d %6d\n", j, st[(0 * 32 + j) * 8 + 0] ? (int)(st[(0 * 32 + j) * 8 + 0] - t0) : -1,
+                   st[(0 * 32 + j) * 8 + 1] ? (int)(st[(0 * 32 + j) * 8 + 1] - t0) : -1, st[(0 * 32 + j) * 8 + 2] ? (int)(st[(0 * 32 + j) * 8 + 2] - t0) : -1, st[(0 * 32 + j) * 8 + 3] ? (int)(st[(0 * 32 + j) * 8 + 3] - t0) : -1, j & 1,
+                   st[((1 + (j & 1)) * 32 + j) * 8 + 0] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 0] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 1] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 1] - t0) : -1,
+                   st[((1 + (j & 1)) * 32 + j) * 8 + 2] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 2] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 3] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 3] - t0) : -1,
+                   st[((1 + (j & 1)) * 32 + j) * 8 + 4] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 4] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 5] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 5] - t0) : -1);
+        }
+        { uint32_t e0 = st[(0 * 32 + 31) * 8 + 0]; t0 = e0;
+          printf("setup: TMA issued / alloc start %d, alloc done %d, B-gen start %d, B-gen done %d\n", (int)(st[30 * 8 + 0] - t0), (int)(st[30 * 8 + 1] - t0), (int)(st[30 * 8 + 2] - t0), (int)(st[30 * 8 + 3] - t0));
+          printf("lifetime: entry 0, setup done %d, loop done (MMA warp) %d, final sync %d, stores read %d\n", (int)(st[(31) * 8 + 1] - t0), (int)(st[(31) * 8 + 2] - t0), (int)(st[(31) * 8 + 3] - t0), (int)(st[(31) * 8 + 4] - t0)); }
+    }
+    // ---- check: a spread of rows (all if few)
+    std::vector<int64_t> rows_to_check;
+    if (rows <= check_rows) for (int64_t r = 0; r < rows; ++r) rows_to_check.push_back(r);
+    else for (int i = 0; i < check_rows; ++i) rows_to_check.push_back((int64_t)((double)i * (rows - 1) / (check_rows - 1)));
+    double max_ref = 0, max_err = 0, max_dbg_err = 0, max_dbg_ref = 0;
+    int64_t bad_r = -1, bad_t = -1, dbad_r = -1, dbad_n = -1;
+    int printed = 0;
+    const int R = 1 << prl, G = 128 >> prl, span = 16 * pny;
+    std::vector<double> u, s, y;
+    for (int64_t r : rows_to_check) {
+        const int c = (int)(r % C);
+        double al = halpha[c], be = (flags & 2) ? halpha[c] : hbeta[c];
+        if (flags & 1) { al = (double)expf((float)al); be = (double)expf((float)be); }
+        const double ib = (double)(1.0f / ((float)be + 0.000000001f));
+        ref_row(&hxf[r * T], T, al, ib, u, s, y);
+        for (int t = 0; t < T; ++t) {
+            const double got = bf16_to_f(hy[r * T + t]);
+            const double err = fabs(got - y[t]);
+            max_ref = std::max(max_ref, fabs(y[t]));
+            if (!(err <= max_err)) { max_err = err; bad_r = r; bad_t = t; }
+            if (!(err < 0.05 * std::max(1.0, fabs(y[t]))) && printed < 12) {
+                printf("  mismatch row %lld t %d: got %g ref %g\n", (long long)r, t, got, y[t]);
+                ++printed;
+            }
+        }
+        if (debug == 1 || debug == 2) {
+            // element (block j, e) of lane l of CTA (rgroup, tstrip) holds n = 2 t_org + 32 j + 6 + e
+            const int64_t rgp = r / R;
+            const int rr = (int)(r % R);
+            for (int64_t tsx = 0; tsx < ts; ++tsx)
+                for (int g = 0; g < G; ++g) {
+                    const int l = g * R + rr;
+                    const int t_org = (int)(tsx * G * span + g * span - 8);
+                    const float* d = &hdbg[((size_t)(rgp * ts + tsx) * 128 + l) * (size_t)((afa_tc::kNYMax + 1) * 32)];
+                    for (int j = 0; j <= pny; ++j)
+                        for (int el = 0; el < 32; ++el) {
+                            const int n = 2 * t_org + 32 * j + 6 + el;
+                            double ref;
+                            if (debug == 1) {
+                                if (n < 0 || n >= 2 * T) continue;      // u outside the row is don't-care
+                                ref = u[n];
+                            } else {
+                                if (n < -5 || n > 2 * T + 4) continue;
+                                ref = s[clampi(n, 0, 2 * T - 1)];
+                            }
+                            const double err = fabs((double)d[j * 32 + el] - ref);
+                            max_dbg_ref = std::max(max_dbg_ref, fabs(ref));
+                            if (!(err <= max_dbg_err)) { max_dbg_err = err; dbad_r = r; dbad_n = n; }
+                        }
+                }
+        }
+    }
+    printf("checked %zu rows: E(y) = %.3e (max |err| %.4g at row %lld t %lld, max |ref| %.4g)\n", rows_to_check.size(),
+           max_err / std::max(max_ref, 1e-30), max_err, (long long)bad_r, (long long)bad_t, max_ref);
+    if (debug == 1 || debug == 2)
+        printf("debug %d (%s): E = %.3e (max |err| %.4g at row %lld n %lld, max |ref| %.4g)\n", debug, debug == 1 ? "U" : "S",
+               max_dbg_err / std::max(max_dbg_ref, 1e-30), max_dbg_err, (long long)dbad_r, (long long)dbad_n, max_dbg_ref);
+    const bool ok = max_err / std::max(max_ref, 1e-30) <= 1e-2;
+    printf(ok ? "PARITY OK\n" : "PARITY FAIL\n");
+
+    if (iters > 0) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; ++i)
+            afa_internal::tc_fwd_launch(dx[i % nsets], dy[i % nsets], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; ++i)
+            afa_internal::tc_fwd_launch(dx[i % nsets], dy[i % nsets], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double us = ms * 1000.0 / iters;
+        printf("TIMING B=%d C=%d T=%d R=%d NY=%d: %.2f us/launch, %.1f GB/s algorithmic (4 B/elem), %d buffer sets\n", B, C, T, R, pny,
+               us, (double)N * 4.0 / (us * 1e-6) / 1e9, nsets);
+    }
+    return ok ? 0 : 4;
+}
