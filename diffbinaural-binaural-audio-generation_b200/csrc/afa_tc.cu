@@ -80,7 +80,16 @@ bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, 
     if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return false;
     const int64_t rows = batch * channels;
     if (rows < 8 || rows >= (1ll << 30)) return false;
-    if (g_tc_enable == 1 && rows * T < (1ll << 20)) return false;   // tiny launches: fewer, simpler CTAs win
+    if (g_tc_enable == 1) {
+        // Built-in choice, fitted to same-box sweeps against the register-walk kernel (profiles/r02_tc_sweep.log): the walk
+        // kernel loses on short and medium rows (every row end costs an edge-mode warp; 2.2-2.8 TB/s at T <= 27552) where this
+        // kernel does not care about row length (2.6-3.0 TB/s), and wins by 3-15 % on very long rows and on single-clip
+        // launches that fill 1-2 waves of this kernel's 128-lane CTAs.
+        const int64_t n = rows * T;
+        const bool many_short_rows = T < 32768 && n >= (16ll << 20);
+        const bool train_like = rows >= 1024 && T <= 16384 && n >= (3ll << 20);
+        if (!many_short_rows && !train_like) return false;
+    }
     return encode_fn() != nullptr;
 }
 

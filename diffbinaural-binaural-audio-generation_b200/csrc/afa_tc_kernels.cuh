@@ -53,14 +53,15 @@ constexpr int kThreads = 320;            // warp 0: TMA producer / TMEM allocato
 constexpr int kNYMax = 16;               // y blocks (16 outputs) per lane, multiple of 4
 constexpr int kChunkBytes = 128 * 128;   // 128 lanes x 64 bf16
 constexpr int kNChunkMax = (kNYMax + 2 + 3) / 4;
-constexpr int kTmemCols = 256;           // 192 used; allocations are powers of two
-constexpr int kColUS = 0;                // U / S ring: 4 slots x 32 columns (U fp32; S = 32 bf16 in the first 16)
-constexpr int kColY = 128;               // Y ring: 4 slots x 16 columns
+constexpr int kTmemCols = 256;           // 240 used; allocations are powers of two
+constexpr int kRing = 5;                 // slots of the U / S and Y rings
+constexpr int kColUS = 0;                // U / S ring: 5 slots x 32 columns (U fp32; S = 32 bf16 in the first 16)
+constexpr int kColY = 160;               // Y ring: 5 slots x 16 columns
 // shared memory carve-up (offsets from a 1024-byte aligned base)
 constexpr int kOffWup = kNChunkMax * kChunkBytes;        // [hi/lo][slice a/b] x (32 x 16 bf16 = 1024 B)
 constexpr int kOffWdn = kOffWup + 4 * 1024;              // [hi/lo][slice a/b/c] x (16 x 16 bf16 = 512 B)
 constexpr int kOffBar = kOffWdn + 6 * 512;
-constexpr int kBarFull = 0, kBarPre = kNChunkMax, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 4, kBarOut = kBarEv + 4;
+constexpr int kBarFull = 0, kBarPre = kNChunkMax, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 8, kBarOut = kBarEv + 8;
 constexpr int kNumBars = kBarOut + kNYMax / 4;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;         // + slack for the manual 1024-byte alignment
@@ -201,21 +202,20 @@ __device__ __forceinline__ float snake_f(float u, float a, float ib) {
 }
 
 // Schedule.  Block j = 16 time steps of the CTA's 128 lanes.  Compute group g (4 warps) owns the blocks j = g (mod 2).
-//   MMA thread, event j:        wait cmp[j & 3] (S(j) is in TMEM);  down(j-1) [S(j-1), S(j) from TMEM -> Y slot (j-1) & 3];
-//                               up(j+3) [x slices j+3, j+4 straight from the swizzled shared-memory chunks -> U slot (j+3) & 3];
-//                               ONE commit -> ev[(j+3) & 3]  (tcgen05.commit tracks every MMA issued before it)
-//   iteration j of its group:   wait ev[j & 3]  (event j-3 committed: up(j) and down(j-4) are complete)
-//                               drain Y(j-4) -> bf16 -> shared memory (out chunk (j-4)/4, over x slice j-4), arrive out[(j-4)/4]
-//                               U(j) -> registers -> Snake -> S(j) over U(j) -> arrive cmp[j & 3]
+//   MMA thread, event j:        wait cmp[j & 7] (S(j) is in TMEM);  down(j-1) [S(j-1), S(j) from TMEM -> Y slot (j-1) % 5];
+//                               up(j+4) [x slices j+4, j+5 straight from the swizzled shared-memory chunks -> U slot (j+4) % 5];
+//                               ONE commit -> ev[(j+4) & 7]  (tcgen05.commit tracks every MMA issued before it)
+//   iteration j of its group:   wait ev[j & 7]  (event j-4 committed: up(j) and down(j-5) are complete)
+//                               drain Y(j-5) -> bf16 -> shared memory (out chunk (j-5)/4, over x slice j-5), arrive out[(j-5)/4]
+//                               U(j) -> registers -> Snake -> S(j) over U(j) -> arrive cmp[j & 7]
 //   warp 0:                     wait out[q] (16 warp arrivals) -> TMA store of out chunk q
-// Ring safety: up(j+3) lands on U/S slot (j-1) & 3 = S(j-1), last read by down(j-1), issued immediately before it (MMAs of one
-// thread execute in issue order).  down(i) lands on Y(i-4), drained at iteration i before that iteration's arrive on cmp[i & 3],
+// The lookahead of 4 blocks is what hides the MMA round trip (arrive -> issue -> execute -> commit -> wake, about one block
+// time): with 3 both sides were found waiting on each other (profiles/r02_tc_ncu_full_fwd_bf16_B16_C384_T13776.txt).
+// Ring safety: up(j+4) lands on U/S slot (j-1) % 5 = S(j-1), last read by down(j-1), issued immediately before it (MMAs of one
+// thread execute in issue order).  down(i) lands on Y(i-5), drained at iteration i before that iteration's arrive on cmp[i & 7],
 // which the MMA thread has consumed before event i+1.  y block i overwrites x slice i, last read by up(i), complete since event
-// i-3.  cmp / ev are indexed by j & 3 because a warp may run ahead of its group-mates by one iteration (its ev wait depends on
-// event j-3 only): on a per-group barrier that early arrival would complete the older phase.
-// 10 warps per CTA put 3 warps of each CTA on two of the four SM sub-partitions; two resident CTAs are 6 warps there, and a
-// sub-partition's 16384 registers allow 6 x 32 x 80 (allocation granularity 8 registers per thread) -- not the 102 a plain
-// __launch_bounds__(320, 2) would let ptxas use; bounds of (384, 2) make ptxas stay within 65536 / 768 -> 80.
+// i-4.  cmp / ev are rings of 8 indexed by the block, not per group: a warp's ev wait depends on event j-4 only, so it may run
+// iterations ahead of a slower warp of its group; it cannot be 8 blocks ahead, because event j+4 needs cmp[j] complete.
 #ifndef AFA_TC_BOUND_THREADS
 #define AFA_TC_BOUND_THREADS 384
 #endif
@@ -251,8 +251,8 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                 bars + 8 * (kBarFull + p));
             }
             mbar_init(bars + 8 * kBarPre, 8);
-            for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * (kBarCmp + i), 4);
-            for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * (kBarEv + i), 1);
+            for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarCmp + i), 4);
+            for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEv + i), 1);
             for (int i = 0; i < kNYMax / 4; ++i) mbar_init(bars + 8 * (kBarOut + i), 16);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
@@ -345,31 +345,36 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // chunks themselves are awaited here, in the order the up-filter products need them
         mbar_wait(bars + 8 * kBarPre, 0);
         mbar_wait(bars + 8 * (kBarFull + 0), 0);
-        if (NCH_IN > 1) mbar_wait(bars + 8 * (kBarFull + 1), 0);        // up(2), up(3) read slice 4
+        mbar_wait(bars + 8 * (kBarFull + 1), 0);                        // up(3) reads slice 4 (NY >= 4: two chunks at least)
         int nfull = 2;
         tc_fence_after();
-        if (elect_one()) {                                   // events -3, -2, -1
+        if (elect_one()) {                                   // events -4 .. -1
             up(tmem + kColUS + 0, xdesc(0), xdesc(1)); tc_commit(bars + 8 * (kBarEv + 0));
             up(tmem + kColUS + 32, xdesc(1), xdesc(2)); tc_commit(bars + 8 * (kBarEv + 1));
             up(tmem + kColUS + 64, xdesc(2), xdesc(3)); tc_commit(bars + 8 * (kBarEv + 2));
+            up(tmem + kColUS + 96, xdesc(3), xdesc(4)); tc_commit(bars + 8 * (kBarEv + 3));
         }
         __syncwarp();
+        int sl_dn = kRing - 1, sl_s2 = 0, sl_up = 4;       // ring slots of blocks j-1, j, j+4
         for (int j = 0; j <= NY; ++j) {
             AFA_TC_STAMP(0, j, 0);
-            if (j + 3 <= NY) {
-                const int p = (j + 4) >> 2;                  // chunk of slice j+4
+            if (j + 4 <= NY) {
+                const int p = (j + 5) >> 2;                  // chunk of slice j+5
                 while (nfull <= p) { mbar_wait(bars + 8 * (kBarFull + nfull), 0); ++nfull; }
             }
-            mbar_wait(bars + 8 * (kBarCmp + (j & 3)), (uint32_t)(j >> 2) & 1u);
+            mbar_wait(bars + 8 * (kBarCmp + (j & 7)), (uint32_t)(j >> 3) & 1u);
             tc_fence_after();
             AFA_TC_STAMP(0, j, 1);
             // addresses of this event, computed by the whole warp (uniform) before the single-thread issue
-            const int i = j - 1, ju = j + 3;
-            const uint32_t dd = tmem + kColY + 16 * (i & 3);
-            const uint32_t s0 = tmem + kColUS + 32 * (i & 3), s2 = tmem + kColUS + 32 * (j & 3);
-            const uint32_t du = tmem + kColUS + 32 * (ju & 3);
+            const int ju = j + 4;
+            const uint32_t dd = tmem + kColY + 16 * sl_dn;
+            const uint32_t s0 = tmem + kColUS + 32 * sl_dn, s2 = tmem + kColUS + 32 * sl_s2;
+            const uint32_t du = tmem + kColUS + 32 * sl_up;
             const uint64_t xa = xdesc(ju), xb = xdesc(ju + 1);
-            const uint32_t evb = bars + 8 * (kBarEv + (ju & 3));
+            const uint32_t evb = bars + 8 * (kBarEv + (ju & 7));
+            sl_dn = sl_s2;
+            sl_s2 = sl_s2 + 1 == kRing ? 0 : sl_s2 + 1;
+            sl_up = sl_up + 1 == kRing ? 0 : sl_up + 1;
             const bool do_dn = j >= 1, do_up = ju <= NY;
             if (elect_one()) {
                 if (do_dn) down(dd, s0, s2);
@@ -428,16 +433,17 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (lane == 0) mbar_arrive(bars + 8 * kBarPre);
 
         const float2 a2 = make_float2(a_eff, a_eff), ib2 = make_float2(ib, ib);
-        for (int j = grp; j <= NY + 3; j += 2) {
+        int slot = grp;                                          // ring slot of block j (and of block j-5): j mod 5
+        for (int j = grp; j <= NY + 4; j += 2, slot = slot + 2 >= kRing ? slot + 2 - kRing : slot + 2) {
             if (q == 2) AFA_TC_STAMP(1 + grp, j, 0);
-            mbar_wait(bars + 8 * (kBarEv + (j & 3)), (uint32_t)(j >> 2) & 1u);
+            mbar_wait(bars + 8 * (kBarEv + (j & 7)), (uint32_t)(j >> 3) & 1u);
             tc_fence_after();
             if (q == 2) AFA_TC_STAMP(1 + grp, j, 1);
-            if (j >= 4) {
-                // drain Y(j-4): fp32 accumulators -> bf16 -> the lane's row of out chunk (j-4)/4 (in place over x slice j-4)
-                const int i = j - 4;
+            if (j >= 5) {
+                // drain Y(j-5): fp32 accumulators -> bf16 -> the lane's row of out chunk (j-5)/4 (in place over x slice j-5)
+                const int i = j - 5;
                 uint32_t yv[16];
-                tmem_ld16(tlane + kColY + 16 * (i & 3), yv);
+                tmem_ld16(tlane + kColY + 16 * slot, yv);
                 tmem_wait_ld();
                 uint32_t pk[8];
 #pragma unroll
@@ -453,7 +459,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (q == 2) AFA_TC_STAMP(1 + grp, j, 2);
             if (j <= NY) {
                 uint32_t u[32];
-                tmem_ld32(tlane + kColUS + 32 * (j & 3), u);
+                tmem_ld32(tlane + kColUS + 32 * slot, u);
                 tmem_wait_ld();
                 if (a.debug == 1 && row < a.rows) {
                     float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)((kNYMax + 1) * 32) + j * 32;
@@ -497,11 +503,11 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     }
                 }
                 if (q == 2) AFA_TC_STAMP(1 + grp, j, 3);
-                tmem_st16(tlane + kColUS + 32 * (j & 3), sp);
+                tmem_st16(tlane + kColUS + 32 * slot, sp);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (kBarCmp + (j & 3)));
+                if (lane == 0) mbar_arrive(bars + 8 * (kBarCmp + (j & 7)));
                 if (q == 2) AFA_TC_STAMP(1 + grp, j, 4);
             }
         }
