@@ -112,6 +112,7 @@ class _Activation1dFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x, a32, b32 = ctx.saved_tensors
         beta = b32 if ctx.has_beta else None

@@ -262,6 +262,7 @@ class _LogMelFn(torch.autograd.Function):
         return logmel_forward_raw(wav, plan, hop, pad, pad_mode, mag_eps, clamp_eps, log_scale, raw)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         (wav,) = ctx.saved_tensors
         return (logmel_backward_raw(wav, gout, *ctx.cfg),) + (None,) * 8
@@ -299,13 +300,17 @@ def mel_spectrogram(y: torch.Tensor, n_fft: int, num_mels: int, sampling_rate: i
             print(f"[WARNING] Min value of input waveform signal is {lo}")
         if hi > 1.0:
             print(f"[WARNING] Max value of input waveform signal is {hi}")
-    key = f"{n_fft}_{num_mels}_{sampling_rate}_{hop_size}_{win_size}_{fmin}_{fmax}_{y.device}" if mel_basis is None else None
-    plan = mel_plan_cache.get(key) if key else None
+    key = f"{n_fft}_{num_mels}_{sampling_rate}_{hop_size}_{win_size}_{fmin}_{fmax}_{y.device}"
+    if mel_basis is not None:
+        # a caller-supplied basis (a checkpointed one, librosa's): cached by identity, so the plan (banded tables, host-to-device
+        # copies) is not rebuilt on every call; the basis object is kept alive by the cache entry
+        key += f"_basis{id(mel_basis)}"
+    entry = mel_plan_cache.get(key)
+    plan = entry[0] if entry is not None and entry[1] is mel_basis else None
     if plan is None:
         basis = slaney_mel_filterbank(sampling_rate, n_fft, num_mels, fmin, fmax) if mel_basis is None else mel_basis
         plan = MelPlan(n_fft, torch.hann_window(win_size, dtype=torch.float64), basis, y.device)
-        if key:
-            mel_plan_cache[key] = plan
+        mel_plan_cache[key] = (plan, mel_basis)
     pad = (n_fft - hop_size) // 2
     if y.dim() == 1:
         return logmel(y.unsqueeze(0), plan, hop_size, pad, AFA_MEL_PAD_ZERO)[0]
@@ -341,12 +346,14 @@ class _MultiScaleL1Fn(torch.autograd.Function):
             saved += [lx, ly]
         ctx.module, ctx.coefs, ctx.shape = module, coefs, (B, C, T)
         ctx.save_for_backward(x2, y2, *saved)
-        key = (str(x.device), B * C, T)
+        # the weights are part of the key: forward must scale with the same coefficients backward reads from ctx.coefs
+        key = (str(x.device), B * C, T, float(module.log_weight), float(module.mag_weight), float(module.clamp_eps))
         if key not in module._coefs:                            # built once per shape: no host-to-device copy in the step (graph capture)
             module._coefs[key] = torch.tensor(coefs, device=x.device, dtype=torch.float32)
         return (partials.sum(dim=1) * module._coefs[key]).sum()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gloss):
         x2, y2, *saved = ctx.saved_tensors
         module, (B, C, T) = ctx.module, ctx.shape

@@ -331,9 +331,14 @@ int afa_activation1d_fwd(const void* x, void* y, const float* alpha, const float
 }
 
 size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int dtype) {
+    // An upper bound over every kernel variant the call may select: the query sees no pointers, and a misaligned base
+    // pointer or a forced segment size moves the launch to a variant with shorter segments (more partial sums).  The
+    // shortest compiled segment is 5 chunks of 16 bytes.
     Plan pl;
     if (make_plan(1, nullptr, nullptr, nullptr, batch, channels, T, dtype, &pl)) return 0;
-    return (size_t)pl.total_segs * 2 * sizeof(float) + 16;
+    const int64_t lmin = 5 * pl.vec;
+    const int64_t nseg = T > 0 ? (T + lmin - 1) / lmin : 0;
+    return (size_t)(batch * channels * nseg) * 2 * sizeof(float) + 16;
 }
 
 int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha, float* gbeta, const float* alpha,

@@ -128,6 +128,8 @@ struct TailSink {
     float* wave;      // row of this batch entry (lane 0 stores)
     int16_t* pcm;
     const int32_t* fmap;   // this batch entry's frame map, or nullptr
+    int64_t t_out;         // samples per output row: a frame index outside [0, t_out / hop) drops its samples (the reference
+                           // clamps every copy to the original length, inference_e2e.py:94-109)
     int hop;
     int il;
     float pcm_scale;
@@ -318,12 +320,15 @@ __device__ __forceinline__ void walk_cl(const T* __restrict__ px, const T* __res
                 v += sink->bias;
                 v = sink->use_tanh ? tanhf(v) : fminf(fmaxf(v, -1.0f), 1.0f);     // bigvgan.py:382-385
                 int64_t pos = to;
+                bool inside = true;
                 if (sink->fmap) {
                     const int f = to / sink->hop;
-                    pos = (int64_t)__ldg(sink->fmap + f) * sink->hop + (to - f * sink->hop);
+                    const int64_t fm = __ldg(sink->fmap + f);
+                    pos = fm * sink->hop + (to - f * sink->hop);
+                    inside = fm >= 0 && pos < sink->t_out;
                 }
-                if (sink->wave) sink->wave[pos] = v;
-                if (sink->pcm) sink->pcm[pos * sink->il] = (int16_t)(v * sink->pcm_scale);   // astype("int16") truncates
+                if (inside && sink->wave) sink->wave[pos] = v;
+                if (inside && sink->pcm) sink->pcm[pos * sink->il] = (int16_t)(v * sink->pcm_scale);   // astype("int16") truncates
             }
         }
     };
@@ -425,6 +430,7 @@ __global__ void __launch_bounds__(kClThreads, 4) afa_cl_tail_kernel(const __grid
     sink.il = args.il;
     sink.pcm = args.pcm ? args.pcm + ((int64_t)(b / (uint32_t)args.il) * args.T_out) * args.il + (b % (uint32_t)args.il) : nullptr;
     sink.fmap = args.frame_map ? args.frame_map + (int64_t)b * args.n_frames : nullptr;
+    sink.t_out = args.T_out;
     sink.hop = args.hop;
     sink.pcm_scale = args.pcm_scale;
     sink.use_tanh = args.use_tanh;

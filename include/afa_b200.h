@@ -136,7 +136,9 @@ int afa_resblock_mean(const void *const *xt, const void *const *xres, int num_ke
  * Zero-frame restoration (BigVGAN/inference_e2e.py:38-111, reconstruct_audio_with_silence): with frame_map
  * (int32 [batch][T / hop], device) sample t of batch entry b is written at frame_map[b][t / hop] * hop + t % hop
  * of an output row of T_out samples (wave [batch][T_out], pcm [batch / il][T_out][il]); the caller zero-fills the
- * outputs first (the silence).  frame_map = NULL: identity, T_out = T (or 0).
+ * outputs first (the silence).  frame_map values must lie in [0, T_out / hop); a sample whose frame index is negative or whose
+ * position falls at or beyond T_out is dropped (the reference clamps every copy to the original length,
+ * inference_e2e.py:94-109).  frame_map = NULL: identity, T_out = T (or 0).
  */
 int afa_tail_fwd_cl(const void *x, int64_t x_bstride,
                     const float *alpha, const float *beta,

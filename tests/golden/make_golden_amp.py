@@ -18,6 +18,7 @@ import json
 import os
 import sys
 import types
+import zlib
 
 import numpy as np
 
@@ -82,6 +83,7 @@ def main():
         ("amp1_k11_snake", bigvgan.AMPBlock1, 3, 64, 11, (1, 3, 5), "snake"),
         ("amp2_k3", bigvgan.AMPBlock2, 5, 40, 3, (1, 3), "snakebeta"),
     ):
+        torch.manual_seed(zlib.crc32(name.encode()))     # the block's initial weights come from the global RNG: seed it per case
         blk = cls(h, C, k, dil, activation=act)
         blk.remove_weight_norm()
         randomise_snake(blk, g, torch)
@@ -152,6 +154,27 @@ def main():
         out[f"{name}/meta"] = np.array([int(resblock)], dtype=np.int64)
         for n, p in gen.state_dict().items():
             out[f"{name}/sd/{n}"] = p.numpy()
+
+    # ---- whole generator with the SHIPPED stage plan (six stages, rates 4,4,2,2,2,2, AMPBlock1 x 3 kernels), narrowed to
+    #      upsample_initial_channel = 192 (channels 96 ... 3) and T_mel = 16.  Weights: tests/golden/synth_weights.py
+    #      (derived from name + shape on both sides), so only the reference's outputs are stored.     bigvgan.py:244-387
+    from synth_weights import synth_state_dict
+
+    hh = AttrDict(dict(h))
+    hh.update(upsample_initial_channel=192)
+    torch.manual_seed(13)
+    gen = bigvgan.BigVGAN(hh)
+    gen.remove_weight_norm()
+    sd = gen.state_dict()
+    new = synth_state_dict({k: tuple(v.shape) for k, v in sd.items()})
+    gen.load_state_dict({k: torch.tensor(new[k]) if k in new else v for k, v in sd.items()})
+    mel = torch.rand(2, 80, 16, generator=g) * 14.5 - 12.0
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        with torch.no_grad():
+            out[f"gen_model_192/y_{tag}"] = gen.to(dt)(mel.to(dt)).numpy()
+    out["gen_model_192/mel"] = mel.numpy()
+    out["gen_model_192/meta"] = np.array([192, 16, len(sd)], dtype=np.int64)
+    out["gen_model_192/param_checksum"] = np.array([float(sum(np.abs(v).sum() for v in new.values()))])
 
     # ---- zero-frame handling of the inference script                                     inference_e2e.py:38-111
     spec = importlib.util.spec_from_file_location("ref_inference_e2e", os.path.join(BIG, "inference_e2e.py"))

@@ -490,3 +490,93 @@ def test_act_conv_addend_and_mean_without_residual():
         m_ref = A.resblock_mean([outs[0].double().cpu().numpy(), x.double().cpu().numpy()], [None, r.double().cpu().numpy()],
                                 bias.double().cpu().numpy(), 0.5)
         assert O.max_normalised_error(m.double().cpu().numpy(), m_ref) <= 4e-3
+
+
+def test_tail_frame_map_out_of_range_is_dropped_not_written():
+    """a frame index that is negative or points at / behind T_out must not become an out-of-bounds store.
+    Such hops are dropped (the reference clamps every copy to the original length, inference_e2e.py:94-109); the sentinels
+    around wave and pcm survive and the in-range frames are what an unmapped call produces."""
+    torch.manual_seed(31)
+    B, C, hop, frames = 2, 24, 8, 12
+    T = hop * frames
+    t_out = T                # the C ABI requires T_out >= T; frame indices >= frames are the out-of-range ones
+    x = torch.randn(B, T, C, device=DEV)
+    a = torch.randn(C, device=DEV) * 0.3
+    b = torch.randn(C, device=DEV) * 0.3
+    w = torch.randn(C, 7, device=DEV) * 0.1
+    F_afa, FC = _fc()
+    tu = td = F_afa.host_taps(TP.make_taps())
+    fmap = torch.arange(frames, dtype=torch.int32, device=DEV).repeat(B, 1).contiguous()
+    fmap[0, 3] = -1          # negative
+    fmap[0, 7] = frames      # == T_out / hop: first frame behind the row
+    fmap[1, 2] = 1 << 20     # far outside
+    guard = 64
+    wbuf = torch.full((B * t_out + 2 * guard,), 7.0, device=DEV)
+    pbuf = torch.full((B * t_out + 2 * guard,), 77, dtype=torch.int16, device=DEV)
+    wave = wbuf[guard : guard + B * t_out].view(B, t_out)
+    pcm = pbuf[guard : guard + B * t_out].view(B, t_out, 1)
+    wave.zero_()
+    pcm.zero_()
+    FC.tail_cl(x, T, a, b, tu, td, True, w, None, want_wave=True, want_pcm=True, pcm_interleave=1, wave=wave, pcm=pcm,
+               frame_map=fmap, hop=hop, t_out=t_out)
+    torch.cuda.synchronize()
+    assert torch.all(wbuf[:guard] == 7.0) and torch.all(wbuf[guard + B * t_out :] == 7.0)
+    assert torch.all(pbuf[:guard] == 77) and torch.all(pbuf[guard + B * t_out :] == 77)
+    ref, _ = FC.tail_cl(x, T, a, b, tu, td, True, w, None, want_wave=True, want_pcm=False)
+    for bi in range(B):
+        for f in range(frames):
+            src = [s for s in range(frames) if int(fmap[bi, s]) == f]
+            got = wave[bi, f * hop : (f + 1) * hop]
+            if not src:
+                assert torch.all(got == 0), (bi, f)                     # silence: nobody mapped here
+            elif len(src) == 1:
+                assert torch.equal(got, ref[bi, src[0] * hop : (src[0] + 1) * hop]), (bi, f)
+
+
+def test_generators_match_the_unmodified_reference_on_the_shipped_stage_plan(amp_golden, true_fp32_convs):
+    """Whole-generator golden produced by the UNMODIFIED bigvgan.BigVGAN (tests/golden/make_golden_amp.py) with the shipped
+    stage plan (six stages, rates 4,4,2,2,2,2, AMPBlock1 x {3, 7, 11}) narrowed to upsample_initial_channel = 192, T_mel = 16.
+    Weights are synthesised from (name, shape) on both sides (tests/golden/synth_weights.py).  The fused [B, C, T] generator
+    and the channels-last engine must reproduce the reference's fp64 output in fp32; the bf16 engine within bf16 budget."""
+    import sys
+
+    sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+    from synth_weights import synth_state_dict
+    from afa_b200.engine import ChannelsLastVocoder
+    from afa_b200.vocoder import BINAURAL_22KHZ_80BAND_256X, BigVGANGenerator
+
+    c = amp_golden["gen_model_192"]
+    h = dict(BINAURAL_22KHZ_80BAND_256X)
+    h.update(upsample_initial_channel=192)
+    gen = BigVGANGenerator(h)
+    sd = gen.state_dict()
+    assert len(sd) == int(c["meta"][2])                           # same state-dict keys as the reference generator
+    new = synth_state_dict({k: tuple(v.shape) for k, v in sd.items()})
+    assert abs(float(sum(np.abs(v).sum() for v in new.values())) - float(c["param_checksum"][0])) <= 1e-6 * float(c["param_checksum"][0])
+    gen.load_state_dict({k: torch.tensor(new[k]) if k in new else v for k, v in sd.items()})
+    gen = gen.to(DEV).eval()
+    mel = torch.tensor(c["mel"], device=DEV)
+    with torch.no_grad():
+        y = gen(mel)
+    ref = c["y_f64"]
+    assert tuple(y.shape) == ref.shape == (2, 1, 16 * 256)
+    e_gen = O.max_normalised_error(y.double().cpu().numpy(), ref)
+    assert e_gen <= 5e-5, e_gen                                   # 109 fused activations + cuDNN fp32 convolutions in between
+    eng = ChannelsLastVocoder(gen, dtype=torch.float32)
+    wave, pcm = eng(mel, want_pcm=True)
+    e_eng = O.max_normalised_error(wave.double().cpu().numpy(), ref)
+    assert e_eng <= 5e-5, e_eng
+    ref_pcm = A.pcm_stereo(c["y_f32"][:, 0, :])
+    diff = np.abs(pcm.cpu().numpy()[0].astype(np.int32) - ref_pcm.astype(np.int32))
+    assert diff.max() <= 1 and (diff == 0).mean() >= 0.95
+    eng_b = ChannelsLastVocoder(gen, dtype=torch.bfloat16)
+    w_b, _ = eng_b(mel)
+    rel_l2 = float(np.linalg.norm(w_b.double().cpu().numpy() - ref) / np.linalg.norm(ref))
+    assert rel_l2 <= 5e-2, rel_l2                                 # bf16 storage between ~110 layers (measured 3.5e-2)
+    gen_b = BigVGANGenerator(h)
+    gen_b.load_state_dict(gen.state_dict())
+    gen_b = gen_b.to(DEV).bfloat16().eval()
+    with torch.no_grad():
+        y_b = gen_b(mel.bfloat16())
+    rel_l2 = float(np.linalg.norm(y_b.double().cpu().numpy() - ref) / np.linalg.norm(ref))
+    assert rel_l2 <= 5e-2, rel_l2
