@@ -52,6 +52,30 @@ def host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown CPU"
+
+
+def traffic_record(kernel: str, dtype: str, shape):
+    """profiles/traffic.json: DRAM bytes of the SAME launch (kernel, dtype, shape) from a committed ncu capture, or None."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        for rec in tj.get("launches", []):
+            if rec["kernel"] == kernel and rec["dtype"] == dtype and list(rec["shape"]) == list(shape):
+                return rec
+    except Exception:
+        pass
+    return None
+
+
 def stage_shapes(clips: int, t_mel: int):
     return [(2 * clips, c, mult * t_mel, calls) for (c, mult, calls) in AMP_STAGES]
 
@@ -141,6 +165,45 @@ def cpu_reference_pass(t_mel: int, clips: int = 1, repeats: int = 1, threads: in
     return elems, times
 
 
+def cpu_generator_pass(t_mel: int, repeats: int = 1):
+    """The second half of the metric on the host: the whole generator (bigvgan.py:361-387 restated by afa_b200/vocoder.py --
+    torch.nn convolutions, the reference's checkpoint layout) with the reference's torch-op Activation1d (oracle/torch_path.py)
+    on CPU, fp32, B = 2 (L, R), random init, all host threads, `t_mel` mel frames (bounded: a 10 s clip takes ~45 s)."""
+    import torch
+    import torch.nn as nn
+
+    from afa_b200.modules import DownSample1d, UpSample1d
+    from afa_b200.vocoder import BigVGANGenerator
+    from oracle import torch_path as TP
+
+    class TorchOpActivation1d(nn.Module):
+        def __init__(self, activation):
+            super().__init__()
+            self.act, self.upsample, self.downsample = activation, UpSample1d(2, 12), DownSample1d(2, 12)
+
+        def forward(self, x):
+            beta = getattr(self.act, "beta", None)
+            return TP.activation1d_torch(x, self.act.alpha, beta, bool(self.act.alpha_logscale), self.upsample.filter,
+                                         self.downsample.lowpass.filter)
+
+    torch.set_num_threads(host_cores())
+    torch.manual_seed(1234)
+    gen = BigVGANGenerator(activation_factory=TorchOpActivation1d).eval()
+    mel = torch.rand(2, 80, t_mel) * 14.5 - 12.0
+    times = []
+    with torch.no_grad():
+        gen(mel[:, :, : min(8, t_mel)])                      # warm the thread pool / oneDNN primitives
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            gen(mel)
+            times.append(time.perf_counter() - t0)
+    audio_s = t_mel * 256 / 22050.0
+    return {"audio_sec_per_sec": round(audio_s / min(times), 4), "unit": "binaural audio-s per wall-s", "t_mel": t_mel,
+            "seconds_per_pass": round(min(times), 3), "cores": host_cores(), "cpu": cpu_model(), "kind": "port",
+            "sample": (f"full generator (112 M parameters, random init), B=2 (L, R), T_mel={t_mel} ({audio_s:.2f} s of audio), fp32, torch CPU "
+                       f"ops incl. the reference's Activation1d op chain, best of {repeats}; compare with vocoder.audio_sec_per_sec of the GPU arm")}
+
+
 def run_reference(args):
     import torch
 
@@ -150,7 +213,8 @@ def run_reference(args):
     cores = host_cores()
     t_mel = args.t_mel
     sample = (f"one Activation1d call per AMP stage shape (6 calls, B=2 i.e. one binaural clip, T_mel={t_mel}, fp32) "
-              f"per step, torch CPU ops, {cores} threads")
+              f"per step, torch CPU ops, {cores} threads on {cpu_model()}; the GPU arm times all 109 calls for 8 clips -- both arms "
+              f"are normalised to GB/s of the same per-element byte count (same_config: shapes equal per stage, batch differs)")
     elems, _ = cpu_reference_pass(t_mel, 1, repeats=max(1, args.warmup))
     elems, times = cpu_reference_pass(t_mel, 1, repeats=args.steps)
     total_s = sum(times)
@@ -165,6 +229,10 @@ def run_reference(args):
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["vocoder_cpu"] = cpu_generator_pass(64, repeats=1)
+    except Exception as exc:  # noqa: BLE001
+        line["vocoder_cpu"] = {"error": repr(exc)[:200]}
     print(json.dumps(line))
     return 0
 
@@ -261,7 +329,25 @@ def run_e2e(wl: Workload, steps: int, warmup: int):
         one_step()
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
-    return dt / steps, h2d, h2d
+
+    # the host-link roofline of this step: the same pinned buffers, device slots and copy streams, no kernels in between
+    def copies_only():
+        for (hx, hy), s in zip(host, wl.stages):
+            n = len(s["xs"])
+            for k in range(s["calls"]):
+                i = k % n
+                with torch.cuda.stream(s_in):
+                    s["xs"][i].copy_(hx, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hy.copy_(s["ys"][i], non_blocking=True)
+
+    copies_only()
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    copies_only()
+    torch.cuda.synchronize(dev)
+    dt_copy = time.perf_counter() - t1
+    return dt / steps, h2d, h2d, dt_copy
 
 
 def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: int, t_mel: int, reps: int = 1,
@@ -291,32 +377,45 @@ def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: i
     ge = GraphedEngine(eng, B, t_mel, want_pcm=True, pcm_interleave=2)
     mine = shard_indices(total_clips, rank, world)
     n_batches = (len(mine) + clips_per_batch - 1) // clips_per_batch
-    mel_host = (torch.rand(B, 80, t_mel) * 14.5 - 12.0).pin_memory()          # U(-12, 2.5): DiffBinaural's mel clamp range
-    pcm_host = torch.empty(clips_per_batch, t_mel * gen.hop, 2, dtype=torch.int16).pin_memory()
+    # one pinned mel buffer and one pinned PCM buffer PER BATCH (distinct inputs, every result kept): U(-12, 2.5) is
+    # DiffBinaural's mel clamp range
+    n_host = max(1, n_batches)
+    mel_hosts = [(torch.rand(B, 80, t_mel) * 14.5 - 12.0).pin_memory() for _ in range(n_host)]
+    pcm_hosts = [torch.empty(clips_per_batch, t_mel * gen.hop, 2, dtype=torch.int16).pin_memory() for _ in range(n_host)]
     for _ in range(2):
-        pcm_host.copy_(ge(mel_host.to(dev, non_blocking=True))[1], non_blocking=True)
+        pcm_hosts[0].copy_(ge(mel_hosts[0].to(dev, non_blocking=True))[1], non_blocking=True)
+    # the only collective of the inference path: gather finished PCM; NCCL has no int16, an interleaved stereo sample pair
+    # travels as one int32.  One device buffer per batch so that the gather runs once, after the last batch.
+    pcm_dev = [torch.empty_like(ge.static_pcm) for _ in range(n_host)] if world > 1 else None
+    gathered = [torch.empty(world, *ge.static_pcm.view(torch.int32).shape, dtype=torch.int32, device=dev) for _ in range(n_host)] if world > 1 else None
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
     e0.record()
     for _ in range(reps):
-        for _b in range(n_batches):
-            _, pcm = ge(mel_host.to(dev, non_blocking=True))
-            pcm_host.copy_(pcm, non_blocking=True)
+        for bi in range(n_batches):
+            _, pcm = ge(mel_hosts[bi].to(dev, non_blocking=True))
+            pcm_hosts[bi].copy_(pcm, non_blocking=True)
+            if world > 1:
+                pcm_dev[bi].copy_(pcm)
     e1.record()
+    if world > 1:
+        for bi in range(n_batches):
+            dist.all_gather_into_tensor(gathered[bi], pcm_dev[bi].view(torch.int32))
     torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    wall = (time.perf_counter() - wall0) / reps
+    t = torch.tensor([e0.elapsed_time(e1) / reps, wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the only collective of the inference path: gather finished PCM (one batch per rank here); NCCL has no int16,
-        # an interleaved stereo sample pair travels as one int32
-        pcm32 = ge.static_pcm.view(torch.int32)
-        outs = [torch.empty_like(pcm32) for _ in range(world)]
-        dist.all_gather(outs, pcm32)
-    ms = float(t.item())
+    ms, wall_ms = float(t[0].item()), float(t[1].item())
     out = {
         "audio_sec_per_sec": round(total_clips * 10.0 / (ms * 1e-3), 1), "unit": "binaural audio-s per wall-s",
+        "e2e_wall_audio_sec_per_sec": round(total_clips * 10.0 / (wall_ms * 1e-3), 1),
+        "e2e_wall_ms_total": round(wall_ms, 2),
+        "e2e_wall_includes": ("host wall clock, max over ranks: pinned H2D of every batch's own mel buffer, graph replay, D2H of every "
+                              "batch's PCM into its own pinned buffer, and (N > 1) the NCCL all_gather of all finished PCM, then a device sync"),
         "total_clips": total_clips, "clips_per_batch": clips_per_batch, "ms_total": round(ms, 2),
         "ms_per_clip_per_gpu": round(ms / max(1, len(mine)), 3),
         "dtype": "bf16 generator (channels-last engine), fp32 math inside the fused AMP kernels, int16 PCM out",
@@ -325,10 +424,10 @@ def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: i
     }
     if compare_ncw and rank == 0:
         try:
-            del ge
+            del ge, pcm_dev, gathered
             torch.cuda.empty_cache()
             gv = GraphedVocoder(gen, B, t_mel, dtype=torch.bfloat16, device=dev)
-            mel_dev = mel_host.to(dev)
+            mel_dev = mel_hosts[0].to(dev)
             for _ in range(2):
                 gv(mel_dev)
             torch.cuda.synchronize(dev)
@@ -501,6 +600,114 @@ def run_mel_step(dev, batch: int = 32, segment: int = 8192, reps: int = 20):
     return out
 
 
+# ----------------------------------------------------------------------------------------------
+# per-shape timing (shared by the main line's `roofline_per_shape` and by --table)
+# ----------------------------------------------------------------------------------------------
+def time_shape(dev, b: int, c: int, t: int, dname: str, which: str, torch_baseline: bool = False, reps: int = 3):
+    """One Activation1d forward (`fwd`) or backward (`bwd`) of a [b, c, t] tensor through the C ABI: CUDA-graph replay over
+    rotating buffer sets that exceed L2 (L2-cold), CUDA events.  Returns a dict with microseconds per call, algorithmic GB/s
+    (fwd 2 x, bwd 3 x element size per element) and the fraction of the measured HBM peak."""
+    import torch
+
+    from afa_b200 import Activation1d
+    from afa_b200 import functional as Fn
+    from afa_b200.activations import SnakeBeta
+    from oracle import torch_path as TP
+
+    dtype = torch.float32 if dname == "fp32" else torch.bfloat16
+    es = 4 if dname == "fp32" else 2
+    peak, _ = measured_peak()
+    act = SnakeBeta(c, alpha_logscale=True)
+    with torch.no_grad():
+        act.alpha.normal_(0, 0.5)
+        act.beta.normal_(0, 0.5)
+    m = Activation1d(activation=act).to(dev)
+    n = b * c * t
+    nbuf = max(2, min(24, int(1.0e9 // (n * es * 2))))
+    xs = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(nbuf)]
+    ys = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(nbuf)]
+    tu, td = m._host_taps()
+    a_, b_ = m.act.alpha.detach(), m.act.beta.detach()
+    if which == "fwd":
+        def call(i):
+            Fn.activation1d_forward_raw(xs[i % nbuf], a_, b_, tu, td, True, out=ys[i % nbuf])
+    else:
+        def call(i):
+            Fn.activation1d_backward_raw(xs[i % nbuf], ys[i % nbuf], a_, b_, tu, td, True)
+    iters = 2 * nbuf
+    call(0)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            call(i)
+    g.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us = e0.elapsed_time(e1) * 1e3 / (reps * iters)
+    bpe = (2 if which == "fwd" else 3) * es
+    gbs = n * bpe / us / 1e3
+    row = {"dtype": dname, "dir": which, "B": b, "C": c, "T": t, "us": round(us, 2), "GBps": round(gbs, 1),
+           "frac_of_measured_peak": round(gbs / peak, 3), "Gelem_per_s": round(n / us / 1e3, 1)}
+    if torch_baseline and which == "fwd":
+        taps = m.upsample.filter.to(dtype)
+        with torch.no_grad():
+            TP.activation1d_torch(xs[0], a_.to(dtype), b_.to(dtype), True, taps, taps)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for i in range(3):
+                TP.activation1d_torch(xs[i % nbuf], a_.to(dtype), b_.to(dtype), True, taps, taps)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        row["torch_ops_gpu_us"] = round(e0.elapsed_time(e1) * 1e3 / 3, 1)
+    del xs, ys, g
+    torch.cuda.empty_cache()
+    return row
+
+
+def per_shape_rooflines(dev, t_mel: int):
+    """fp32 + bf16, forward + backward, on: BASELINE config 1 (2, 512, 8192; target <= 12.0 us = 70 % of 8 TB/s for the fp32
+    forward), one binaural clip (B = 2), eight clips (B = 16) and the config-5 training shapes (B = 32, T_mel = 32).
+    Compact rows: [dtype, dir, B, C, T, us, GB/s, fraction of the measured HBM peak]."""
+    shapes = [("cfg1", 2, 512, 8192)]
+    for clips, tag in ((1, "clip1"), (8, "clips8")):
+        shapes += [(tag, b, c, t) for (b, c, t, _) in stage_shapes(clips, t_mel)]
+    shapes += [("train", 32, c, mult * 32) for (c, mult, _) in AMP_STAGES]
+    rows = []
+    for dname in ("fp32", "bf16"):
+        for which in ("fwd", "bwd"):
+            for (tag, b, c, t) in shapes:
+                r = time_shape(dev, b, c, t, dname, which)
+                rows.append([tag, dname, which, b, c, t, r["us"], r["GBps"], r["frac_of_measured_peak"]])
+    def worst(tag, dname, which):
+        v = [r[8] for r in rows if r[0] == tag and r[1] == dname and r[2] == which]
+        return [min(v), round(sum(v) / len(v), 3), max(v)] if v else None
+    summary = {f"{dname}_{which}_{tag}": worst(tag, dname, which) for dname in ("fp32", "bf16") for which in ("fwd", "bwd")
+               for tag in ("cfg1", "clip1", "clips8", "train")}
+    cfg1 = next(r for r in rows if r[0] == "cfg1" and r[1] == "fp32" and r[2] == "fwd")
+    return {"columns": ["set", "dtype", "dir", "B", "C", "T", "us", "GBps", "frac_of_measured_peak"], "rows": rows,
+            "min_mean_max_frac": summary, "cfg1_fp32_fwd_us": cfg1[6], "cfg1_target_us": 12.0,
+            "how": "one call per row, CUDA-graph replay over rotating buffer sets > L2, CUDA events; algorithmic bytes: forward 2 x, backward 3 x element size"}
+
+
+def gpu_torch_baseline(dev, clips: int, t_mel: int):
+    """SURVEY.md section 8(d) 'GPU baselines': the reference's torch-op chain (oracle/torch_path.py, the same ATen calls as
+    alias_free_activation/*.py) on THIS GPU, one call per AMP stage shape of the main workload, fp32, next to the fused kernel."""
+    rows, t_torch, t_fused = [], 0.0, 0.0
+    for (b, c, t, calls) in stage_shapes(clips, t_mel):
+        r = time_shape(dev, b, c, t, "fp32", "fwd", torch_baseline=True)
+        rows.append({"shape": [b, c, t], "calls": calls, "fused_us": r["us"], "torch_ops_us": r["torch_ops_gpu_us"]})
+        t_torch += calls * r["torch_ops_gpu_us"]
+        t_fused += calls * r["us"]
+    return {"per_stage": rows, "pass_ms_torch_ops": round(t_torch / 1e3, 3), "pass_ms_fused": round(t_fused / 1e3, 3),
+            "speedup": round(t_torch / t_fused, 2), "what": "reference torch-op Activation1d on the same B200, fp32, eager, 109 calls weighted"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -515,6 +722,7 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # the `train` object captures DDP's all-reduce in a CUDA graph
         dist.init_process_group(backend="nccl", device_id=dev)
     _lib.load_library()
     if args.chunks:
@@ -574,29 +782,32 @@ def run_gpu(args):
     per_launch_bytes = bytes_per_step / wl.launches
     per_launch_us = ms_per_step * 1e3 / wl.launches
     achieved = per_launch_bytes / (per_launch_us * 1e-6) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-        key = f"fwd_{args.dtype}_clips{args.clips}"
-        if key in tj:
-            traffic = tj[key]
-    except Exception:
-        pass
     kb, kc, kt = max((s["shape"] for s in wl.stages), key=lambda sh: sh[2])          # the long-row (dominant) variant
     kinfo = _lib.kernel_info(0, 0 if args.dtype == "fp32" else 1, kt, kb, kc)
+    # DRAM traffic of the SAME launch (kernel, dtype, shape) from the committed ncu capture; its algorithmic size beside it
+    trec = traffic_record("afa::afa_fwd_kernel", args.dtype, (kb, kc, kt))
+    traffic = None if trec is None else trec["dram_bytes"]
 
     # e2e through the module with host buffers
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        sec, h2d, d2h = run_e2e(wl, e2e_steps, 1)
-        t2 = torch.tensor([sec], dtype=torch.float64, device=dev)
+        sec, h2d, d2h, sec_copy = run_e2e(wl, e2e_steps, 1)
+        t2 = torch.tensor([sec, sec_copy], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * bytes_per_step / float(t2.item()) / 1e9, 3), "unit": UNIT,
+        sec, sec_copy = float(t2[0].item()), float(t2[1].item())
+        # value counts algorithmic bytes (in + out) = the bytes that cross the host link (h2d + d2h): same unit as the peak
+        pcie_peak = world * (h2d + d2h) / sec_copy / 1e9
+        e2e = {"value": round(world * bytes_per_step / sec / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "ms_per_step": round(float(t2.item()) * 1e3, 3),
+               "ms_per_step": round(sec * 1e3, 3),
+               "pcie_peak_gbs": round(pcie_peak, 3),
+               "frac_of_pcie_peak": round(world * bytes_per_step / sec / 1e9 / pcie_peak, 3),
+               "pcie_peak_how": ("the step's own pinned buffers, device slots and two copy streams with the kernels removed (H2D and D2H "
+                                 "concurrently), all ranks at once, max over ranks: the host link + host memory ceiling this e2e figure "
+                                 "is bound by; every intermediate activation crosses PCIe here, which no caller of the op does -- see "
+                                 "vocoder.e2e_wall_audio_sec_per_sec for the realistic end-to-end"),
                "api": "afa_b200.Activation1d.forward (ctypes -> afa_activation1d_fwd), pinned host buffers"}
 
     cpu_base = None
@@ -604,9 +815,9 @@ def run_gpu(args):
         cores = host_cores()
         cpu_reference_pass(args.t_mel, 1, repeats=1)
         elems, times = cpu_reference_pass(args.t_mel, 1, repeats=args.cpu_repeats)
-        cpu_base = {"value": round(elems * 8 / min(times) / 1e9, 4), "unit": UNIT, "cores": cores, "kind": "port",
+        cpu_base = {"value": round(elems * 8 / min(times) / 1e9, 4), "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model(),
                     "sample": (f"one Activation1d call per AMP stage shape (6 calls, B=2, T_mel={args.t_mel}, fp32, "
-                               f"{elems} elements), torch CPU ops (oracle/torch_path.py), best of {args.cpu_repeats}")}
+                               f"{elems} elements), torch CPU ops (oracle/torch_path.py), {cores} threads on {cpu_model()}, best of {args.cpu_repeats}")}
 
     used_graph = graph is not None
     vocoder = None
@@ -634,6 +845,22 @@ def run_gpu(args):
         except Exception as exc:  # noqa: BLE001
             mel = {"error": repr(exc)[:200]}
 
+    per_shape = torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_per_shape:
+        try:
+            torch.cuda.empty_cache()
+            per_shape = per_shape_rooflines(dev, args.t_mel)
+            torch_gpu = gpu_torch_baseline(dev, args.clips, args.t_mel)
+        except Exception as exc:  # noqa: BLE001
+            per_shape = {"error": repr(exc)[:200]}
+    train = None
+    if not args.no_train:
+        try:
+            torch.cuda.empty_cache()
+            train = train_step_bench(args, dev, world, rank, local_rank, min(5, max(1, args.steps)), 3, profile_share=True)
+        except Exception as exc:  # noqa: BLE001
+            train = {"error": repr(exc)[:200]}
+
     if world > 1 and wl is not None:
         # the only collective: gather one checksum per rank (stands in for gathering finished waveforms)
         chk = torch.stack([s["ys"][0].float().abs().mean() for s in wl.stages]).sum().reshape(1)
@@ -656,7 +883,12 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "afa::afa_fwd_kernel", "avg_launch_us": round(per_launch_us, 3),
-                         "algorithmic_bytes_per_launch": int(per_launch_bytes), "kernel_info": kinfo},
+                         "algorithmic_bytes_per_launch": int(per_launch_bytes), "kernel_info": kinfo,
+                         "traffic_launch": None if trec is None else {
+                             "shape": trec["shape"], "algorithmic_bytes": trec["algorithmic_bytes"], "dram_read_bytes": trec["dram_read_bytes"],
+                             "traffic_over_algorithmic": round(trec["dram_bytes"] / trec["algorithmic_bytes"], 3), "source": trec["source"],
+                             "note": "per launch of the largest stage shape of this workload (not the 109-launch average printed above)"},
+                         "tensor_core_forward": traffic_record("afa_tc::afa_tc_fwd_kernel", "bf16", (16, 384, 13776))},
             "cpu_baseline": cpu_base,
             "e2e": e2e,
             "gpu_launches": int(gpu_launches),
@@ -665,6 +897,9 @@ def run_gpu(args):
             "vocoder": vocoder,
             "channels_last_amp_kernels": channels_last,
             "log_mel": mel,
+            "roofline_per_shape": per_shape,
+            "gpu_torch_baseline": torch_gpu,
+            "train": train,
         }
         print(json.dumps(line))
     if world > 1:
@@ -701,8 +936,8 @@ def run_vocoder_mode(args):
     return 0
 
 
-def run_train_mode(args):
-    """`--mode train`: BASELINE config 5 -- the generator's forward + backward with the fused Activation1d forward and
+def train_step_bench(args, dev, world: int, rank: int, local_rank: int, steps: int, warmup: int, profile_share: bool = True):
+    """BASELINE config 5 -- the generator's forward + backward with the fused Activation1d forward and
     backward kernels in it (train_binaural_mel.py:431-543, 787-791: BigVGAN(h) under DDP, AdamW, clip_grad_norm_), at
     the training segment (8192 samples = 32 mel frames, `--t-mel 32`) and `--batch` items per GPU.  The discriminators
     and losses of the reference are not importable here (nnAudio, librosa, pesq, auraloss absent: SURVEY.md section 8c), so
@@ -715,16 +950,20 @@ def run_train_mode(args):
     from afa_b200 import _lib
     from afa_b200.vocoder import BigVGANGenerator
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
     t_mel = args.t_mel if args.t_mel != T_MEL_10S else 32
     B = args.batch
+    ddp_opts = {"gradient_as_bucket_view": True, "bucket_cap_mb": int(os.environ.get("AFA_DDP_BUCKET_MB", "100")),
+                "static_graph": os.environ.get("AFA_DDP_STATIC", "1") == "1",
+                # DDP's default, as train_binaural_mel.py:541 runs it.  (Round 1 lost 20 ms per step here: the in-place re-broadcast of
+                # the constant filter buffers made each of the 109 fused modules re-read its taps with a synchronising device-to-host
+                # copy; the tap cache now follows reloads, not version bumps -- profiles/r02_ddp_probe_n2.log.)
+                "broadcast_buffers": os.environ.get("AFA_DDP_BROADCAST_BUFFERS", "1") == "1"}
+    # Whole-step CUDA graph.  One GPU: only with --graph-step (the eager step is device-bound there).  Under DDP it is the
+    # default: DDP's per-parameter autograd hooks and bucket bookkeeping make the eager step HOST-bound (profiles/
+    # r02_ddp_probe_n2.log: 41 ms of kernels, 1 ms of NCCL, 58 ms per step), and a captured step replays with no host work.
+    # Recipe of the CUDA-graphs note: DDP built and warmed up (>= 11 steps) on a side stream, NCCL async error handling off.
+    want_graph = bool(args.graph_step) or (world > 1 and os.environ.get("AFA_TRAIN_GRAPH", "1") == "1")
 
     def build(factory=None):
         torch.manual_seed(1234)                                    # configs/bigvgan_binaural_22khz_80band_256x.json:9
@@ -735,10 +974,20 @@ def run_train_mode(args):
                     p.normal_(0, 0.5)
         gen = gen.to(dev).train()
         # train_binaural_mel.py:540-543 wraps the generator in plain DDP; bucket views avoid one gradient copy per step
-        model = nn.parallel.DistributedDataParallel(gen, device_ids=[local_rank], gradient_as_bucket_view=True,
-                                                    bucket_cap_mb=int(os.environ.get("AFA_DDP_BUCKET_MB", "25"))) if world > 1 else gen
+        if world > 1:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                model = nn.parallel.DistributedDataParallel(gen, device_ids=[local_rank], **ddp_opts)
+            torch.cuda.current_stream(dev).wait_stream(side)
+        else:
+            model = gen
+        if world > 1 and os.environ.get("AFA_DDP_BF16_HOOK", "0") == "1":
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+
+            model.register_comm_hook(None, default_hooks.bf16_compress_hook)
         opt = torch.optim.AdamW(gen.parameters(), 5e-5, betas=(0.8, 0.99),       # train_binaural_mel.py:548-551, config lr / betas
-                                capturable=bool(args.graph_step))
+                                capturable=want_graph)
         return gen, model, opt
 
     def make_loss(fused: bool):
@@ -790,12 +1039,12 @@ def run_train_mode(args):
             return loss
 
         graph = None
-        if args.graph_step and world == 1:
-            # the whole step (forward, fused backward kernels, clip, AdamW) captured once and replayed: no host work
+        if want_graph and fused:
+            # the whole step (forward, fused backward kernels, DDP's bucketed all-reduce, clip, AdamW) captured once and replayed
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                for _ in range(warmup):
+                for _ in range(max(warmup, 11 if world > 1 else warmup)):
                     one()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
@@ -835,22 +1084,30 @@ def run_train_mode(args):
 
     with ClockSampler(local_rank) as clocks:
         gen, model, opt = build()
-        ms, loss, launches = time_steps(model, gen, opt, max(1, args.steps), max(3, args.warmup))
+        n_params = sum(p.numel() for p in gen.parameters())
+        ms, loss, launches = time_steps(model, gen, opt, max(1, steps), max(3, warmup))
     # share of the fused activation kernels in the step (device time, one profiled step on rank 0)
-    act_ms = None
-    if rank == 0:
+    act_ms = tot_ms = nccl_ms = None
+    if profile_share:
+        # one extra step on every rank (DDP's all-reduce needs all of them); rank 0 records it with the kernel profiler
         try:
+            import contextlib
+
             from torch.profiler import ProfilerActivity, profile
 
             mel = torch.rand(B, 80, t_mel, device=dev) * 14.5 - 12.0
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ctx = profile(activities=[ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()
+            with ctx as prof:
                 opt.zero_grad(set_to_none=True)
-                gen(mel).abs().mean().backward()
+                model(mel).abs().mean().backward()
                 torch.cuda.synchronize(dev)
-            act_ms = sum(r.device_time_total for r in prof.key_averages() if "afa::" in r.key) / 1e3
-            tot_ms = sum(r.device_time_total for r in prof.key_averages()) / 1e3
+            if rank == 0:
+                ka = prof.key_averages()
+                act_ms = sum(r.device_time_total for r in ka if "afa" in r.key) / 1e3
+                nccl_ms = sum(r.device_time_total for r in ka if "nccl" in r.key.lower()) / 1e3
+                tot_ms = sum(r.device_time_total for r in ka) / 1e3
         except Exception:  # noqa: BLE001
-            act_ms = tot_ms = None
+            act_ms = tot_ms = nccl_ms = None
     base = None
     if args.torch_baseline:
         del gen, model, opt
@@ -869,27 +1126,49 @@ def run_train_mode(args):
                                              self.downsample.lowpass.filter)
 
         gen_t, model_t, opt_t = build(TorchOpActivation1d)
-        ms_t, loss_t, _ = time_steps(model_t, gen_t, opt_t, max(1, args.steps), 3, fused=False)
+        ms_t, loss_t, _ = time_steps(model_t, gen_t, opt_t, max(1, steps), 3, fused=False)
         base = {"ms_per_step": round(ms_t, 3), "loss": loss_t, "what": "same step, reference torch-op Activation1d on the same GPU"}
+    samples = world * B * t_mel * 256
+    result = {
+        "metric": "train_step_generator_fwd_bwd_ms", "value": round(ms, 3), "unit": "ms per step", "n_gpus": world,
+        "steps": max(1, steps), "warmup": max(3, warmup), "ms_per_step": round(ms, 3), "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": (f"BASELINE config 5: BigVGAN generator (bigvgan_binaural_22khz_80band_256x, random init) forward + "
+                                f"backward + clip_grad_norm + AdamW, batch {B} per GPU, segment {t_mel * 256} samples (T_mel={t_mel}), "
+                                + ("multi-scale mel loss x 60 + single-scale mel of the estimate (fused log-mel kernels, forward + adjoint)"
+                                   if args.mel_loss else "synthetic scalar loss")
+                                + "; fused Activation1d forward and backward ([B, C, T] kernels)"),
+                   "parallelism": f"DDP dp{world}" if world > 1 else "single GPU",
+                   "ddp": ddp_opts if world > 1 else None,
+                   "collective": (f"DDP bucketed NCCL all-reduce of the fp32 gradients ({n_params * 4 / 1e6:.0f} MB per step, "
+                                  f"{ddp_opts['bucket_cap_mb']} MB buckets, overlapped with backward)") if world > 1 else None,
+                   "cuda_graph_step": want_graph},
+        "audio_sec_per_sec_trained": round(samples / 22050.0 / (ms * 1e-3), 1),
+        "activation_kernels_ms_per_step": None if act_ms is None else round(act_ms, 3),
+        "all_kernels_ms_per_step": None if act_ms is None else round(tot_ms, 3),
+        "nccl_kernels_ms_per_step": None if nccl_ms is None else round(nccl_ms, 3),
+        "gpu_launches": int(launches) * max(1, steps), "loss": loss, "torch_op_activation_baseline": base,
+        "clocks": clocks.summary(),
+    }
+    return result
+
+
+def run_train_mode(args):
+    """`--mode train`: BASELINE config 5 as the main line (see train_step_bench)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # required to capture DDP's all-reduce in a CUDA graph
+        dist.init_process_group(backend="nccl", device_id=dev)
+    result = train_step_bench(args, dev, world, rank, local_rank, max(1, args.steps), max(3, args.warmup))
     if rank == 0:
-        samples = world * B * t_mel * 256
-        print(json.dumps({
-            "metric": "train_step_generator_fwd_bwd_ms", "value": round(ms, 3), "unit": "ms per step", "n_gpus": world,
-            "steps": max(1, args.steps), "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"BASELINE config 5: BigVGAN generator (bigvgan_binaural_22khz_80band_256x, random init) forward + "
-                                    f"backward + clip_grad_norm + AdamW, batch {B} per GPU, segment {t_mel * 256} samples (T_mel={t_mel}), "
-                                    + ("multi-scale mel loss x 60 + single-scale mel of the estimate (fused log-mel kernels, forward + adjoint)"
-                                       if args.mel_loss else "synthetic scalar loss")
-                                    + "; fused Activation1d forward and backward ([B, C, T] kernels)"),
-                       "parallelism": f"DDP dp{world}" if world > 1 else "single GPU",
-                       "cuda_graph_step": bool(args.graph_step and world == 1)},
-            "audio_sec_per_sec_trained": round(samples / 22050.0 / (ms * 1e-3), 1),
-            "activation_kernels_ms_per_step": None if act_ms is None else round(act_ms, 3),
-            "all_kernels_ms_per_step": None if act_ms is None else round(tot_ms, 3),
-            "gpu_launches": int(launches) * max(1, args.steps), "loss": loss, "torch_op_activation_baseline": base,
-            "clocks": clocks.summary(),
-        }))
+        print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -913,62 +1192,12 @@ def run_table(args):
     for clips in (1, 8):
         shapes += [(b, c, t) for (b, c, t, _) in stage_shapes(clips, args.t_mel)]
     shapes += [(32, c, mult * 32) for (c, mult, _) in AMP_STAGES]
-    for dtype, dname in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
-        es = 4 if dname == "fp32" else 2
+    for dname in ("fp32", "bf16"):
         for which in ("fwd", "bwd"):
             for (b, c, t) in shapes:
-                act = SnakeBeta(c, alpha_logscale=True)
-                with torch.no_grad():
-                    act.alpha.normal_(0, 0.5)
-                    act.beta.normal_(0, 0.5)
-                m = Activation1d(activation=act).to(dev)
-                n = b * c * t
-                nbuf = max(2, min(24, int(1.0e9 // (n * es * 2))))
-                xs = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(nbuf)]
-                ys = [torch.randn(b, c, t, device=dev).to(dtype) for _ in range(nbuf)]
-                tu, td = m._host_taps()
-                a_, b_ = m.act.alpha.detach(), m.act.beta.detach()
-                if which == "fwd":
-                    def call(i):
-                        Fn.activation1d_forward_raw(xs[i % nbuf], a_, b_, tu, td, True, out=ys[i % nbuf])
-                else:
-                    def call(i):
-                        Fn.activation1d_backward_raw(xs[i % nbuf], ys[i % nbuf], a_, b_, tu, td, True)
-                iters = 2 * nbuf
-                call(0)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    for i in range(iters):
-                        call(i)
-                g.replay()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(3):
-                    g.replay()
-                e1.record()
-                torch.cuda.synchronize()
-                us = e0.elapsed_time(e1) * 1e3 / (3 * iters)
-                bpe = (2 if which == "fwd" else 3) * es
-                gbs = n * bpe / us / 1e3
-                row = {"dtype": dname, "dir": which, "B": b, "C": c, "T": t, "us": round(us, 2), "GBps": round(gbs, 1),
-                       "frac_of_measured_peak": round(gbs / peak, 3), "Gelem_per_s": round(n / us / 1e3, 1)}
-                if args.torch_baseline and which == "fwd":
-                    taps = m.upsample.filter.to(dtype)
-                    with torch.no_grad():
-                        TP.activation1d_torch(xs[0], a_.to(dtype), b_.to(dtype), True, taps, taps)
-                        torch.cuda.synchronize()
-                        e0.record()
-                        for i in range(3):
-                            TP.activation1d_torch(xs[i % nbuf], a_.to(dtype), b_.to(dtype), True, taps, taps)
-                        e1.record()
-                        torch.cuda.synchronize()
-                    row["torch_ops_gpu_us"] = round(e0.elapsed_time(e1) * 1e3 / 3, 1)
+                row = time_shape(dev, b, c, t, dname, which, torch_baseline=args.torch_baseline)
                 rows.append(row)
                 print(json.dumps(row), file=sys.stderr, flush=True)
-                del xs, ys, g
-                torch.cuda.empty_cache()
     out = os.path.join(REPO, "gpurun_out", "shape_table.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as f:
@@ -991,6 +1220,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the whole-generator audio-s/s companion number")
+    ap.add_argument("--no-per-shape", action="store_true", help="skip roofline_per_shape / gpu_torch_baseline (one GPU only)")
+    ap.add_argument("--no-train", action="store_true", help="skip the BASELINE config 5 training-step object")
     ap.add_argument("--mode", choices=["activation", "vocoder", "train"], default="activation",
                     help="vocoder: BASELINE config 4 (--total-clips clips sharded over the ranks, strong scaling); "
                          "train: BASELINE config 5 (generator forward + backward step, --batch per GPU, segment 8192)")

@@ -135,13 +135,32 @@ class Activation1d(nn.Module):
         self._p32 = None
 
     # -- host copies of the filter buffers (they travel in checkpoints; read them, never recompute) --
+    # The copy is refreshed when the buffers are REPLACED or RELOADED: a new storage (`.to()`, `.cuda()`, `.double()`, assigning a
+    # new tensor) changes the key, `load_state_dict` and `_apply` drop the cache.  In-place writes with the values they already
+    # hold -- DistributedDataParallel's broadcast_buffers=True does that before every forward (train_binaural_mel.py:541 uses the
+    # default) -- do NOT trigger a re-read: each would be a synchronising device-to-host copy per module per step (measured on
+    # two B200s: 64 ms instead of 44 ms per training step, profiles/r02_ddp_probe_n2.log).  Code that edits a filter in place
+    # with NEW values calls `refresh_filters()`.
     def _host_taps(self):
         up, dn = self.upsample.filter, self.downsample.lowpass.filter
-        key = (up.data_ptr(), up._version, dn.data_ptr(), dn._version)
-        if key != self._taps_key:
+        key = (up.data_ptr(), dn.data_ptr(), up.dtype, up.device)
+        if key != self._taps_key or self._taps is None:
             self._taps = (F_afa.host_taps(up), F_afa.host_taps(dn))
             self._taps_key = key
         return self._taps
+
+    def refresh_filters(self):
+        """Forget the cached host copy of the filter taps (after editing `upsample.filter` / `downsample.lowpass.filter` in place)."""
+        self._taps_key = None
+        self._taps = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.refresh_filters()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.refresh_filters()
+        return super()._apply(fn, *args, **kwargs)
 
     def _params(self):
         """alpha / beta as the autograd function wants them. fp32 parameters pass through untouched

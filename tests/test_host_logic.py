@@ -246,3 +246,32 @@ def test_clip_sharding_gather_two_ranks_gloo(tmp_path, n_items):
         assert torch.equal(got, expect)
         got_pcm = torch.load(os.path.join(str(tmp_path), f"p{r}.pt"))
         assert got_pcm.dtype == torch.int16 and torch.equal(got_pcm, expect_pcm)
+
+
+def test_filter_tap_cache_follows_reloads_not_rebroadcasts():
+    """The host copy of the 12 filter taps is re-read when the buffers are reloaded or replaced (`load_state_dict`, `.to()`,
+    `refresh_filters()`), and NOT when the same values are written in place -- what DistributedDataParallel's
+    broadcast_buffers=True (the default the reference's trainer uses, train_binaural_mel.py:541) does before every forward:
+    each re-read would be a synchronising device-to-host copy per module per step."""
+    from afa_b200 import Activation1d
+    from afa_b200.activations import SnakeBeta
+
+    m = Activation1d(activation=SnakeBeta(4, alpha_logscale=True))
+    t0 = m._host_taps()
+    first = list(t0[0])
+    with torch.no_grad():
+        m.upsample.filter.copy_(m.upsample.filter.clone())          # in-place rewrite, same values (bumps the version counter)
+    assert m._host_taps() is t0
+    sd = m.state_dict()
+    sd["upsample.filter"] = sd["upsample.filter"] * 0.5
+    m.load_state_dict(sd)
+    t1 = m._host_taps()
+    assert t1 is not t0 and np.allclose(list(t1[0]), np.array(first) * 0.5)
+    with torch.no_grad():
+        m.downsample.lowpass.filter.mul_(2.0)
+    assert m._host_taps() is t1                                      # in-place edit with new values: the caller must say so
+    m.refresh_filters()
+    t2 = m._host_taps()
+    assert np.allclose(list(t2[1]), np.array(list(t1[1])) * 2.0)
+    m.double()
+    assert m._host_taps() is not t2                                  # new storage
