@@ -444,6 +444,144 @@ def run_vocoder(dev, world: int, rank: int, total_clips: int, clips_per_batch: i
     return out
 
 
+def run_vocoder_files(dev, world: int, rank: int, total_clips: int, clips_per_batch: int, t_mel: int, zero_every: int = 8):
+    """inference_e2e.py:129-205 as a measured, file-to-file path: `total_clips` synthetic clips as
+    left/right mel `.npy` files on tmpfs (every `zero_every`-th clip carries zero frames, as DiffBinaural's padded silence
+    does) -> loader thread (np.load into pinned staging buffers, a batch ahead) -> one H2D per batch -> zero-frame
+    compaction on the device (afa_compact_zero_frames) -> bf16 channels-last generator (CUDA-graph replay for full-length
+    rows, eager per-length launches for rows that lost frames) -> D2H of int16 stereo PCM -> writer thread
+    (scipy.io.wavfile.write to tmpfs, off the critical path).  Wall clock, max over ranks."""
+    import queue
+    import shutil
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from afa_b200 import ingest, shard_indices
+    from afa_b200.engine import ChannelsLastVocoder
+    from afa_b200.vocoder import BigVGANGenerator
+
+    root = os.environ.get("AFA_BENCH_TMP", "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
+    work = os.path.join(root, f"afa_bench_npy_{os.environ.get('MASTER_PORT', '0')}")
+    if rank == 0:
+        shutil.rmtree(work, ignore_errors=True)
+        for d in ("left", "right", "wav"):
+            os.makedirs(os.path.join(work, d))
+        rng = np.random.default_rng(1234)
+        for i in range(total_clips):
+            for side in ("left", "right"):
+                mel = (rng.random((80, t_mel)) * 14.5 - 12.0).astype(np.float32)        # U(-12, 2.5): DiffBinaural's clamp range
+                if zero_every and i % zero_every == zero_every - 1:
+                    a = int(rng.integers(0, t_mel - 40))
+                    mel[:, a : a + int(rng.integers(5, 40))] = 0.0                      # a run of silent (zero) frames
+                    if side == "left":
+                        mel[:, -7:] = 0.0                                                # left and right keep different counts
+                np.save(os.path.join(work, side, f"clip_{i:04d}.npy"), mel)
+    if world > 1:
+        dist.barrier()
+    torch.manual_seed(1234)
+    gen = BigVGANGenerator().to(dev)
+    with torch.no_grad():
+        for n, p in gen.named_parameters():
+            if n.endswith("alpha") or n.endswith("beta"):
+                p.normal_(0, 0.5)
+    gen = gen.bfloat16().eval()
+    eng = ChannelsLastVocoder(gen, dtype=torch.bfloat16)
+    bv = ingest.BatchedVocoder(eng, clips_per_batch, t_mel)
+    mine = shard_indices(total_clips, rank, world)
+    batches = [mine[i : i + clips_per_batch] for i in range(0, len(mine) - len(mine) % clips_per_batch, clips_per_batch)]
+    n_stage = 3
+    stage = [torch.empty(clips_per_batch, 2, 80, t_mel).pin_memory() for _ in range(n_stage)]
+    pcm_host = [torch.empty(clips_per_batch, t_mel * gen.hop, 2, dtype=torch.int16).pin_memory() for _ in range(n_stage)]
+    free_in, ready_in, to_write, free_out = queue.Queue(), queue.Queue(), queue.Queue(), queue.Queue()
+    for i in range(n_stage):
+        free_in.put(i)
+        free_out.put(i)
+
+    def loader():
+        for b in batches:
+            slot = free_in.get()
+            buf = stage[slot].numpy()
+            for j, ci in enumerate(b):
+                buf[j, 0] = ingest.load_mel_npy(os.path.join(work, "left", f"clip_{ci:04d}.npy"))      # inference_e2e.py:140-141
+                buf[j, 1] = ingest.load_mel_npy(os.path.join(work, "right", f"clip_{ci:04d}.npy"))
+            ready_in.put((slot, b))
+        ready_in.put(None)
+
+    def writer():
+        while True:
+            item = to_write.get()
+            if item is None:
+                return
+            slot, b, ev = item
+            ev.synchronize()
+            for j, ci in enumerate(b):
+                ingest.write_wav(os.path.join(work, "wav", f"clip_{ci:04d}.wav"), 22050, pcm_host[slot][j].numpy())     # :205
+            free_out.put(slot)
+
+    # warm-up: one full-length batch (graph replay path) outside the timed region
+    bv(torch.zeros(clips_per_batch, 2, 80, t_mel, device=dev) - 5.0)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    def one_pass():
+        tl, tw = threading.Thread(target=loader), threading.Thread(target=writer)
+        t0 = time.perf_counter()
+        tl.start()
+        tw.start()
+        ragged_rows = 0
+        while True:
+            item = ready_in.get()
+            if item is None:
+                break
+            slot, b = item
+            mel_dev = stage[slot].to(dev, non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record()
+            pcm = bv(mel_dev)                                   # synchronises on n_kept: the staging buffer is free after this
+            ev_in.synchronize()
+            free_in.put(slot)
+            out_slot = free_out.get()
+            pcm_host[out_slot].copy_(pcm, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            to_write.put((out_slot, b, ev))
+        torch.cuda.synchronize(dev)
+        t_pcm = time.perf_counter() - t0
+        to_write.put(None)
+        tl.join()
+        tw.join()
+        t_wav = time.perf_counter() - t0
+        return t_pcm, t_wav
+
+    cold = one_pass()                                   # first sight of the ragged lengths: cuDNN builds plans for them
+    if world > 1:
+        dist.barrier()
+    t_pcm, t_wav = one_pass()                           # the same files again: what a running service sees
+    n_done = sum(len(b) for b in batches)
+    t = torch.tensor([t_pcm, t_wav], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n_done], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    wavs = len(os.listdir(os.path.join(work, "wav"))) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        shutil.rmtree(work, ignore_errors=True)
+    clips_done = int(cnt.item())
+    return {"first_pass_audio_sec_per_sec": round(n_done * 10.0 / cold[1], 1),
+            "first_pass_note": "this rank, first sight of the ragged lengths: cuDNN builds execution plans for every new (rows, length) of the ~110 convolutions",
+            "audio_sec_per_sec_pcm_on_host": round(clips_done * 10.0 / float(t[0].item()), 1),
+            "audio_sec_per_sec_wav_written": round(clips_done * 10.0 / float(t[1].item()), 1),
+            "clips": clips_done, "clips_with_zero_frames": len([i for i in range(total_clips) if zero_every and i % zero_every == zero_every - 1]),
+            "wav_files_written": wavs, "clips_per_batch": clips_per_batch, "t_mel": t_mel, "tmpfs": root,
+            "unit": "binaural audio-s per wall-s (10 s per clip)",
+            "path": ".npy (tmpfs) -> pinned staging (loader thread) -> H2D -> afa_compact_zero_frames -> bf16 channels-last generator -> "
+                    "int16 stereo PCM -> D2H -> .wav (tmpfs, writer thread)"}
+
+
 def run_cl_step(dev, clips: int, t_mel: int, steps: int = 5):
     """The fused AMP kernels of one channels-last generator pass (bf16, CUDA-graph replay, rotating buffers):
     72 x activation+bias, 36 x activation+bias+residual (writes the new residual stream), 6 x resblock mean,
@@ -829,6 +967,11 @@ def run_gpu(args):
             vocoder = run_vocoder(dev, world, rank, args.clips * world, min(4, args.clips), args.t_mel)
         except Exception as exc:  # noqa: BLE001  (the headline metric must still print)
             vocoder = {"error": repr(exc)[:200]}
+        try:
+            torch.cuda.empty_cache()
+            vocoder["files"] = run_vocoder_files(dev, world, rank, 2 * args.clips * world, min(4, args.clips), args.t_mel)
+        except Exception as exc:  # noqa: BLE001
+            vocoder["files"] = {"error": repr(exc)[:200]}
         wl = None
     channels_last = None
     if not args.no_vocoder and rank == 0 and world == 1:
@@ -921,6 +1064,9 @@ def run_vocoder_mode(args):
         dist.init_process_group(backend="nccl", device_id=dev)
     with ClockSampler(local_rank) as clocks:
         v = run_vocoder(dev, world, rank, args.total_clips, min(4, args.total_clips), args.t_mel, reps=max(1, args.steps))
+        if args.from_npy:
+            torch.cuda.empty_cache()
+            v["files"] = run_vocoder_files(dev, world, rank, args.total_clips, min(4, args.total_clips), args.t_mel)
     if rank == 0:
         print(json.dumps({
             "metric": "vocoded_audio_sec_per_sec", "value": v["audio_sec_per_sec"], "unit": "audio-s/s", "n_gpus": world,
@@ -1229,6 +1375,7 @@ def main():
     ap.add_argument("--mel-loss", action="store_true", help="--mode train: the reference's multi-scale mel loss x 60 instead of the synthetic scalar loss")
     ap.add_argument("--graph-step", action="store_true", help="--mode train, one GPU: capture the whole step in a CUDA graph")
     ap.add_argument("--total-clips", type=int, default=64)
+    ap.add_argument("--from-npy", action="store_true", help="--mode vocoder: also run the file-to-file path (.npy mels on tmpfs in, .wav out)")
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=0, help="tuning: 16-byte chunks per thread segment for the forward (0 = library default)")
     ap.add_argument("--table", action="store_true")

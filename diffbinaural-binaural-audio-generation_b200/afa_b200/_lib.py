@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "afa_logmel_bwd_workspace_bytes",
     "afa_logmel_bwd",
     "afa_l1_partial_sums",
+    "afa_compact_zero_frames",
     "afa_set_tuning",
     "afa_kernel_info",
     "afa_kernel_info_shape",
@@ -93,6 +94,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
                                        f32, f32, f32, i32, fp, f32, fp, vp, ctypes.c_size_t, vp]
         lib.afa_l1_partial_sums.restype = i32
         lib.afa_l1_partial_sums.argtypes = [fp, fp, i64, fp, i32, vp]
+        lib.afa_compact_zero_frames.restype = i32
+        lib.afa_compact_zero_frames.argtypes = [vp, vp, vp, vp, i64, i32, i64, f32, vp]
         lib.afa_set_tuning.restype = i32
         lib.afa_set_tuning.argtypes = [i32, i32, i32]
         lib.afa_kernel_info.restype = i32

@@ -23,6 +23,7 @@ _UNITS = {
     "afa_capi.cu": ["afa_kernels.cuh", "afa_cl_kernels.cuh", "afa_actconv_kernels.cuh"],
     "afa_mel.cu": [],
     "afa_tc.cu": ["afa_tc_kernels.cuh"],
+    "afa_ingest.cu": [],
 }
 
 
@@ -41,13 +42,19 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libafa_sm100.so (there is no CPU fallback)")
 
 
+LAST_BUILD = {"action": None, "compiled_units": []}   # what the most recent build_library() call did (for build()'s report)
+
+
 def build_library(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
-    """Compile csrc/ -> afa_b200/libafa_sm100.so.  Rebuilds only when a source is newer.
-    `out` / `defines` build an experimental variant elsewhere (tuning sweeps)."""
+    """Compile csrc/ -> afa_b200/libafa_sm100.so.  Rebuilds only when a source is newer (AFA_FORCE_REBUILD=1 rebuilds
+    everything).  `out` / `defines` build an experimental variant elsewhere (tuning sweeps)."""
     out = out or library_path()
+    force = force or os.environ.get("AFA_FORCE_REBUILD", "0") == "1"
+    LAST_BUILD["compiled_units"] = []
     if not force and os.path.exists(out):
         t = os.path.getmtime(out)
         if all(os.path.getmtime(d) <= t for d in _deps()):
+            LAST_BUILD["action"] = "reused: the library is newer than every source and header"
             return out
     nvcc = _nvcc()
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -70,6 +77,9 @@ def build_library(force: bool = False, verbose: bool = False, out: str | None = 
         deps = [src] + [os.path.join(_CSRC, h) for h in headers] + _COMMON
         if force or defines or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
             run([nvcc] + flags + ["-c", src, "-o", obj])
+            LAST_BUILD["compiled_units"].append(unit)
         objs.append(obj)
     run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", out] + objs)
+    LAST_BUILD["action"] = ("compiled " + ", ".join(LAST_BUILD["compiled_units"]) if LAST_BUILD["compiled_units"] else "relinked cached objects") + \
+        " with nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo"
     return out

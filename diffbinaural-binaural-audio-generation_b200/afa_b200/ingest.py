@@ -97,3 +97,73 @@ def write_wav(path: str, sampling_rate: int, pcm_stereo) -> None:
     if isinstance(pcm_stereo, torch.Tensor):
         pcm_stereo = pcm_stereo.cpu().numpy()
     write(path, sampling_rate, np.ascontiguousarray(pcm_stereo, dtype=np.int16))
+
+
+# ------------------------------------------------------------------------------------------------
+# batched path: many clips per launch, zero-frame compaction on the device
+# ------------------------------------------------------------------------------------------------
+def compact_zero_frames(mel: torch.Tensor, zero_threshold: float = 1e-10):
+    """detect_and_exclude_zero_frames (inference_e2e.py:38-74) for a whole batch in one launch (afa_compact_zero_frames).
+    mel: float32 [rows, n_mels, T] on the device.  Returns (packed [rows, n_mels, T] with the kept frames left-packed,
+    frame_map int32 [rows, T] (original frame of each kept frame, -1 behind them), n_kept int32 [rows])."""
+    from . import _lib
+
+    if not mel.is_cuda or mel.dtype != torch.float32 or mel.dim() != 3 or not mel.is_contiguous():
+        raise RuntimeError("compact_zero_frames takes a contiguous float32 [rows, n_mels, T] CUDA tensor (there is no CPU fallback)")
+    rows, n_mels, T = mel.shape
+    packed = torch.empty_like(mel)
+    frame_map = torch.empty(rows, T, dtype=torch.int32, device=mel.device)
+    n_kept = torch.empty(rows, dtype=torch.int32, device=mel.device)
+    with torch.cuda.device_of(mel):
+        rc = _lib.load_library().afa_compact_zero_frames(mel.data_ptr(), packed.data_ptr(), frame_map.data_ptr(), n_kept.data_ptr(),
+                                                         rows, n_mels, T, float(zero_threshold),
+                                                         torch.cuda.current_stream(mel.device).cuda_stream)
+    _lib.check(rc, "afa_compact_zero_frames")
+    return packed, frame_map, n_kept
+
+
+class BatchedVocoder:
+    """inference_e2e.py:129-205 for BATCHES of clips: pinned mels -> one H2D -> one compaction launch -> generator ->
+    interleaved int16 stereo PCM.  Rows (clip x channel) that keep every frame -- the normal case -- run through a CUDA-graph
+    replay of the channels-last engine, `clips_per_batch` clips (2 x that many rows) at a time; rows that lost frames run
+    eagerly at their own length, grouped by length (padding a shorter row would change its last samples, which the reference
+    does not do), and are scattered back through their frame map by the tail kernel.  The only host synchronisation per batch
+    is the read of `n_kept` (rows x 4 bytes) that decides the routing."""
+
+    def __init__(self, engine, clips_per_batch: int, t_mel: int):
+        from .engine import GraphedEngine
+
+        self.engine, self.clips, self.t_mel = engine, clips_per_batch, t_mel
+        self.hop = 1
+        for u in engine.h["upsample_rates"]:
+            self.hop *= u
+        self.graphed = GraphedEngine(engine, 2 * clips_per_batch, t_mel, want_pcm=True, pcm_interleave=2)
+
+    def __call__(self, mel_batch: torch.Tensor) -> torch.Tensor:
+        """mel_batch: float32 [clips, 2, n_mels, t_mel] on the device -> int16 PCM [clips, t_mel * hop, 2] (a fresh tensor)."""
+        clips, two, n_mels, T = mel_batch.shape
+        if (clips, two, T) != (self.clips, 2, self.t_mel):
+            raise ValueError(f"expected [{self.clips}, 2, n_mels, {self.t_mel}] mels, got {tuple(mel_batch.shape)}")
+        rows = mel_batch.reshape(2 * clips, n_mels, T)
+        packed, fmap, n_kept = compact_zero_frames(rows)
+        kept = n_kept.cpu().tolist()                               # the one synchronising read: routes the rows
+        t_out = T * self.hop
+        if all(k == T for k in kept):
+            _, pcm = self.graphed(rows)                            # nothing dropped: the batch as it came
+            return pcm.clone()
+        pcm = torch.zeros(clips, t_out, 2, dtype=torch.int16, device=rows.device)
+        by_len = {}
+        for r, k in enumerate(kept):
+            by_len.setdefault(k, []).append(r)
+        flat = pcm.view(clips, t_out, 2)
+        # rare lengths run eagerly: no cuDNN autotuning for a shape that will not come back (it costs seconds per new length)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False):
+            for k, rs in sorted(by_len.items()):
+                if k == 0:
+                    continue                                       # a silent channel stays silence
+                idx = torch.tensor(rs, device=rows.device)
+                _, mono = self.engine(packed.index_select(0, idx)[:, :, :k].contiguous(), want_pcm=True, pcm_interleave=1,
+                                      frame_map=fmap.index_select(0, idx)[:, :k].contiguous(), t_out=t_out)
+                for j, r in enumerate(rs):
+                    flat[r // 2, :, r % 2] = mono[j, :, 0]
+        return pcm

@@ -87,7 +87,7 @@ bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, 
         // launches that fill 1-2 waves of this kernel's 128-lane CTAs.
         const int64_t n = rows * T;
         const bool many_short_rows = T < 32768 && n >= (16ll << 20);
-        const bool train_like = rows >= 1024 && T <= 16384 && n >= (3ll << 20);
+        const bool train_like = rows >= 768 && T <= 8192 && n >= (3ll << 20);
         if (!many_short_rows && !train_like) return false;
     }
     return encode_fn() != nullptr;

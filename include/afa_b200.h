@@ -239,6 +239,19 @@ int afa_logmel_bwd(const float *wav, const float *gout, float *gwav, int64_t row
 int afa_l1_partial_sums(const float *a, const float *b, int64_t n, float *partial, int n_partial, void *stream);
 
 /*
+ * Zero-frame compaction of a batch of mel spectrograms on the device:  <->  detect_and_exclude_zero_frames,
+ * BigVGAN/inference_e2e.py:38-74 (called per file and channel on the host at :146-147).
+ * mel / packed: float32 [rows, n_mels, T] device (rows = clips x channels); a frame is dropped when the sum of |mel| over its
+ * bands is <= zero_threshold (1e-10 in the reference; the sum runs in the reference's float32 order, so the mask is
+ * bit-identical).  packed[r][m][p] = mel[r][m][f] for the p-th kept frame f of row r (columns >= n_kept[r] are zero-filled),
+ * frame_map[r][p] = f (-1 beyond n_kept[r]: afa_tail_fwd_cl drops such hops), n_kept: int32 [rows].  One launch for the
+ * whole batch; the generator then runs on packed[:, :, :n_kept] and afa_tail_fwd_cl scatters the hops back through
+ * frame_map (reconstruct_audio_with_silence, inference_e2e.py:77-111).
+ */
+int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map, int32_t *n_kept,
+                            int64_t rows, int n_mels, int64_t T, float zero_threshold, void *stream);
+
+/*
  * Tuning / introspection (used by bench.py and the tests; not part of the reference interface).
  * afa_set_tuning: which=0 forward, 1 backward; chunks = 16-byte chunks per thread segment
  * (odd, one of the compiled values), threads = CTA size.  0 keeps the built-in choice.
