@@ -266,8 +266,8 @@ int64_t afa_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int afa_set_tuning(int which, int chunks, int threads) {
     if (which == 5) {   // tensor-core Activation1d (bf16): chunks = 0 off / 1 heuristic / 2 whenever eligible; threads = forced blocks per lane (0 = heuristic)
-        if (chunks < 0 || chunks > 2 || !(threads == 0 || threads == 4 || threads == 8 || threads == 12 || threads == 16))
-            return fail(AFA_ERR_BAD_ARG, "tensor-core path: mode 0..2, blocks per lane 0 / 4 / 8 / 12 / 16");
+        if (chunks < 0 || chunks > 2 || threads < 0 || threads > 4096 || threads % 4)
+            return fail(AFA_ERR_BAD_ARG, "tensor-core path: mode 0..2, blocks per lane 0 or a multiple of 4 up to 4096");
         g_tc_mode = chunks;
         g_tc_ny = threads;
         afa_internal::tc_set_tuning(g_tc_mode, g_tc_ny, g_tc_rlog2);

@@ -103,26 +103,36 @@ void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rg
     if (g_tc_rlog2 >= 3 && g_tc_rlog2 <= 7) rlog2 = g_tc_rlog2;
     const int64_t R = 1ll << rlog2, G = 128 / R;
     const int64_t rg = (rows + R - 1) / R;
-    auto ctas = [&](int ny) { return rg * ((T + G * 16 * ny - 1) / (G * 16 * ny)); };
-    // blocks per lane: a CTA costs ~5 block-times of set-up / fill / drain plus one per block, and the grid runs in waves of
-    // 2 CTAs per SM (fitted to same-box sweeps, profiles/r02_tc_sweep.log): take the cheapest, the longer strip on ties
+    // Blocks of 16 outputs per lane and CTA (NY, a multiple of 4).  A CTA streams its strip through a recycled chunk ring, so a
+    // strip may be any length: its set-up, pipeline fill and drain cost ~5 block-times once, and the grid runs in waves of
+    // 2 CTAs per SM.  Candidates: the short strips (4 ... 16) and the strip lengths that make the grid exactly w waves; the
+    // cheapest under  waves * (5 + NY)  wins, the longer strip on ties (profiles/r02_tc_sweep*.log).
     static int slots = 0;
     if (!slots) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = 2 * (sms > 0 ? sms : 148);
     }
-    int ny = 16;
-    int64_t best = -1;
-    for (int cand = 16; cand >= 4; cand -= 4) {
-        const int64_t cost = ((ctas(cand) + slots - 1) / slots) * (5 + cand);
-        if (best < 0 || cost < best) { best = cost; ny = cand; }
+    const int64_t tb = (T + 15) / 16;                                  // blocks per row
+    auto strips = [&](int64_t ny) { return (tb + G * ny - 1) / (G * ny); };
+    int64_t ny = 16, best = -1;
+    auto consider = [&](int64_t cand) {
+        cand = (cand + 3) / 4 * 4;
+        if (cand < 4) cand = 4;
+        if (cand > 4096) cand = 4096;
+        const int64_t cost = ((rg * strips(cand) + slots - 1) / slots) * (5 + cand);
+        if (best < 0 || cost < best || (cost == best && cand > ny)) { best = cost; ny = cand; }
+    };
+    for (int cand = 4; cand <= 16; cand += 4) consider(cand);
+    for (int w = 1; w <= 8; ++w) {
+        const int64_t nts = (int64_t)slots * w / rg;                   // strips per row group that fill w waves
+        if (nts >= 1) consider((tb + G * nts - 1) / (G * nts));
     }
-    if (g_tc_ny == 4 || g_tc_ny == 8 || g_tc_ny == 12 || g_tc_ny == 16) ny = g_tc_ny;
+    if (g_tc_ny >= 4 && g_tc_ny % 4 == 0) ny = g_tc_ny;
     *rlog2_out = rlog2;
-    *ny_out = ny;
+    *ny_out = (int)ny;
     *n_rgroups = rg;
-    *n_tstrips = (T + G * 16 * ny - 1) / (G * 16 * ny);
+    *n_tstrips = strips(ny);
 }
 
 int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta, const float* taps_up12,
@@ -155,6 +165,7 @@ int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta,
     a.debug = debug;
     a.dbg = dbg;
     a.dbg_cta = (int32_t)(rg * ts / 2);
+    a.dbg_blocks = ny + 1;
     static thread_local bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -186,7 +197,7 @@ int tc_kernel_info(int32_t out[6]) {
     out[0] = fa.numRegs;
     out[1] = (int32_t)(fa.sharedSizeBytes + afa_tc::kSmemBytes);
     out[2] = afa_tc::kThreads;
-    out[3] = 16 * afa_tc::kNYMax;
+    out[3] = 16;                     // outputs per block; blocks per lane are chosen per launch
     out[4] = occ;
     out[5] = 0;
     return 0;

@@ -50,19 +50,18 @@
 namespace afa_tc {
 
 constexpr int kThreads = 320;            // warp 0: TMA producer / TMEM allocator / TMA store, warp 1: MMA, warps 2..9: compute
-constexpr int kNYMax = 16;               // y blocks (16 outputs) per lane, multiple of 4
+constexpr int kSlots = 5;                // shared-memory chunk ring: slots of 64 samples x 128 lanes, recycled along the strip
 constexpr int kChunkBytes = 128 * 128;   // 128 lanes x 64 bf16
-constexpr int kNChunkMax = (kNYMax + 2 + 3) / 4;
 constexpr int kTmemCols = 256;           // 240 used; allocations are powers of two
 constexpr int kRing = 5;                 // slots of the U / S and Y rings
 constexpr int kColUS = 0;                // U / S ring: 5 slots x 32 columns (U fp32; S = 32 bf16 in the first 16)
 constexpr int kColY = 160;               // Y ring: 5 slots x 16 columns
 // shared memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int kOffWup = kNChunkMax * kChunkBytes;        // [hi/lo][slice a/b] x (32 x 16 bf16 = 1024 B)
+constexpr int kOffWup = kSlots * kChunkBytes;           // [hi/lo][slice a/b] x (32 x 16 bf16 = 1024 B)
 constexpr int kOffWdn = kOffWup + 4 * 1024;              // [hi/lo][slice a/b/c] x (16 x 16 bf16 = 512 B)
 constexpr int kOffBar = kOffWdn + 6 * 512;
-constexpr int kBarFull = 0, kBarPre = kNChunkMax, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 8, kBarOut = kBarEv + 8;
-constexpr int kNumBars = kBarOut + kNYMax / 4;
+constexpr int kBarFull = 0, kBarPre = kSlots, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 8, kBarOut = kBarEv + 8;
+constexpr int kNumBars = kBarOut + kSlots;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;         // + slack for the manual 1024-byte alignment
 
@@ -74,10 +73,11 @@ struct Args {
     uint16_t dn_hi[12], dn_lo[12];   // low-pass taps as bf16 hi + lo
     int32_t rows, C, T, flags;
     int32_t R_log2;        // lanes = R rows x G groups, R = 1 << R_log2
-    int32_t NY;            // y blocks per lane (4, 8, 12, 16)
+    int32_t NY;            // y blocks (16 outputs) per lane and CTA: a multiple of 4, any length (the chunk ring is recycled)
     int32_t n_tstrips;     // CTAs along time; blockIdx.x = row_group * n_tstrips + tstrip
     int32_t debug;         // harness only: 1 = dump U blocks, 2 = dump S, 3 = clock stamps of CTA dbg_cta
     int32_t dbg_cta;
+    int32_t dbg_blocks;    // harness: blocks per lane the U / S dump holds (NY + 1)
     float* dbg;
 };
 
@@ -91,16 +91,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// bounded wait: a protocol or descriptor mistake must end in a trap, never in a hung GPU
+// bounded wait: a protocol or descriptor mistake must end in a trap, never in a hung GPU.  The suspend-time hint lets the
+// hardware park the warp until the phase completes (or the hint expires) instead of re-issuing the poll: in the first versions
+// a quarter of all issued instructions were these polls, on the sub-partitions that also host the MMA and TMA warps.
+#ifndef AFA_TC_WAIT_HINT_NS
+#define AFA_TC_WAIT_HINT_NS 4000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spins > (1u << 24)) __trap();
+            : "=r"(done) : "r"(bar), "r"(parity), "r"((uint32_t)AFA_TC_WAIT_HINT_NS) : "memory");
+        if (spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
@@ -190,7 +195,7 @@ __device__ __forceinline__ uint32_t clk32() {
     return c;
 }
 // harness timeline (debug == 3): dbg[(role * 32 + j) * 8 + slot] = clock, for CTA `dbg_cta`
-#define AFA_TC_STAMP(role, j, slot) do { if (a.debug >= 3 && lane == 0 && blockIdx.x == (unsigned)a.dbg_cta) a.dbg[((role) * 32 + (j)) * 8 + (slot)] = __uint_as_float(clk32()); } while (0)
+#define AFA_TC_STAMP(role, j, slot) do { if (a.debug >= 3 && lane == 0 && (j) < 32 && blockIdx.x == (unsigned)a.dbg_cta) a.dbg[((role) * 32 + (j)) * 8 + (slot)] = __uint_as_float(clk32()); } while (0)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -226,9 +231,9 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp == 1) AFA_TC_STAMP(0, 31, 0);
+    if (warp == 1) AFA_TC_STAMP(3, 1, 0);
     const int NY = a.NY;
-    const int NCH_IN = (NY + 2 + 3) >> 2, NCH_OUT = NY >> 2;
+    const int NCH_IN = (NY + 2 + 3) >> 2, NCH_OUT = NY >> 2;       // x chunks / out chunks of this CTA's strip
     const int R = 1 << a.R_log2, G = 128 >> a.R_log2;
     const int tstrip = (int)(blockIdx.x % (uint32_t)a.n_tstrips);
     const int rgroup = (int)(blockIdx.x / (uint32_t)a.n_tstrips);
@@ -241,10 +246,10 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
     if (warp == 0) {
         if (elect_one()) {
-            // the loads first: every chunk of the CTA is requested up front, G boxes of R rows x 64 samples per chunk
-            for (int p = 0; p < NCH_IN; ++p) mbar_init(bars + 8 * (kBarFull + p), 1);
+            // the loads first: the first kSlots chunks of the strip, G boxes of R rows x 64 samples per chunk
+            for (int p = 0; p < kSlots; ++p) mbar_init(bars + 8 * (kBarFull + p), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            for (int p = 0; p < NCH_IN; ++p) {
+            for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
                 mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
                 for (int g = 0; g < G; ++g)
                     tma_load_2d(sbase + p * kChunkBytes + g * R * 128, &tm_x, t_cta0 + g * span - 8 + 64 * p, row0,
@@ -253,19 +258,19 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_init(bars + 8 * kBarPre, 8);
             for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarCmp + i), 4);
             for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEv + i), 1);
-            for (int i = 0; i < kNYMax / 4; ++i) mbar_init(bars + 8 * (kBarOut + i), 16);
+            for (int i = 0; i < kSlots; ++i) mbar_init(bars + 8 * (kBarOut + i), 16);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
         }
         __syncwarp();
-        AFA_TC_STAMP(0, 30, 0);
+        AFA_TC_STAMP(3, 0, 0);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        AFA_TC_STAMP(0, 30, 1);
+        AFA_TC_STAMP(3, 0, 1);
     } else {
         // banded Toeplitz B matrices (hi + lo bf16 split of the taps), K-major core-matrix layout: element (n, k) of a matrix at
         // (k / 8) * (N * 8) + n * 8 + (k % 8).  Zero fill by 16-byte stores, then the 6 (up) / 12 (down) taps of every column.
-        if (warp == 1) AFA_TC_STAMP(0, 30, 2);
+        if (warp == 1) AFA_TC_STAMP(3, 0, 2);
         const int t2 = tid - 32;                                   // 0 .. 287
         uint4* wz = reinterpret_cast<uint4*>(sgen + kOffWup);
         for (int i = t2; i < (4 * 1024 + 6 * 512) / 16; i += kThreads - 32) wz[i] = make_uint4(0, 0, 0, 0);
@@ -291,29 +296,38 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 wdn[(1 * 3 + sl) * 256 + off] = a.dn_lo[tap];
             }
         }
-        if (warp == 1) AFA_TC_STAMP(0, 30, 3);
+        if (warp == 1) AFA_TC_STAMP(3, 0, 3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp == 1) AFA_TC_STAMP(0, 31, 1);
+    if (warp == 1) AFA_TC_STAMP(3, 1, 1);
 
     if (warp == 0) {
-        // ===== TMA store of finished output chunks =====
+        // ===== TMA store of finished output chunks, then the slot takes the x chunk kSlots further down the strip =====
         for (int qc = 0; qc < NCH_OUT; ++qc) {
-            mbar_wait(bars + 8 * (kBarOut + qc), 0);
+            const int slot = qc % kSlots;
+            mbar_wait(bars + 8 * (kBarOut + slot), (uint32_t)(qc / kSlots) & 1u);
             if (elect_one()) {
                 for (int g = 0; g < G; ++g)
-                    tma_store_2d(&tm_y, t_cta0 + g * span + 64 * qc, row0, sbase + qc * kChunkBytes + g * R * 128);
+                    tma_store_2d(&tm_y, t_cta0 + g * span + 64 * qc, row0, sbase + slot * kChunkBytes + g * R * 128);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                const int nc = qc + kSlots;                         // next x chunk for this slot
+                if (nc < NCH_IN) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has finished reading the slot
+                    mbar_expect_tx(bars + 8 * (kBarFull + slot), (uint32_t)kChunkBytes);
+                    for (int g = 0; g < G; ++g)
+                        tma_load_2d(sbase + slot * kChunkBytes + g * R * 128, &tm_x, t_cta0 + g * span - 8 + 64 * nc, row0,
+                                    bars + 8 * (kBarFull + slot));
+                }
             }
             __syncwarp();
         }
         if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-        AFA_TC_STAMP(0, 31, 4);
+        AFA_TC_STAMP(3, 1, 4);
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // InstrDescriptor: D f32 [4,6) = 1, A bf16 [7,10) = 1, B bf16 [10,13) = 1, K-major both, N >> 3 [17,23), M >> 4 [24,29)
@@ -322,7 +336,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint64_t bup = bdesc_kmajor(sbase + kOffWup, 32 * 16);     // + 64 (1024 B >> 4) per matrix
         const uint64_t bdn = bdesc_kmajor(sbase + kOffWdn, 16 * 16);     // + 32 (512 B >> 4) per matrix
         const uint64_t ax = adesc_sw128(sbase);                          // x slice k: + (k / 4) * 1024 + (k % 4) * 2 (16-byte units)
-        auto xdesc = [&](int k) { return ax + (uint64_t)((k >> 2) * (kChunkBytes >> 4) + (k & 3) * 2); };
+        auto xdesc = [&](int k) { return ax + (uint64_t)(((k >> 2) % kSlots) * (kChunkBytes >> 4) + (k & 3) * 2); };
         // loop-invariant B descriptors (hi / lo halves of every K slice), kept in registers
         const uint64_t bu_a_hi = bup + 0 * 64, bu_b_hi = bup + 1 * 64, bu_a_lo = bup + 2 * 64, bu_b_lo = bup + 3 * 64;
         const uint64_t bd_a_hi = bdn + 0 * 32, bd_b_hi = bdn + 1 * 32, bd_c_hi = bdn + 2 * 32;
@@ -360,7 +374,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             AFA_TC_STAMP(0, j, 0);
             if (j + 4 <= NY) {
                 const int p = (j + 5) >> 2;                  // chunk of slice j+5
-                while (nfull <= p) { mbar_wait(bars + 8 * (kBarFull + nfull), 0); ++nfull; }
+                while (nfull <= p) { mbar_wait(bars + 8 * (kBarFull + nfull % kSlots), (uint32_t)(nfull / kSlots) & 1u); ++nfull; }
             }
             mbar_wait(bars + 8 * (kBarCmp + (j & 7)), (uint32_t)(j >> 3) & 1u);
             tc_fence_after();
@@ -384,7 +398,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             __syncwarp();
             AFA_TC_STAMP(0, j, 2);
         }
-        AFA_TC_STAMP(0, 31, 2);
+        AFA_TC_STAMP(3, 1, 2);
     } else {
         // ===== compute groups =====
         const int grp = (warp - 2) >> 2;
@@ -400,7 +414,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const bool left_lane = t_org < 0;                        // the lane starts its row (t_org = -8)
         // first 8-sample chunk of the lane's window that lies beyond the row (T % 8 == 0: chunk granular), if any
         const int cb = (T - t_org) >> 3;
-        const bool right_lane = T > t_org && cb < 8 * NCH_IN;
+        const bool right_lane = T > t_org && cb < 8 * NCH_IN;       // cb: 8-sample units from the lane's window start
         if (row < a.rows) {
             const int c = row % a.C;
             float al = __ldg(a.alpha + c);
@@ -410,24 +424,33 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             ib = 1.0f / (be + 0.000000001f);
         }
         // replicate padding of x (resample.py:32), patched into the staged chunks by group 0 (the TMA unit zero-filled what lies
-        // outside the tensor): x[0] over the 8 samples before the row, x[T-1] over the 16 samples behind it (3 are read)
-        if (grp == 0 && __any_sync(0xffffffffu, left_lane || right_lane)) {
-            if (row < a.rows && (left_lane || right_lane)) {
-                const unsigned short* xr16 = reinterpret_cast<const unsigned short*>(a.x) + (size_t)row * (size_t)T;
-                if (left_lane) {
-                    const uint32_t v = __ldg(xr16), xl = v | (v << 16);
-                    mbar_wait(bars + 8 * (kBarFull + 0), 0);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(srow + ((0u ^ sw) << 4)), "r"(xl) : "memory");
-                }
-                if (right_lane) {
-                    const uint32_t v = __ldg(xr16 + (T - 1)), xr = v | (v << 16);
-                    for (int c = cb; c < cb + 2 && c < 8 * NCH_IN; ++c) {
-                        mbar_wait(bars + 8 * (kBarFull + (c >> 3)), 0);
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(srow + (uint32_t)(c >> 3) * kChunkBytes + (((uint32_t)(c & 7) ^ sw) << 4)), "r"(xr) : "memory");
+        // outside the tensor): x[0] over the 8 samples before the row, x[T-1] over the 16 samples behind it (3 are read).  Chunk c
+        // is patched after it has landed and before the first product that reads it (up(4c-1), issued at event 4c-5): chunks 0 and
+        // 1 here, chunk c >= 2 at iteration 4c-8 of group 0, ahead of that iteration's arrive on cmp.
+        auto patch_chunk = [&](int c) {
+            const bool need = row < a.rows && ((left_lane && c == 0) || (right_lane && ((cb >> 3) == c || ((cb + 1) >> 3) == c)));
+            if (__any_sync(0xffffffffu, need)) {
+                if (need) {
+                    const unsigned short* xr16 = reinterpret_cast<const unsigned short*>(a.x) + (size_t)row * (size_t)T;
+                    mbar_wait(bars + 8 * (kBarFull + c % kSlots), (uint32_t)(c / kSlots) & 1u);
+                    const uint32_t cbase = srow + (uint32_t)(c % kSlots) * kChunkBytes;
+                    if (left_lane && c == 0) {
+                        const uint32_t v = __ldg(xr16), xl = v | (v << 16);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(cbase + ((0u ^ sw) << 4)), "r"(xl) : "memory");
+                    }
+                    if (right_lane) {
+                        const uint32_t v = __ldg(xr16 + (T - 1)), xr = v | (v << 16);
+                        for (int cc = cb; cc < cb + 2; ++cc)
+                            if ((cc >> 3) == c)
+                                asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(cbase + (((uint32_t)(cc & 7) ^ sw) << 4)), "r"(xr) : "memory");
                     }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        };
+        if (grp == 0) {
+            patch_chunk(0);
+            patch_chunk(1);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 8 * kBarPre);
@@ -449,33 +472,55 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(__uint_as_float(yv[2 * e]), __uint_as_float(yv[2 * e + 1]));
                 const uint32_t c0 = (uint32_t)(i & 3) * 2u;
-                const uint32_t base = srow + (uint32_t)(i >> 2) * kChunkBytes;
+                const uint32_t base = srow + (uint32_t)((i >> 2) % kSlots) * kChunkBytes;
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((c0 ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((c0 + 1) ^ sw) << 4)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + (i >> 2)));
+                if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + (i >> 2) % kSlots));
             }
             if (q == 2) AFA_TC_STAMP(1 + grp, j, 2);
+            if ((j & 3) == 0 && ((j + 8) >> 2) < NCH_IN) patch_chunk((j + 8) >> 2);      // group 0 only: j even
             if (j <= NY) {
-                uint32_t u[32];
-                tmem_ld32(tlane + kColUS + 32 * slot, u);
+                // U(j) in two halves of 16 columns: the second load is in flight while the first half goes through Snake, and
+                // only 16 fp32 values are live at a time (the register budget of two CTAs per SM is 80 per thread)
+                uint32_t sp[16];
+                uint32_t ua[16], ub[16];
+                tmem_ld16(tlane + kColUS + 32 * slot, ua);
                 tmem_wait_ld();
+                tmem_ld16(tlane + kColUS + 32 * slot + 16, ub);
                 if (a.debug == 1 && row < a.rows) {
-                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)((kNYMax + 1) * 32) + j * 32;
+                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 32) + j * 32;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) d[e] = __uint_as_float(u[e]);
+                    for (int e = 0; e < 16; ++e) d[e] = __uint_as_float(ua[e]);
                 }
                 // Snake on packed pairs: s = u + ib * sin^2(a u)      activations.py:60, :124
-                uint32_t sp[16];
+                auto snake8 = [&](const uint32_t (&u)[16], int h) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float2 u2 = make_float2(__uint_as_float(u[2 * e]), __uint_as_float(u[2 * e + 1]));
-                    const float2 th = __fmul2_rn(u2, a2);
-                    const float2 sn = make_float2(__sinf(th.x), __sinf(th.y));
-                    const float2 s2 = __ffma2_rn(ib2, __fmul2_rn(sn, sn), u2);
-                    sp[e] = pack_bf16(s2.x, s2.y);
+                    for (int c = 0; c < 2; ++c) {
+                        float2 u2[4], th[4], sn[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            u2[e] = make_float2(__uint_as_float(u[8 * c + 2 * e]), __uint_as_float(u[8 * c + 2 * e + 1]));
+                            th[e] = __fmul2_rn(u2[e], a2);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) sn[e] = make_float2(__sinf(th[e].x), __sinf(th[e].y));
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 s2 = __ffma2_rn(ib2, __fmul2_rn(sn[e], sn[e]), u2[e]);
+                            sp[8 * h + 4 * c + e] = pack_bf16(s2.x, s2.y);
+                        }
+                    }
+                };
+                snake8(ua, 0);
+                tmem_wait_ld();
+                if (a.debug == 1 && row < a.rows) {
+                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 32) + j * 32 + 16;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) d[e] = __uint_as_float(ub[e]);
                 }
+                snake8(ub, 1);
                 // replicate padding of the ACTIVATED signal (filter.py:98), in the 2x domain; rare -> uniform branch
                 const int eb = 2 * (T - t_org) - 32 * j - 6;      // element of n = 2T in this block: 10 or 26 when inside
                 if (__any_sync(0xffffffffu, (left_lane && j == 0) || eb == 10 || eb == 26)) {
@@ -495,7 +540,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     }
                 }
                 if (a.debug == 2 && row < a.rows) {
-                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)((kNYMax + 1) * 32) + j * 32;
+                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 32) + j * 32;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         d[2 * e] = __uint_as_float(sp[e] << 16);
@@ -514,7 +559,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) AFA_TC_STAMP(0, 31, 3);
+    if (warp == 1) AFA_TC_STAMP(3, 1, 3);
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");

@@ -260,7 +260,7 @@ int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map,
  * which=4: its input staging: chunks = 1 bulk-copy the tile's input rows into shared memory (default), 0 global loads.
  * which=5: tensor-core forward (bf16 tensors, T % 8 == 0, 16-byte aligned x and y: both FIR filters as banded-Toeplitz
  *          tcgen05 products, csrc/afa_tc_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible;
- *          threads = blocks of 16 outputs per TMEM lane (4 / 8 / 12 / 16; 0 = built-in choice).
+ *          threads = blocks of 16 outputs per TMEM lane and CTA (a multiple of 4 up to 4096; 0 = built-in choice).
  * which=6: its rows per CTA as log2 (3..7; -1 = built-in choice).
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
  * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects (which = 5: the tensor-core forward).

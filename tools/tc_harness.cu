@@ -148,7 +148,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dbeta, C * 4));
     CK(cudaMemcpy(dalpha, halpha.data(), C * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbeta, hbeta.data(), C * 4, cudaMemcpyHostToDevice));
-    const size_t dbg_per_cta = (size_t)128 * (afa_tc::kNYMax + 1) * 32;
+    const size_t dbg_per_cta = (size_t)128 * (pny + 1) * 32;
     if (debug) {
         CK(cudaMalloc(&ddbg, (size_t)(rg * ts) * dbg_per_cta * 4));
         CK(cudaMemset(ddbg, 0, (size_t)(rg * ts) * dbg_per_cta * 4));
@@ -174,19 +174,19 @@ int main(int argc, char** argv) {
     if (debug >= 3) {
         const uint32_t* st = reinterpret_cast<const uint32_t*>(hdbg.data());
         uint32_t t0 = 0xffffffffu;
-        for (int i = 0; i < 3 * 32 * 8; ++i) if ((i / 8) % 32 < 30 && st[i] && st[i] < t0) t0 = st[i];
-        printf("first loop stamp at %d cycles after kernel entry\n", (int)(t0 - st[31 * 8]));
+        for (int i = 0; i < 3 * 32 * 8; ++i) if (i < 3 * 32 * 8 && st[i] && st[i] < t0) t0 = st[i];
+        printf("first loop stamp at %d cycles after kernel entry\n", (int)(t0 - st[(3 * 32 + 1) * 8]));
         printf("timeline of CTA %lld (cycles since first stamp); MMA: wait-start, woke, issued | group g: wait-up, woke, U loaded, snake done, arrived, dn woke\n", (long long)(rg * ts / 2));
-        for (int j = 0; j <= pny + 1; ++j) {
+        for (int j = 0; j <= pny + 1 && j < 30; ++j) {
             printf("j=%2d MMA %6d %6d %6d (batch done %6d) | g%d %6d %6d %6d %6d %6d %6d\n", j, st[(0 * 32 + j) * 8 + 0] ? (int)(st[(0 * 32 + j) * 8 + 0] - t0) : -1,
                    st[(0 * 32 + j) * 8 + 1] ? (int)(st[(0 * 32 + j) * 8 + 1] - t0) : -1, st[(0 * 32 + j) * 8 + 2] ? (int)(st[(0 * 32 + j) * 8 + 2] - t0) : -1, st[(0 * 32 + j) * 8 + 3] ? (int)(st[(0 * 32 + j) * 8 + 3] - t0) : -1, j & 1,
                    st[((1 + (j & 1)) * 32 + j) * 8 + 0] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 0] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 1] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 1] - t0) : -1,
                    st[((1 + (j & 1)) * 32 + j) * 8 + 2] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 2] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 3] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 3] - t0) : -1,
                    st[((1 + (j & 1)) * 32 + j) * 8 + 4] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 4] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 5] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 5] - t0) : -1);
         }
-        { uint32_t e0 = st[(0 * 32 + 31) * 8 + 0]; t0 = e0;
-          printf("setup: TMA issued / alloc start %d, alloc done %d, B-gen start %d, B-gen done %d\n", (int)(st[30 * 8 + 0] - t0), (int)(st[30 * 8 + 1] - t0), (int)(st[30 * 8 + 2] - t0), (int)(st[30 * 8 + 3] - t0));
-          printf("lifetime: entry 0, setup done %d, loop done (MMA warp) %d, final sync %d, stores read %d\n", (int)(st[(31) * 8 + 1] - t0), (int)(st[(31) * 8 + 2] - t0), (int)(st[(31) * 8 + 3] - t0), (int)(st[(31) * 8 + 4] - t0)); }
+        { uint32_t e0 = st[(3 * 32 + 1) * 8 + 0]; t0 = e0;
+          printf("setup: TMA issued / alloc start %d, alloc done %d, B-gen start %d, B-gen done %d\n", (int)(st[(3 * 32 + 0) * 8 + 0] - t0), (int)(st[(3 * 32 + 0) * 8 + 1] - t0), (int)(st[(3 * 32 + 0) * 8 + 2] - t0), (int)(st[(3 * 32 + 0) * 8 + 3] - t0));
+          printf("lifetime: entry 0, setup done %d, loop done (MMA warp) %d, final sync %d, stores read %d\n", (int)(st[(3 * 32 + 1) * 8 + 1] - t0), (int)(st[(3 * 32 + 1) * 8 + 2] - t0), (int)(st[(3 * 32 + 1) * 8 + 3] - t0), (int)(st[(3 * 32 + 1) * 8 + 4] - t0)); }
     }
     // ---- check: a spread of rows (all if few)
     std::vector<int64_t> rows_to_check;
@@ -221,7 +221,7 @@ int main(int argc, char** argv) {
                 for (int g = 0; g < G; ++g) {
                     const int l = g * R + rr;
                     const int t_org = (int)(tsx * G * span + g * span - 8);
-                    const float* d = &hdbg[((size_t)(rgp * ts + tsx) * 128 + l) * (size_t)((afa_tc::kNYMax + 1) * 32)];
+                    const float* d = &hdbg[((size_t)(rgp * ts + tsx) * 128 + l) * (size_t)((pny + 1) * 32)];
                     for (int j = 0; j <= pny; ++j)
                         for (int el = 0; el < 32; ++el) {
                             const int n = 2 * t_org + 32 * j + 6 + el;
