@@ -11,6 +11,8 @@ void count_launch();
 
 // afa_tc.cu: Activation1d forward with both FIR filters on the tensor cores (bf16 I/O, 16-byte aligned rows)
 void tc_set_tuning(int enable, int ny, int rlog2);
+void tc_set_mats(int mats);              // tap matrices per K slice, up * 10 + down: 22 (default), 21; harness also 12, 11
+void tc_set_debug_window(int j0);        // harness: first block of the clock-stamp window
 bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, int64_t T, int dtype);
 void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rgroups, int64_t* n_tstrips);
 int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta, const float* taps_up12,

@@ -31,6 +31,8 @@ EncodeTiledFn encode_fn() {
 int g_tc_enable = 1;      // afa_set_tuning(5, ...): 0 = never take the tensor-core path
 int g_tc_ny = 0;          // forced y blocks per lane (0 = heuristic)
 int g_tc_rlog2 = -1;      // forced log2(rows per CTA) (-1 = heuristic)
+int g_tc_mats = 22;       // tap matrices per K slice, up * 10 + down: 2 = bf16 hi + lo (16 mantissa bits), 1 = taps rounded to bf16
+int g_tc_dbg_j0 = 0;      // harness: first block of the clock-stamp window
 
 // [rows, T] bf16 row-major, box = R rows x 64 samples, 128-byte swizzle, zero fill outside the tensor
 int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) {
@@ -62,9 +64,35 @@ void split_bf16(float v, uint16_t* hi, uint16_t* lo) {
     *lo = bf16_rne(v - hf);
 }
 
+template <int kUp, int kDn, bool kDebug>
+cudaError_t prepare_kernel(int dev) {
+    static bool attr_set[64] = {};
+    if (dev >= 0 && dev < 64 && attr_set[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel<kUp, kDn, kDebug>, cudaFuncAttributeMaxDynamicSharedMemorySize, afa_tc::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    // two CTAs per SM need the largest shared-memory carveout (2 x 88 KB)
+    e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel<kUp, kDn, kDebug>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    return cudaSuccess;
+}
+
+template <int kUp, int kDn, bool kDebug>
+cudaError_t launch_kernel(unsigned grid, cudaStream_t st, const CUtensorMap& tmx, const CUtensorMap& tmy, const afa_tc::Args& a) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = prepare_kernel<kUp, kDn, kDebug>(dev);
+    if (e != cudaSuccess) return e;
+    afa_tc::afa_tc_fwd_kernel<kUp, kDn, kDebug><<<grid, afa_tc::kThreads, afa_tc::kSmemBytes, st>>>(tmx, tmy, a);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 namespace afa_internal {
+
+void tc_set_mats(int mats) { g_tc_mats = (mats == 11 || mats == 12 || mats == 21) ? mats : 22; }
+void tc_set_debug_window(int j0) { g_tc_dbg_j0 = j0; }
 
 void tc_set_tuning(int enable, int ny, int rlog2) {
     g_tc_enable = enable;
@@ -151,6 +179,7 @@ int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta,
     a.x = static_cast<const __nv_bfloat16*>(x);
     a.alpha = alpha;
     a.beta = beta;
+    const int mats = g_tc_mats;
     for (int i = 0; i < 12; ++i) {
         split_bf16(2.0f * taps_up12[i], &a.up_hi[i], &a.up_lo[i]);      // ratio * conv_transpose taps        resample.py:33
         split_bf16(taps_down12[i], &a.dn_hi[i], &a.dn_lo[i]);
@@ -165,42 +194,39 @@ int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta,
     a.debug = debug;
     a.dbg = dbg;
     a.dbg_cta = (int32_t)(rg * ts / 2);
-    a.dbg_blocks = ny + 1;
-    static thread_local bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, afa_tc::kSmemBytes);
-        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel)");
-        // two CTAs per SM need the largest shared-memory carveout (2 x 88 KB)
-        e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel, carveout)");
-        attr_set[dev] = true;
-    }
-    afa_tc::afa_tc_fwd_kernel<<<(unsigned)(rg * ts), afa_tc::kThreads, afa_tc::kSmemBytes, st>>>(tmx, tmy, a);
+    a.dbg_blocks = ny / 2 + 1;
+    a.dbg_j0 = g_tc_dbg_j0;
+    cudaError_t e;
+    const unsigned grid = (unsigned)(rg * ts);
+#ifdef AFA_TC_HARNESS
+    if (debug) e = mats == 22 ? launch_kernel<2, 2, true>(grid, st, tmx, tmy, a) : launch_kernel<2, 1, true>(grid, st, tmx, tmy, a);
+    else if (mats == 11) e = launch_kernel<1, 1, false>(grid, st, tmx, tmy, a);
+    else if (mats == 12) e = launch_kernel<1, 2, false>(grid, st, tmx, tmy, a);
+    else
+#endif
+        e = mats == 22 ? launch_kernel<2, 2, false>(grid, st, tmx, tmy, a) : launch_kernel<2, 1, false>(grid, st, tmx, tmy, a);
     count_launch();
-    cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_error(e, "afa_tc_fwd_kernel launch");
 }
 
-int tc_kernel_info(int32_t out[6]) {
+template <int kUp, int kDn>
+static int kernel_info_t(int32_t out[6]) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, afa_tc::afa_tc_fwd_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, afa_tc::afa_tc_fwd_kernel<kUp, kDn, false>);
     if (e != cudaSuccess) return cuda_error(e, "cudaFuncGetAttributes(afa_tc_fwd_kernel)");
-    e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, afa_tc::kSmemBytes);
+    e = prepare_kernel<kUp, kDn, false>(-1);
     if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel)");
-    e = cudaFuncSetAttribute(afa_tc::afa_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(afa_tc_fwd_kernel, carveout)");
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, afa_tc::afa_tc_fwd_kernel, afa_tc::kThreads, afa_tc::kSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, afa_tc::afa_tc_fwd_kernel<kUp, kDn, false>, afa_tc::kThreads, afa_tc::kSmemBytes);
     if (e != cudaSuccess) return cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     out[0] = fa.numRegs;
     out[1] = (int32_t)(fa.sharedSizeBytes + afa_tc::kSmemBytes);
     out[2] = afa_tc::kThreads;
-    out[3] = 16;                     // outputs per block; blocks per lane are chosen per launch
+    out[3] = 32;                     // outputs per block; blocks per lane are chosen per launch
     out[4] = occ;
     out[5] = 0;
     return 0;
 }
+int tc_kernel_info(int32_t out[6]) { return g_tc_mats == 22 ? kernel_info_t<2, 2>(out) : kernel_info_t<2, 1>(out); }
 
 }  // namespace afa_internal

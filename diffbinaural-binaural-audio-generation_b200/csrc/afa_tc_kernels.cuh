@@ -1,5 +1,5 @@
 // afa_tc_kernels.cuh -- fused Activation1d (bf16 I/O) with BOTH FIR filters on the 5th-generation tensor cores
-// (tcgen05.mma, accumulators and the A operands in TMEM), sm_100a.
+// (tcgen05.mma, accumulators and the down filter's A operand in TMEM), sm_100a.
 //
 // What it replaces (reference, /root/reference/BigVGAN): alias_free_activation/act.py:25-30 =
 // resample.py:29-38 (UpSample1d) + activations.py:51-62 / 113-126 (Snake / SnakeBeta) + filter.py:94-101
@@ -7,40 +7,42 @@
 //
 // Why: the register-walk kernel of afa_kernels.cuh spends 24 of its 27 instructions per output on the two
 // 12-tap FIRs and is bound by the FP32 FMA pipe -- at bf16 I/O it reaches 0.29-0.44 of the HBM roofline
-// (VERDICT round 1).  The FIRs are linear and shift invariant, so a block of 16 time steps of 128 rows is a
-// product with a small CONSTANT banded Toeplitz matrix:
+// (VERDICT round 1).  The FIRs are linear and shift invariant, so a block of 32 time steps of 128 rows is a
+// product with a small CONSTANT banded Toeplitz matrix (K = 16 samples per tcgen05.mma):
 //
-//   U_j  [128 rows x 32 u-values]  =  X_j  [128 x 16] * Wup_a [16 x 32]  +  X_j+1 [128 x 16] * Wup_b [16 x 32]
-//   Y_i  [128 rows x 16 outputs ]  =  S_2i [128 x 16] * Wdn_a [16 x 16]  +  S_2i+1 * Wdn_b  +  S_2i+2 * Wdn_c
+//   U_b [128 rows x 64 u-values] = sum_{k<3} X_{2b+k} [128 x 16] * Wup_k [16 x 64]        (x slices of 16 samples)
+//   Y_b [128 rows x 32 outputs ] = sum_{k<5} S_{4b+k} [128 x 16] * Wdn_k [16 x 32]        (s slices of 16 values)
 //
-// with M = 128 rows of the tensor (one TMEM lane each), K = 16 consecutive time samples, N = the block's
-// outputs.  Only Snake (2 MUFU + 5 FMA-pipe instructions per output) stays on the CUDA cores.
+// with M = 128 rows of the tensor (one TMEM lane each) and N = the block's outputs.  Only Snake (2 MUFU + 6
+// FMA-pipe instructions per output) stays on the CUDA cores.
 //   * taps are split hi + lo into two bf16 matrices (16 mantissa bits), both products accumulate in fp32 in
 //     TMEM; x is bf16 by contract, so U is exact to fp32 rounding.  s is rounded to bf16 once, as the A operand
-//     of the down filter (the same rounding step the bf16 output applies anyway).
-//   * A operands come from TENSOR MEMORY: a lane's x slice is copied shared -> registers -> TMEM by the thread
-//     that owns the lane (tcgen05.st; replicate padding is patched in registers on the way), and the activated
-//     block S_j overwrites the first half of the accumulator U_j it was computed from.  Shared memory therefore
-//     sees each byte of x and y exactly once plus the small B matrices: the MMAs' operand traffic would
-//     otherwise exceed the 128 B/clk shared-memory port at the HBM roofline.
+//     of the down filter (the same rounding step the bf16 output applies anyway).  (A single fp16 tap matrix
+//     against bf16 activations is rejected by the hardware -- "illegal instruction" -- although the descriptor
+//     has separate format fields; kMats = 1 uses the bf16 hi part alone and exists for measurements.)
+//   * up filter in SS mode: A = the x slices straight from the 128-byte swizzled chunks the tensor-map TMA
+//     wrote (no thread touches x).  Down filter in TS mode: A = S from TENSOR MEMORY.  Shared memory therefore
+//     sees each byte of x and y once plus the operand reads of the up filter.
+//   * tensor memory: 4 slots of 64 columns.  up(b) fills slot b % 4 with U_b (64 fp32).  Snake reads it and writes
+//     S_b (64 bf16) over columns 0..31; down(b) then puts Y_b (32 fp32) into columns 32..63 of the SAME slot --
+//     the half of U_b that is dead by then -- so the output accumulators cost no columns of their own.
 //   * a CTA owns 128 lanes = R rows x G time groups (R * G = 128; R = 16 for one binaural clip at C = 24) and
-//     NY blocks of 16 outputs per lane.  x arrives as 64-sample (128-byte, 128B-swizzled) chunks by tensor-map
-//     TMA, out-of-range samples and rows are zero-filled by the TMA unit; y leaves through the same chunks in
-//     place (TMA store clips what lies outside the tensor).
-//   * warp roles: warp 0 = TMA producer / TMEM allocator / TMA store; warp 1 = MMA issuer (one thread);
-//     warps 2-9 = two compute groups of four warps (one thread per TMEM lane) that ping-pong over the blocks:
-//     tcgen05.ld U_j -> Snake -> tcgen05.st S_j, next x slice -> TMEM, drain Y_j-2 -> shared memory.  All
-//     hand-offs are mbarriers (tcgen05.commit on the MMA side); no CTA-wide barrier inside the block loop.
+//     NY / 2 blocks of 32 outputs per lane.  x arrives as 64-sample chunks through a recycled ring of 5 slots;
+//     out-of-range samples and rows are zero-filled by the TMA unit; y leaves through the same chunks in place
+//     (TMA store clips what lies outside the tensor).
+//   * warp roles: warp 0 = TMA producer / TMEM allocator / TMA store; warp 1 = MMA issuer (one elected thread);
+//     warps 2-9 = two compute groups of four warps (one thread per TMEM lane) that alternate over the blocks.
+//     All hand-offs are mbarriers (tcgen05.commit on the MMA side); no CTA-wide barrier inside the block loop.
 //
 // Index algebra (t_org = the lane's first staged sample, t_org % 8 == 0, first output t_org + 8):
 //   x slice k   : x_ext[t_org + 16k + (0..15)]
-//   u block j   : u_ext[n0 + e], n0 = 2*t_org + 32j + 6, e = 0..31;  u[n] = 2 * sum_i f[n + 5 - 2i] * x_ext[i]
-//                 -> Wup[kappa][e] = 2 f[e + 11 - 2 kappa],  kappa = 0..31 over slices j, j+1
-//   y block i   : y[t_org + 8 + 16i + e], e = 0..15;  y[t] = sum_k f[k] * s_ext[2t + k - 5]
-//                 -> Wdn[kappa][e] = f[kappa - 2e - 5],  kappa = 0..47 over the s slices of u blocks i, i+1
+//   u block b   : u_ext[n0 + e], n0 = 2*t_org + 64b + 6, e = 0..63;  u[n] = 2 * sum_i f[n + 5 - 2i] * x_ext[i]
+//                 -> Wup[kappa][e] = 2 f[e + 11 - 2 kappa],  kappa = 0..47 over slices 2b, 2b+1, 2b+2
+//   y block b   : y[t_org + 8 + 32b + e], e = 0..31;  y[t] = sum_k f[k] * s_ext[2t + k - 5]
+//                 -> Wdn[kappa][e] = f[kappa - 2e - 5],  kappa = 0..79 over the 4 s slices of block b and the first of b+1
 //   replicate padding: x_ext clamps in the 1x domain (chunks with t < 0 or t >= T, always whole 8-sample
 //   chunks because T % 8 == 0); s_ext clamps the ACTIVATED signal in the 2x domain (filter.py:98): elements
-//   e < 10 of block 0 of a row's first lane, and elements e >= e_b (e_b = 10 or 26) of the block holding 2T.
+//   e < 10 of block 0 of a row's first lane, and elements e >= e_b (e_b = 10, 26, 42 or 58) of the block holding 2T.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -52,14 +54,15 @@ namespace afa_tc {
 constexpr int kThreads = 320;            // warp 0: TMA producer / TMEM allocator / TMA store, warp 1: MMA, warps 2..9: compute
 constexpr int kSlots = 5;                // shared-memory chunk ring: slots of 64 samples x 128 lanes, recycled along the strip
 constexpr int kChunkBytes = 128 * 128;   // 128 lanes x 64 bf16
-constexpr int kTmemCols = 256;           // 240 used; allocations are powers of two
-constexpr int kRing = 5;                 // slots of the U / S and Y rings
-constexpr int kColUS = 0;                // U / S ring: 5 slots x 32 columns (U fp32; S = 32 bf16 in the first 16)
-constexpr int kColY = 160;               // Y ring: 5 slots x 16 columns
+constexpr int kTmemCols = 256;           // 4 slots x 64 columns
+constexpr int kRing = 4;                 // tensor-memory slots: U(b) = 64 fp32 columns; then S(b) = 64 bf16 in columns 0..31 and
+constexpr int kSlotCols = 64;            //   Y(b) = 32 fp32 outputs in columns 32..63 (the half of U that Snake has consumed)
+constexpr int kUpSlices = 3, kDnSlices = 5;          // K = 16 slices per product: 64 u need 38 samples, 32 y need 75 s-values
+constexpr int kWupBytes = 64 * 16 * 2, kWdnBytes = 32 * 16 * 2;
 // shared memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int kOffWup = kSlots * kChunkBytes;           // [hi/lo][slice a/b] x (32 x 16 bf16 = 1024 B)
-constexpr int kOffWdn = kOffWup + 4 * 1024;              // [hi/lo][slice a/b/c] x (16 x 16 bf16 = 512 B)
-constexpr int kOffBar = kOffWdn + 6 * 512;
+constexpr int kOffWup = kSlots * kChunkBytes;                    // [hi/lo][slice] x (64 x 16 bf16 = 2048 B)
+constexpr int kOffWdn = kOffWup + 2 * kUpSlices * kWupBytes;     // [hi/lo][slice] x (32 x 16 bf16 = 1024 B)
+constexpr int kOffBar = kOffWdn + 2 * kDnSlices * kWdnBytes;
 constexpr int kBarFull = 0, kBarPre = kSlots, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 8, kBarOut = kBarEv + 8;
 constexpr int kNumBars = kBarOut + kSlots;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
@@ -69,15 +72,16 @@ struct Args {
     const __nv_bfloat16* x;
     const float* alpha;
     const float* beta;
-    uint16_t up_hi[12], up_lo[12];   // 2 * upsample taps (ratio folded, resample.py:33) as bf16 hi + lo
-    uint16_t dn_hi[12], dn_lo[12];   // low-pass taps as bf16 hi + lo
+    uint16_t up_hi[12], up_lo[12];   // 2 * upsample taps (ratio folded, resample.py:33): bf16 hi + lo, or fp16 in up_hi (kMats = 1)
+    uint16_t dn_hi[12], dn_lo[12];   // low-pass taps, same split
     int32_t rows, C, T, flags;
     int32_t R_log2;        // lanes = R rows x G groups, R = 1 << R_log2
-    int32_t NY;            // y blocks (16 outputs) per lane and CTA: a multiple of 4, any length (the chunk ring is recycled)
+    int32_t NY;            // outputs per lane and CTA in units of 16: a multiple of 4, any length (the chunk ring is recycled)
     int32_t n_tstrips;     // CTAs along time; blockIdx.x = row_group * n_tstrips + tstrip
     int32_t debug;         // harness only: 1 = dump U blocks, 2 = dump S, 3 = clock stamps of CTA dbg_cta
     int32_t dbg_cta;
-    int32_t dbg_blocks;    // harness: blocks per lane the U / S dump holds (NY + 1)
+    int32_t dbg_blocks;    // harness: 64-value blocks per lane the U / S dump holds (NY / 2 + 1)
+    int32_t dbg_j0;        // harness: first block of the 32-block window the clock stamps cover
     float* dbg;
 };
 
@@ -195,7 +199,7 @@ __device__ __forceinline__ uint32_t clk32() {
     return c;
 }
 // harness timeline (debug == 3): dbg[(role * 32 + j) * 8 + slot] = clock, for CTA `dbg_cta`
-#define AFA_TC_STAMP(role, j, slot) do { if (a.debug >= 3 && lane == 0 && (j) < 32 && blockIdx.x == (unsigned)a.dbg_cta) a.dbg[((role) * 32 + (j)) * 8 + (slot)] = __uint_as_float(clk32()); } while (0)
+#define AFA_TC_STAMP(role, j, slot) do { if (kDebug) { const int jw_ = (j) - ((role) == 3 ? 0 : a.dbg_j0); if (a.debug >= 3 && lane == 0 && jw_ >= 0 && jw_ < 32 && blockIdx.x == (unsigned)a.dbg_cta) a.dbg[((role) * 32 + jw_) * 8 + (slot)] = __uint_as_float(clk32()); } } while (0)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -206,34 +210,43 @@ __device__ __forceinline__ float snake_f(float u, float a, float ib) {
     return fmaf(ib, sn * sn, u);
 }
 
-// Schedule.  Block j = 16 time steps of the CTA's 128 lanes.  Compute group g (4 warps) owns the blocks j = g (mod 2).
-//   MMA thread, event j:        wait cmp[j & 7] (S(j) is in TMEM);  down(j-1) [S(j-1), S(j) from TMEM -> Y slot (j-1) % 5];
-//                               up(j+4) [x slices j+4, j+5 straight from the swizzled shared-memory chunks -> U slot (j+4) % 5];
-//                               ONE commit -> ev[(j+4) & 7]  (tcgen05.commit tracks every MMA issued before it)
-//   iteration j of its group:   wait ev[j & 7]  (event j-4 committed: up(j) and down(j-5) are complete)
-//                               drain Y(j-5) -> bf16 -> shared memory (out chunk (j-5)/4, over x slice j-5), arrive out[(j-5)/4]
-//                               U(j) -> registers -> Snake -> S(j) over U(j) -> arrive cmp[j & 7]
-//   warp 0:                     wait out[q] (16 warp arrivals) -> TMA store of out chunk q
-// The lookahead of 4 blocks is what hides the MMA round trip (arrive -> issue -> execute -> commit -> wake, about one block
-// time): with 3 both sides were found waiting on each other (profiles/r02_tc_ncu_full_fwd_bf16_B16_C384_T13776.txt).
-// Ring safety: up(j+4) lands on U/S slot (j-1) % 5 = S(j-1), last read by down(j-1), issued immediately before it (MMAs of one
-// thread execute in issue order).  down(i) lands on Y(i-5), drained at iteration i before that iteration's arrive on cmp[i & 7],
-// which the MMA thread has consumed before event i+1.  y block i overwrites x slice i, last read by up(i), complete since event
-// i-4.  cmp / ev are rings of 8 indexed by the block, not per group: a warp's ev wait depends on event j-4 only, so it may run
-// iterations ahead of a slower warp of its group; it cannot be 8 blocks ahead, because event j+4 needs cmp[j] complete.
+// Schedule.  Block b = 32 time steps of the CTA's 128 lanes (64 u-values, 32 outputs per lane).  Compute group g (4 warps)
+// owns the blocks b = g (mod 2).  Tensor-memory slot of block b: b % 4.
+//   MMA thread, event e:        wait cmp[e & 7]  (S(e) is in TMEM and Y(e-2) has been read out of slot (e+2) % 4);
+//                               down(e-1): S(e-1) and the first slice of S(e) -> Y(e-1) in columns 32..63 of slot (e-1) % 4;
+//                               up(e+2): x slices 2e+4 .. 2e+6 straight from the swizzled chunks -> U(e+2) in slot (e+2) % 4;
+//                               ONE commit -> ev[(e+2) & 7]  (tcgen05.commit tracks every MMA issued before it)
+//   iteration b of its group:   wait ev[b & 7]  (event b-2: U(b) is complete)
+//                               U(b) -> registers (4 loads of 16 columns, the next in flight behind the math) -> Snake ->
+//                               S(b) over columns 0..31 (two tcgen05.st)
+//                               wait ev[(b+1) & 7]  (event b-1: Y(b-2) is complete) -> registers -> bf16 -> shared memory (in
+//                               place over x slices 2b-4, 2b-3 of out chunk (b-2)/2) -> proxy fence -> arrive out[...]
+//                               tcgen05.wait::st -> arrive cmp[b & 7]
+//   warp 0:                     wait out[q] (8 warp arrivals) -> TMA store of out chunk q -> the slot takes x chunk q + 5
+// One barrier round trip, one tensor-memory store wait and one proxy fence now cover 32 outputs per lane (16 in the first
+// versions: the fixed latencies of an iteration, ~1300 cycles, outweighed its ~900 cycles of Snake math).
+// Ring safety: up(e+2) overwrites slot (e-2) % 4: S(e-2) was last read by down(e-2), issued at event e-1 by the same thread
+// (MMAs execute in issue order); Y(e-2) was read by iteration e of group e % 2 before its arrive on cmp[e & 7].  down(b)
+// writes columns 32..63 of slot b: the upper half of U(b), in registers since iteration b.  y block i overwrites x slices 2i,
+// 2i+1, last read by up(i), complete since event i-2.  cmp / ev are rings of 8 indexed by block / event: a warp's waits depend
+// on events b-2 and b-1 only, so it may run ahead of a slower warp of its group, never 8 events ahead (event e needs cmp[e]).
+// kUpMats / kDnMats: tap matrices per K slice of the up / down filter -- 2 = bf16 hi + lo (16 mantissa bits), 1 = the taps
+// rounded to bf16 (8 bits).  kDebug: harness dumps and clock stamps; compiled out of the product instantiation.
 #ifndef AFA_TC_BOUND_THREADS
-#define AFA_TC_BOUND_THREADS 384
+#define AFA_TC_BOUND_THREADS 320
 #endif
+template <int kUpMats, int kDnMats, bool kDebug>
 __global__ void __launch_bounds__(AFA_TC_BOUND_THREADS, 2)
 afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                   const __grid_constant__ Args a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: role code runs on the uniform datapath
     if (warp == 1) AFA_TC_STAMP(3, 1, 0);
-    const int NY = a.NY;
-    const int NCH_IN = (NY + 2 + 3) >> 2, NCH_OUT = NY >> 2;       // x chunks / out chunks of this CTA's strip
+    const int NY = a.NY, NB = NY >> 1;                            // NB blocks of 32 outputs per lane
+    const int NCH_IN = (NY >> 2) + 1, NCH_OUT = NY >> 2;          // x chunks (slices 0 .. NY + 2) / out chunks of this CTA's strip
     const int R = 1 << a.R_log2, G = 128 >> a.R_log2;
     const int tstrip = (int)(blockIdx.x % (uint32_t)a.n_tstrips);
     const int rgroup = (int)(blockIdx.x / (uint32_t)a.n_tstrips);
@@ -258,7 +271,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_init(bars + 8 * kBarPre, 8);
             for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarCmp + i), 4);
             for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEv + i), 1);
-            for (int i = 0; i < kSlots; ++i) mbar_init(bars + 8 * (kBarOut + i), 16);
+            for (int i = 0; i < kSlots; ++i) mbar_init(bars + 8 * (kBarOut + i), 8);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
         }
@@ -273,27 +286,27 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (warp == 1) AFA_TC_STAMP(3, 0, 2);
         const int t2 = tid - 32;                                   // 0 .. 287
         uint4* wz = reinterpret_cast<uint4*>(sgen + kOffWup);
-        for (int i = t2; i < (4 * 1024 + 6 * 512) / 16; i += kThreads - 32) wz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = t2; i < (kOffBar - kOffWup) / 16; i += kThreads - 32) wz[i] = make_uint4(0, 0, 0, 0);
         asm volatile("bar.sync 1, 288;" ::: "memory");
         uint16_t* wup = reinterpret_cast<uint16_t*>(sgen + kOffWup);
         uint16_t* wdn = reinterpret_cast<uint16_t*>(sgen + kOffWdn);
-        for (int i = t2; i < 32 * 6 + 16 * 12; i += kThreads - 32) {
-            if (i < 192) {                                          // up: column e, i-th tap of its phase: tap = e + 11 - 2 kappa
+        for (int i = t2; i < 64 * 6 + 32 * 12; i += kThreads - 32) {
+            if (i < 384) {                                          // up: column e, i-th tap of its phase: tap = e + 11 - 2 kappa
                 const int e = i / 6, ii = i - e * 6;
                 const int tap = ((e + 11) & 1) + 2 * ii;
-                const int kappa = (e + 11 - tap) >> 1;              // 0 .. 21 over slices a (0..15), b (16..31)
+                const int kappa = (e + 11 - tap) >> 1;              // 0 .. 37 over slices 0 .. 2
+                const int sl = kappa >> 4, k = kappa & 15;
+                const int off = (k >> 3) * (64 * 8) + e * 8 + (k & 7);
+                wup[(0 * kUpSlices + sl) * (kWupBytes / 2) + off] = a.up_hi[tap];
+                if (kUpMats == 2) wup[(1 * kUpSlices + sl) * (kWupBytes / 2) + off] = a.up_lo[tap];
+            } else {                                                // down: column e, tap: kappa = 2 e + 5 + tap
+                const int i2 = i - 384;
+                const int e = i2 / 12, tap = i2 - e * 12;
+                const int kappa = 2 * e + 5 + tap;                  // 5 .. 78 over slices 0 .. 4
                 const int sl = kappa >> 4, k = kappa & 15;
                 const int off = (k >> 3) * (32 * 8) + e * 8 + (k & 7);
-                wup[(0 * 2 + sl) * 512 + off] = a.up_hi[tap];
-                wup[(1 * 2 + sl) * 512 + off] = a.up_lo[tap];
-            } else {                                                // down: column e, tap: kappa = 2 e + 5 + tap
-                const int i2 = i - 192;
-                const int e = i2 / 12, tap = i2 - e * 12;
-                const int kappa = 2 * e + 5 + tap;                  // 5 .. 46 over slices a, b, c
-                const int sl = kappa >> 4, k = kappa & 15;
-                const int off = (k >> 3) * (16 * 8) + e * 8 + (k & 7);
-                wdn[(0 * 3 + sl) * 256 + off] = a.dn_hi[tap];
-                wdn[(1 * 3 + sl) * 256 + off] = a.dn_lo[tap];
+                wdn[(0 * kDnSlices + sl) * (kWdnBytes / 2) + off] = a.dn_hi[tap];
+                if (kDnMats == 2) wdn[(1 * kDnSlices + sl) * (kWdnBytes / 2) + off] = a.dn_lo[tap];
             }
         }
         if (warp == 1) AFA_TC_STAMP(3, 0, 3);
@@ -302,7 +315,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     if (warp == 1) AFA_TC_STAMP(3, 1, 1);
 
     if (warp == 0) {
@@ -331,72 +344,72 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // InstrDescriptor: D f32 [4,6) = 1, A bf16 [7,10) = 1, B bf16 [10,13) = 1, K-major both, N >> 3 [17,23), M >> 4 [24,29)
-        constexpr uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-        constexpr uint32_t idesc_dn = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t bup = bdesc_kmajor(sbase + kOffWup, 32 * 16);     // + 64 (1024 B >> 4) per matrix
-        const uint64_t bdn = bdesc_kmajor(sbase + kOffWdn, 16 * 16);     // + 32 (512 B >> 4) per matrix
-        const uint64_t ax = adesc_sw128(sbase);                          // x slice k: + (k / 4) * 1024 + (k % 4) * 2 (16-byte units)
-        auto xdesc = [&](int k) { return ax + (uint64_t)(((k >> 2) % kSlots) * (kChunkBytes >> 4) + (k & 3) * 2); };
-        // loop-invariant B descriptors (hi / lo halves of every K slice), kept in registers
-        const uint64_t bu_a_hi = bup + 0 * 64, bu_b_hi = bup + 1 * 64, bu_a_lo = bup + 2 * 64, bu_b_lo = bup + 3 * 64;
-        const uint64_t bd_a_hi = bdn + 0 * 32, bd_b_hi = bdn + 1 * 32, bd_c_hi = bdn + 2 * 32;
-        const uint64_t bd_a_lo = bdn + 3 * 32, bd_b_lo = bdn + 4 * 32, bd_c_lo = bdn + 5 * 32;
-        auto up = [&](uint32_t d, uint64_t xa, uint64_t xb) {
-            mma_ss(d, xa, bu_a_hi, idesc_up, 0);
-            mma_ss(d, xa, bu_a_lo, idesc_up, 1);
-            mma_ss(d, xb, bu_b_hi, idesc_up, 1);
-            mma_ss(d, xb, bu_b_lo, idesc_up, 1);
+        constexpr uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc_dn = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bup = bdesc_kmajor(sbase + kOffWup, 64 * 16);     // + kWupBytes >> 4 per matrix; the lo set follows the hi set
+        const uint64_t bdn = bdesc_kmajor(sbase + kOffWdn, 32 * 16);     // + kWdnBytes >> 4 per matrix
+        const uint64_t ax = adesc_sw128(sbase);                          // x slice k: chunk slot (k / 4) % kSlots, + (k % 4) * 32 bytes
+        // U(bu) <- x slices 2 bu .. 2 bu + 2; xs = ring slot of the chunk that holds slice 2 bu
+        auto up = [&](uint32_t d, int bu, int xs) {
+            const int xs1 = xs + 1 == kSlots ? 0 : xs + 1;
+            uint64_t xd[3];
+            if (bu & 1) {                                                // sub-slices 2, 3 of the chunk, 0 of the next
+                xd[0] = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 4);
+                xd[1] = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 6);
+                xd[2] = ax + (uint64_t)(xs1 * (kChunkBytes >> 4));
+            } else {                                                     // sub-slices 0, 1, 2
+                xd[0] = ax + (uint64_t)(xs * (kChunkBytes >> 4));
+                xd[1] = xd[0] + 2;
+                xd[2] = xd[0] + 4;
+            }
+#pragma unroll
+            for (int k = 0; k < kUpSlices; ++k) {
+                mma_ss(d, xd[k], bup + (uint64_t)(k * (kWupBytes >> 4)), idesc_up, k > 0);
+                if (kUpMats == 2) mma_ss(d, xd[k], bup + (uint64_t)((kUpSlices + k) * (kWupBytes >> 4)), idesc_up, 1);
+            }
         };
-        auto down = [&](uint32_t d, uint32_t s0, uint32_t s2) {
-            mma_ts(d, s0, bd_a_hi, idesc_dn, 0);
-            mma_ts(d, s0, bd_a_lo, idesc_dn, 1);
-            mma_ts(d, s0 + 8, bd_b_hi, idesc_dn, 1);
-            mma_ts(d, s0 + 8, bd_b_lo, idesc_dn, 1);
-            mma_ts(d, s2, bd_c_hi, idesc_dn, 1);
-            mma_ts(d, s2, bd_c_lo, idesc_dn, 1);
+        // Y(bd) <- the four s slices of S(bd) (columns 0, 8, 16, 24 of its slot) and the first of S(bd + 1)
+        auto down = [&](int bd) {
+            const uint32_t sl0 = tmem + (uint32_t)(kSlotCols * (bd & 3)), sl1 = tmem + (uint32_t)(kSlotCols * ((bd + 1) & 3));
+            const uint32_t d = sl0 + 32;
+#pragma unroll
+            for (int k = 0; k < kDnSlices; ++k) {
+                const uint32_t aa = k < 4 ? sl0 + 8u * k : sl1;
+                mma_ts(d, aa, bdn + (uint64_t)(k * (kWdnBytes >> 4)), idesc_dn, k > 0);
+                if (kDnMats == 2) mma_ts(d, aa, bdn + (uint64_t)((kDnSlices + k) * (kWdnBytes >> 4)), idesc_dn, 1);
+            }
         };
         // the compute threads have patched the replicate padding of x into the chunks that hold a row end (pre barrier); the
         // chunks themselves are awaited here, in the order the up-filter products need them
         mbar_wait(bars + 8 * kBarPre, 0);
         mbar_wait(bars + 8 * (kBarFull + 0), 0);
-        mbar_wait(bars + 8 * (kBarFull + 1), 0);                        // up(3) reads slice 4 (NY >= 4: two chunks at least)
+        mbar_wait(bars + 8 * (kBarFull + 1), 0);                        // up(1) reads slice 4 (NY >= 4: two chunks at least)
         int nfull = 2;
         tc_fence_after();
-        if (elect_one()) {                                   // events -4 .. -1
-            up(tmem + kColUS + 0, xdesc(0), xdesc(1)); tc_commit(bars + 8 * (kBarEv + 0));
-            up(tmem + kColUS + 32, xdesc(1), xdesc(2)); tc_commit(bars + 8 * (kBarEv + 1));
-            up(tmem + kColUS + 64, xdesc(2), xdesc(3)); tc_commit(bars + 8 * (kBarEv + 2));
-            up(tmem + kColUS + 96, xdesc(3), xdesc(4)); tc_commit(bars + 8 * (kBarEv + 3));
+        if (elect_one()) {                                   // events -2, -1
+            up(tmem + 0 * kSlotCols, 0, 0); tc_commit(bars + 8 * (kBarEv + 0));
+            up(tmem + 1 * kSlotCols, 1, 0); tc_commit(bars + 8 * (kBarEv + 1));
         }
         __syncwarp();
-        int sl_dn = kRing - 1, sl_s2 = 0, sl_up = 4;       // ring slots of blocks j-1, j, j+4
-        for (int j = 0; j <= NY; ++j) {
-            AFA_TC_STAMP(0, j, 0);
-            if (j + 4 <= NY) {
-                const int p = (j + 5) >> 2;                  // chunk of slice j+5
+        int xs = 1;                                          // ring slot of the chunk holding slice 2 (e + 2) = chunk (e + 2) / 2
+        for (int e = 0; e <= NB; ++e) {
+            AFA_TC_STAMP(0, e, 0);
+            const int bu = e + 2;
+            if (bu <= NB) {
+                const int p = (bu + 1) >> 1;                 // chunk of slice 2 bu + 2
                 while (nfull <= p) { mbar_wait(bars + 8 * (kBarFull + nfull % kSlots), (uint32_t)(nfull / kSlots) & 1u); ++nfull; }
             }
-            mbar_wait(bars + 8 * (kBarCmp + (j & 7)), (uint32_t)(j >> 3) & 1u);
+            mbar_wait(bars + 8 * (kBarCmp + (e & 7)), (uint32_t)(e >> 3) & 1u);
             tc_fence_after();
-            AFA_TC_STAMP(0, j, 1);
-            // addresses of this event, computed by the whole warp (uniform) before the single-thread issue
-            const int ju = j + 4;
-            const uint32_t dd = tmem + kColY + 16 * sl_dn;
-            const uint32_t s0 = tmem + kColUS + 32 * sl_dn, s2 = tmem + kColUS + 32 * sl_s2;
-            const uint32_t du = tmem + kColUS + 32 * sl_up;
-            const uint64_t xa = xdesc(ju), xb = xdesc(ju + 1);
-            const uint32_t evb = bars + 8 * (kBarEv + (ju & 7));
-            sl_dn = sl_s2;
-            sl_s2 = sl_s2 + 1 == kRing ? 0 : sl_s2 + 1;
-            sl_up = sl_up + 1 == kRing ? 0 : sl_up + 1;
-            const bool do_dn = j >= 1, do_up = ju <= NY;
+            AFA_TC_STAMP(0, e, 1);
             if (elect_one()) {
-                if (do_dn) down(dd, s0, s2);
-                if (do_up) up(du, xa, xb);
-                tc_commit(evb);
+                if (e >= 1) down(e - 1);
+                if (bu <= NB) up(tmem + (uint32_t)(kSlotCols * (bu & 3)), bu, xs);
+                tc_commit(bars + 8 * (kBarEv + (bu & 7)));
             }
             __syncwarp();
-            AFA_TC_STAMP(0, j, 2);
+            if (bu & 1) xs = xs + 1 == kSlots ? 0 : xs + 1;      // slice 2 (bu + 1) opens the next chunk when bu is odd
+            AFA_TC_STAMP(0, e, 2);
         }
         AFA_TC_STAMP(3, 1, 2);
     } else {
@@ -425,8 +438,8 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
         // replicate padding of x (resample.py:32), patched into the staged chunks by group 0 (the TMA unit zero-filled what lies
         // outside the tensor): x[0] over the 8 samples before the row, x[T-1] over the 16 samples behind it (3 are read).  Chunk c
-        // is patched after it has landed and before the first product that reads it (up(4c-1), issued at event 4c-5): chunks 0 and
-        // 1 here, chunk c >= 2 at iteration 4c-8 of group 0, ahead of that iteration's arrive on cmp.
+        // is patched after it has landed and before the first product that reads it (up(2c-1), issued at event 2c-3): chunks 0 and
+        // 1 here, chunk c >= 2 at iteration 2c-4 of group 0, ahead of that iteration's arrive on cmp.
         auto patch_chunk = [&](int c) {
             const bool need = row < a.rows && ((left_lane && c == 0) || (right_lane && ((cb >> 3) == c || ((cb + 1) >> 3) == c)));
             if (__any_sync(0xffffffffu, need)) {
@@ -456,105 +469,140 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (lane == 0) mbar_arrive(bars + 8 * kBarPre);
 
         const float2 a2 = make_float2(a_eff, a_eff), ib2 = make_float2(ib, ib);
-        int slot = grp;                                          // ring slot of block j (and of block j-5): j mod 5
-        for (int j = grp; j <= NY + 4; j += 2, slot = slot + 2 >= kRing ? slot + 2 - kRing : slot + 2) {
-            if (q == 2) AFA_TC_STAMP(1 + grp, j, 0);
-            mbar_wait(bars + 8 * (kBarEv + (j & 7)), (uint32_t)(j >> 3) & 1u);
-            tc_fence_after();
-            if (q == 2) AFA_TC_STAMP(1 + grp, j, 1);
-            if (j >= 5) {
-                // drain Y(j-5): fp32 accumulators -> bf16 -> the lane's row of out chunk (j-5)/4 (in place over x slice j-5)
-                const int i = j - 5;
-                uint32_t yv[16];
-                tmem_ld16(tlane + kColY + 16 * slot, yv);
-                tmem_wait_ld();
-                uint32_t pk[8];
+        // Snake on packed pairs, 16 values at a time (8 independent chains): s = u + ib * sin^2(a u)   activations.py:60, :124
+        auto snake16 = [&](const uint32_t (&u)[16], uint32_t* sp) {
+            float2 u2[8], sn[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) pk[e] = pack_bf16(__uint_as_float(yv[2 * e]), __uint_as_float(yv[2 * e + 1]));
-                const uint32_t c0 = (uint32_t)(i & 3) * 2u;
-                const uint32_t base = srow + (uint32_t)((i >> 2) % kSlots) * kChunkBytes;
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((c0 ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((c0 + 1) ^ sw) << 4)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + (i >> 2) % kSlots));
+            for (int e = 0; e < 8; ++e) {
+                u2[e] = make_float2(__uint_as_float(u[2 * e]), __uint_as_float(u[2 * e + 1]));
+                const float2 th = __fmul2_rn(u2[e], a2);
+                sn[e] = make_float2(__sinf(th.x), __sinf(th.y));
             }
-            if (q == 2) AFA_TC_STAMP(1 + grp, j, 2);
-            if ((j & 3) == 0 && ((j + 8) >> 2) < NCH_IN) patch_chunk((j + 8) >> 2);      // group 0 only: j even
-            if (j <= NY) {
-                // U(j) in two halves of 16 columns: the second load is in flight while the first half goes through Snake, and
-                // only 16 fp32 values are live at a time (the register budget of two CTAs per SM is 80 per thread)
-                uint32_t sp[16];
-                uint32_t ua[16], ub[16];
-                tmem_ld16(tlane + kColUS + 32 * slot, ua);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 s2 = __ffma2_rn(ib2, __fmul2_rn(sn[e], sn[e]), u2[e]);
+                sp[e] = pack_bf16(s2.x, s2.y);
+            }
+        };
+        for (int b = grp; b <= NB + 1; b += 2) {
+            if (q == 2) AFA_TC_STAMP(1 + grp, b, 0);
+            const bool has_u = b <= NB, has_y = b >= 2;
+            if (has_u) {
+                mbar_wait(bars + 8 * (kBarEv + (b & 7)), (uint32_t)(b >> 3) & 1u);
+                tc_fence_after();
+                if (q == 2) AFA_TC_STAMP(1 + grp, b, 1);
+                if ((b & 1) == 0 && (b >> 1) + 2 < NCH_IN) patch_chunk((b >> 1) + 2);     // group 0 only: b even
+                const uint32_t tslot = tlane + (uint32_t)(kSlotCols * (b & 3));
+                uint32_t ua[16], ub[16], uc[16], sp[16];
+                tmem_ld16(tslot, ua);
+                tmem_ld16(tslot + 16, ub);
                 tmem_wait_ld();
-                tmem_ld16(tlane + kColUS + 32 * slot + 16, ub);
-                if (a.debug == 1 && row < a.rows) {
-                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 32) + j * 32;
+                float* dbg_row = nullptr;
+                if (kDebug && (a.debug == 1 || a.debug == 2) && row < a.rows)
+                    dbg_row = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 64) + b * 64;
+                if (kDebug && a.debug == 1 && dbg_row) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) d[e] = __uint_as_float(ua[e]);
+                    for (int e = 0; e < 16; ++e) { dbg_row[e] = __uint_as_float(ua[e]); dbg_row[16 + e] = __uint_as_float(ub[e]); }
                 }
-                // Snake on packed pairs: s = u + ib * sin^2(a u)      activations.py:60, :124
-                auto snake8 = [&](const uint32_t (&u)[16], int h) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        float2 u2[4], th[4], sn[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            u2[e] = make_float2(__uint_as_float(u[8 * c + 2 * e]), __uint_as_float(u[8 * c + 2 * e + 1]));
-                            th[e] = __fmul2_rn(u2[e], a2);
-                        }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) sn[e] = make_float2(__sinf(th[e].x), __sinf(th[e].y));
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 s2 = __ffma2_rn(ib2, __fmul2_rn(sn[e], sn[e]), u2[e]);
-                            sp[8 * h + 4 * c + e] = pack_bf16(s2.x, s2.y);
-                        }
-                    }
-                };
-                snake8(ua, 0);
-                tmem_wait_ld();
-                if (a.debug == 1 && row < a.rows) {
-                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 32) + j * 32 + 16;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) d[e] = __uint_as_float(ub[e]);
-                }
-                snake8(ub, 1);
-                // replicate padding of the ACTIVATED signal (filter.py:98), in the 2x domain; rare -> uniform branch
-                const int eb = 2 * (T - t_org) - 32 * j - 6;      // element of n = 2T in this block: 10 or 26 when inside
-                if (__any_sync(0xffffffffu, (left_lane && j == 0) || eb == 10 || eb == 26)) {
-                    if (left_lane && j == 0) {                    // n < 0 <-> e < 10: s[0] is element 10
+                snake16(ua, sp);
+                tmem_ld16(tslot + 32, ua);
+                tmem_ld16(tslot + 48, uc);
+                snake16(ub, sp + 8);
+                // replicate padding of the ACTIVATED signal (filter.py:98), in the 2x domain; rare -> uniform branch.  eb = element
+                // of n = 2T in this block (10, 26, 42 or 58 when inside): elements >= eb repeat element eb - 1.
+                const int eb = 2 * (T - t_org) - 64 * b - 6;
+                const bool lclamp = left_lane && b == 0, rclamp = eb >= 10 && eb <= 58;
+                uint32_t fill = 0;
+                const bool any_clamp = __any_sync(0xffffffffu, lclamp || rclamp);
+                if (any_clamp) {
+                    if (lclamp) {                                 // n < 0 <-> e < 10: s[0] is element 10
                         const uint32_t s0 = __byte_perm(sp[5], sp[5], 0x1010);
 #pragma unroll
                         for (int e = 0; e < 5; ++e) sp[e] = s0;
                     }
                     if (eb == 10) {
-                        const uint32_t sl = __byte_perm(sp[4], sp[4], 0x3232);
+                        fill = __byte_perm(sp[4], sp[4], 0x3232);
 #pragma unroll
-                        for (int e = 5; e < 16; ++e) sp[e] = sl;
+                        for (int e = 5; e < 16; ++e) sp[e] = fill;
                     } else if (eb == 26) {
-                        const uint32_t sl = __byte_perm(sp[12], sp[12], 0x3232);
+                        fill = __byte_perm(sp[12], sp[12], 0x3232);
 #pragma unroll
-                        for (int e = 13; e < 16; ++e) sp[e] = sl;
+                        for (int e = 13; e < 16; ++e) sp[e] = fill;
                     }
                 }
-                if (a.debug == 2 && row < a.rows) {
-                    float* d = a.dbg + ((size_t)blockIdx.x * 128 + l) * (size_t)(a.dbg_blocks * 32) + j * 32;
+                if (kDebug && a.debug == 2 && dbg_row) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        d[2 * e] = __uint_as_float(sp[e] << 16);
-                        d[2 * e + 1] = __uint_as_float(sp[e] & 0xffff0000u);
+                        dbg_row[2 * e] = __uint_as_float(sp[e] << 16);
+                        dbg_row[2 * e + 1] = __uint_as_float(sp[e] & 0xffff0000u);
                     }
                 }
-                if (q == 2) AFA_TC_STAMP(1 + grp, j, 3);
-                tmem_st16(tlane + kColUS + 32 * slot, sp);
+                tmem_st16(tslot, sp);
+                tmem_wait_ld();
+                if (kDebug && a.debug == 1 && dbg_row) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { dbg_row[32 + e] = __uint_as_float(ua[e]); dbg_row[48 + e] = __uint_as_float(uc[e]); }
+                }
+                snake16(ua, sp);
+                snake16(uc, sp + 8);
+                if (any_clamp) {
+                    if (eb == 10 || eb == 26) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) sp[e] = fill;
+                    } else if (eb == 42) {
+                        fill = __byte_perm(sp[4], sp[4], 0x3232);
+#pragma unroll
+                        for (int e = 5; e < 16; ++e) sp[e] = fill;
+                    } else if (eb == 58) {
+                        fill = __byte_perm(sp[12], sp[12], 0x3232);
+#pragma unroll
+                        for (int e = 13; e < 16; ++e) sp[e] = fill;
+                    }
+                }
+                if (kDebug && a.debug == 2 && dbg_row) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        dbg_row[32 + 2 * e] = __uint_as_float(sp[e] << 16);
+                        dbg_row[32 + 2 * e + 1] = __uint_as_float(sp[e] & 0xffff0000u);
+                    }
+                }
+                tmem_st16(tslot + 16, sp);
+                if (q == 2) AFA_TC_STAMP(1 + grp, b, 2);
+            }
+            if (has_y) {
+                // Y(b-2): fp32 accumulators -> bf16 -> the lane's row of out chunk (b-2)/2, in place over x slices 2b-4, 2b-3
+                const int i = b - 2;
+                mbar_wait(bars + 8 * (kBarEv + ((b + 1) & 7)), (uint32_t)((b + 1) >> 3) & 1u);
+                tc_fence_after();
+                if (q == 2) AFA_TC_STAMP(1 + grp, b, 3);
+                const uint32_t yslot = tlane + (uint32_t)(kSlotCols * (i & 3) + 32);
+                uint32_t ya[16], yb[16];
+                tmem_ld16(yslot, ya);
+                tmem_ld16(yslot + 16, yb);
+                tmem_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    pk[e] = pack_bf16(__uint_as_float(ya[2 * e]), __uint_as_float(ya[2 * e + 1]));
+                    pk[8 + e] = pack_bf16(__uint_as_float(yb[2 * e]), __uint_as_float(yb[2 * e + 1]));
+                }
+                const uint32_t c0 = (uint32_t)(i & 1) * 4u;
+                const uint32_t base = srow + (uint32_t)((i >> 1) % kSlots) * kChunkBytes;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((c0 + c) ^ sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                                 "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + (i >> 1) % kSlots));
+            }
+            if (has_u) {
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (kBarCmp + (j & 7)));
-                if (q == 2) AFA_TC_STAMP(1 + grp, j, 4);
+                if (lane == 0) mbar_arrive(bars + 8 * (kBarCmp + (b & 7)));
             }
+            if (q == 2) AFA_TC_STAMP(1 + grp, b, 4);
         }
     }
     tc_fence_before();

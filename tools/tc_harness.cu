@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <vector>
 
+#define AFA_TC_HARNESS 1
 #include "afa_tc.cu"
 
 namespace afa_internal {
@@ -90,7 +91,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     const int B = atoi(argv[1]), C = atoi(argv[2]), T = atoi(argv[3]);
-    int ny = 0, rlog2 = -1, debug = 0, iters = 0, flags = 1, check_rows = 64;
+    int ny = 0, rlog2 = -1, debug = 0, iters = 0, flags = 1, check_rows = 64, mats = 22, j0 = 0;
     for (int i = 4; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--ny")) ny = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--rlog2")) rlog2 = atoi(argv[i + 1]);
@@ -98,7 +99,11 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--flags")) flags = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--check-rows")) check_rows = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--mats")) mats = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--j0")) j0 = atoi(argv[i + 1]);
     }
+    afa_internal::tc_set_mats(mats);
+    afa_internal::tc_set_debug_window(j0);
     afa_internal::tc_set_tuning(2, ny, rlog2);
     const int64_t rows = (int64_t)B * C, N = rows * T;
     int prl, pny;
@@ -148,15 +153,30 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dbeta, C * 4));
     CK(cudaMemcpy(dalpha, halpha.data(), C * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbeta, hbeta.data(), C * 4, cudaMemcpyHostToDevice));
-    const size_t dbg_per_cta = (size_t)128 * (pny + 1) * 32;
+    const size_t dbg_per_cta = (size_t)128 * (pny / 2 + 1) * 64;
     if (debug) {
         CK(cudaMalloc(&ddbg, (size_t)(rg * ts) * dbg_per_cta * 4));
         CK(cudaMemset(ddbg, 0, (size_t)(rg * ts) * dbg_per_cta * 4));
     }
 
-    if (debug >= 3) {   // warm the instruction cache / tensor maps first, then stamp a CTA in the middle of the grid
-        afa_internal::tc_fwd_launch(dx[0], dy[0], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
-        CK(cudaDeviceSynchronize());
+    if (debug >= 3) {   // bring the clocks and the power state to steady load first (~0.4 s of launches), then stamp a CTA in the
+                        // middle of the grid of the very next launch: stamps of a cold launch see an idle-clocked SM against a
+                        // full-speed memory system and under-state every memory wait
+        cudaEvent_t w0, w1;
+        CK(cudaEventCreate(&w0));
+        CK(cudaEventCreate(&w1));
+        CK(cudaEventRecord(w0));
+        for (int rep = 0; rep < 100000; ++rep) {
+            for (int i = 0; i < 8; ++i)
+                afa_internal::tc_fwd_launch(dx[0], dy[0], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
+            CK(cudaEventRecord(w1));
+            CK(cudaEventSynchronize(w1));
+            float wms = 0;
+            CK(cudaEventElapsedTime(&wms, w0, w1));
+            if (wms > 400.f) break;
+        }
+        for (int i = 0; i < 8; ++i)
+            afa_internal::tc_fwd_launch(dx[0], dy[0], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
     }
     int rc = afa_internal::tc_fwd_launch(dx[0], dy[0], dalpha, dbeta, tu, td, B, C, T, flags, 0, debug, ddbg);
     if (rc) { printf("launch failed rc=%d\n", rc); return 2; }
@@ -176,9 +196,9 @@ int main(int argc, char** argv) {
         uint32_t t0 = 0xffffffffu;
         for (int i = 0; i < 3 * 32 * 8; ++i) if (i < 3 * 32 * 8 && st[i] && st[i] < t0) t0 = st[i];
         printf("first loop stamp at %d cycles after kernel entry\n", (int)(t0 - st[(3 * 32 + 1) * 8]));
-        printf("timeline of CTA %lld (cycles since first stamp); MMA: wait-start, woke, issued | group g: wait-up, woke, U loaded, snake done, arrived, dn woke\n", (long long)(rg * ts / 2));
+        printf("timeline of CTA %lld (cycles since first stamp); MMA: wait-start, woke, issued | group g: start, U ready, S stored, Y ready, arrived\n", (long long)(rg * ts / 2));
         for (int j = 0; j <= pny + 1 && j < 30; ++j) {
-            printf("j=%2d MMA %6d %6d %6d (batch done %6d) | g%d %6d %6d %6d %6d %6d %6d\n", j, st[(0 * 32 + j) * 8 + 0] ? (int)(st[(0 * 32 + j) * 8 + 0] - t0) : -1,
+            printf("j=%2d MMA %6d %6d %6d (batch done %6d) | g%d %6d %6d %6d %6d %6d %6d\n", j + j0, st[(0 * 32 + j) * 8 + 0] ? (int)(st[(0 * 32 + j) * 8 + 0] - t0) : -1,
                    st[(0 * 32 + j) * 8 + 1] ? (int)(st[(0 * 32 + j) * 8 + 1] - t0) : -1, st[(0 * 32 + j) * 8 + 2] ? (int)(st[(0 * 32 + j) * 8 + 2] - t0) : -1, st[(0 * 32 + j) * 8 + 3] ? (int)(st[(0 * 32 + j) * 8 + 3] - t0) : -1, j & 1,
                    st[((1 + (j & 1)) * 32 + j) * 8 + 0] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 0] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 1] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 1] - t0) : -1,
                    st[((1 + (j & 1)) * 32 + j) * 8 + 2] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 2] - t0) : -1, st[((1 + (j & 1)) * 32 + j) * 8 + 3] ? (int)(st[((1 + (j & 1)) * 32 + j) * 8 + 3] - t0) : -1,
@@ -214,17 +234,17 @@ int main(int argc, char** argv) {
             }
         }
         if (debug == 1 || debug == 2) {
-            // element (block j, e) of lane l of CTA (rgroup, tstrip) holds n = 2 t_org + 32 j + 6 + e
+            // element (block j, e) of lane l of CTA (rgroup, tstrip) holds n = 2 t_org + 64 j + 6 + e
             const int64_t rgp = r / R;
             const int rr = (int)(r % R);
             for (int64_t tsx = 0; tsx < ts; ++tsx)
                 for (int g = 0; g < G; ++g) {
                     const int l = g * R + rr;
                     const int t_org = (int)(tsx * G * span + g * span - 8);
-                    const float* d = &hdbg[((size_t)(rgp * ts + tsx) * 128 + l) * (size_t)((pny + 1) * 32)];
-                    for (int j = 0; j <= pny; ++j)
-                        for (int el = 0; el < 32; ++el) {
-                            const int n = 2 * t_org + 32 * j + 6 + el;
+                    const float* d = &hdbg[((size_t)(rgp * ts + tsx) * 128 + l) * (size_t)((pny / 2 + 1) * 64)];
+                    for (int j = 0; j <= pny / 2; ++j)
+                        for (int el = 0; el < 64; ++el) {
+                            const int n = 2 * t_org + 64 * j + 6 + el;
                             double ref;
                             if (debug == 1) {
                                 if (n < 0 || n >= 2 * T) continue;      // u outside the row is don't-care
@@ -233,7 +253,7 @@ int main(int argc, char** argv) {
                                 if (n < -5 || n > 2 * T + 4) continue;
                                 ref = s[clampi(n, 0, 2 * T - 1)];
                             }
-                            const double err = fabs((double)d[j * 32 + el] - ref);
+                            const double err = fabs((double)d[j * 64 + el] - ref);
                             max_dbg_ref = std::max(max_dbg_ref, fabs(ref));
                             if (!(err <= max_dbg_err)) { max_dbg_err = err; dbad_r = r; dbad_n = n; }
                         }
@@ -252,8 +272,19 @@ int main(int argc, char** argv) {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        for (int i = 0; i < 3; ++i)
-            afa_internal::tc_fwd_launch(dx[i % nsets], dy[i % nsets], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
+        // warm-up long enough for the clocks to leave idle (the parity check above ran on the host for seconds): ~0.3 s of launches
+        {
+            CK(cudaEventRecord(e0));
+            for (int rep = 0; rep < 4000; ++rep) {
+                for (int i = 0; i < 8; ++i)
+                    afa_internal::tc_fwd_launch(dx[i % nsets], dy[i % nsets], dalpha, dbeta, tu, td, B, C, T, flags, 0, 0, nullptr);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                float wms = 0;
+                CK(cudaEventElapsedTime(&wms, e0, e1));
+                if (wms > 300.f) break;
+            }
+        }
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
         for (int i = 0; i < iters; ++i)
