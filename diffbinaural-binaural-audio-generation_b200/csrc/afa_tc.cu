@@ -109,14 +109,12 @@ bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, 
     const int64_t rows = batch * channels;
     if (rows < 8 || rows >= (1ll << 30)) return false;
     if (g_tc_enable == 1) {
-        // Built-in choice, fitted to same-box sweeps against the register-walk kernel (profiles/r02_tc_sweep.log): the walk
-        // kernel loses on short and medium rows (every row end costs an edge-mode warp; 2.2-2.8 TB/s at T <= 27552) where this
-        // kernel does not care about row length (2.6-3.0 TB/s), and wins by 3-15 % on very long rows and on single-clip
-        // launches that fill 1-2 waves of this kernel's 128-lane CTAs.
+        // Built-in choice, fitted to same-box sustained sweeps against the register-walk kernel (profiles/r02_tc_sweep_v9.log):
+        // this kernel wins by 20-60 % on eight-clip launches (3.5-3.9 against 2.2-3.1 TB/s), by 25-30 % on the training
+        // shapes (batch 32) and by 0-15 % on single-clip launches; the walk kernel keeps the short launches (< 6 M elements,
+        // where this kernel's set-up and pipeline fill weigh most) and rows shorter than 256 samples.
         const int64_t n = rows * T;
-        const bool many_short_rows = T < 32768 && n >= (16ll << 20);
-        const bool train_like = rows >= 768 && T <= 8192 && n >= (3ll << 20);
-        if (!many_short_rows && !train_like) return false;
+        if (T < 256 || n < (6ll << 20)) return false;
     }
     return encode_fn() != nullptr;
 }

@@ -24,8 +24,8 @@
 //     wrote (no thread touches x).  Down filter in TS mode: A = S from TENSOR MEMORY.  Shared memory therefore
 //     sees each byte of x and y once plus the operand reads of the up filter.
 //   * tensor memory: 4 slots of 64 columns.  up(b) fills slot b % 4 with U_b (64 fp32).  Snake reads it and writes
-//     S_b (64 bf16) over columns 0..31; down(b) then puts Y_b (32 fp32) into columns 32..63 of the SAME slot --
-//     the half of U_b that is dead by then -- so the output accumulators cost no columns of their own.
+//     S_b (64 bf16) over columns 0..31; down(b) then puts Y_b (32 fp32) into columns 32..63 of the slot of block b + 1 --
+//     the half of U_(b+1) that Snake has consumed by then -- so the output accumulators cost no columns of their own.
 //   * a CTA owns 128 lanes = R rows x G time groups (R * G = 128; R = 16 for one binaural clip at C = 24) and
 //     NY / 2 blocks of 32 outputs per lane.  x arrives as 64-sample chunks through a recycled ring of 5 slots;
 //     out-of-range samples and rows are zero-filled by the TMA unit; y leaves through the same chunks in place
@@ -199,7 +199,7 @@ __device__ __forceinline__ uint32_t clk32() {
     return c;
 }
 // harness timeline (debug == 3): dbg[(role * 32 + j) * 8 + slot] = clock, for CTA `dbg_cta`
-#define AFA_TC_STAMP(role, j, slot) do { if (kDebug) { const int jw_ = (j) - ((role) == 3 ? 0 : a.dbg_j0); if (a.debug >= 3 && lane == 0 && jw_ >= 0 && jw_ < 32 && blockIdx.x == (unsigned)a.dbg_cta) a.dbg[((role) * 32 + jw_) * 8 + (slot)] = __uint_as_float(clk32()); } } while (0)
+#define AFA_TC_STAMP(role, j, slot) do { if (kDebug) { const int jw_ = (j) - ((role) == 3 ? 0 : a.dbg_j0); if (a.debug == 3 && lane == 0 && jw_ >= 0 && jw_ < 32 && blockIdx.x == (unsigned)a.dbg_cta) a.dbg[((role) * 32 + jw_) * 8 + (slot)] = __uint_as_float(clk32()); } } while (0)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -212,24 +212,28 @@ __device__ __forceinline__ float snake_f(float u, float a, float ib) {
 
 // Schedule.  Block b = 32 time steps of the CTA's 128 lanes (64 u-values, 32 outputs per lane).  Compute group g (4 warps)
 // owns the blocks b = g (mod 2).  Tensor-memory slot of block b: b % 4.
-//   MMA thread, event e:        wait cmp[e & 7]  (S(e) is in TMEM and Y(e-2) has been read out of slot (e+2) % 4);
-//                               down(e-1): S(e-1) and the first slice of S(e) -> Y(e-1) in columns 32..63 of slot (e-1) % 4;
-//                               up(e+2): x slices 2e+4 .. 2e+6 straight from the swizzled chunks -> U(e+2) in slot (e+2) % 4;
-//                               ONE commit -> ev[(e+2) & 7]  (tcgen05.commit tracks every MMA issued before it)
-//   iteration b of its group:   wait ev[b & 7]  (event b-2: U(b) is complete)
+//   MMA thread, event e:        wait cmp[e & 7]  (S(e) is in TMEM and Y(e-2) has been read out of slot (e-1) % 4);
+//                               down(e-1): S(e-1) and the first slice of S(e) -> Y(e-1) in columns 32..63 of slot e % 4 (the
+//                               half of U(e) that Snake has consumed);
+//                               up(e+3): x slices 2e+6 .. 2e+8 straight from the swizzled chunks -> U(e+3) in slot (e-1) % 4;
+//                               ONE commit -> ev[(e+3) & 7]  (tcgen05.commit tracks every MMA issued before it)
+//   iteration b of its group:   wait ev[b & 7]  (event b-3: U(b) is complete -- issued a whole iteration of the OTHER group ago,
+//                               so the MMA round trip is off the group's critical path)
 //                               U(b) -> registers (4 loads of 16 columns, the next in flight behind the math) -> Snake ->
 //                               S(b) over columns 0..31 (two tcgen05.st)
-//                               wait ev[(b+1) & 7]  (event b-1: Y(b-2) is complete) -> registers -> bf16 -> shared memory (in
-//                               place over x slices 2b-4, 2b-3 of out chunk (b-2)/2) -> proxy fence -> arrive out[...]
+//                               wait ev[(b+2) & 7]  (event b-1: Y(b-2) is complete) -> registers -> bf16 -> shared memory
+//                               (out chunk (b-2)/2, staged in the ring slot of x chunk (b-2)/2 + 1) -> proxy fence -> arrive out[...]
 //                               tcgen05.wait::st -> arrive cmp[b & 7]
-//   warp 0:                     wait out[q] (8 warp arrivals) -> TMA store of out chunk q -> the slot takes x chunk q + 5
-// One barrier round trip, one tensor-memory store wait and one proxy fence now cover 32 outputs per lane (16 in the first
+//   warp 0:                     wait out[q] (8 warp arrivals) -> TMA store of out chunk q -> the slot takes x chunk q + 6
+// One barrier round trip, one tensor-memory store wait and one proxy fence cover 32 outputs per lane (16 in the first
 // versions: the fixed latencies of an iteration, ~1300 cycles, outweighed its ~900 cycles of Snake math).
-// Ring safety: up(e+2) overwrites slot (e-2) % 4: S(e-2) was last read by down(e-2), issued at event e-1 by the same thread
-// (MMAs execute in issue order); Y(e-2) was read by iteration e of group e % 2 before its arrive on cmp[e & 7].  down(b)
-// writes columns 32..63 of slot b: the upper half of U(b), in registers since iteration b.  y block i overwrites x slices 2i,
-// 2i+1, last read by up(i), complete since event i-2.  cmp / ev are rings of 8 indexed by block / event: a warp's waits depend
-// on events b-2 and b-1 only, so it may run ahead of a slower warp of its group, never 8 events ahead (event e needs cmp[e]).
+// Ring safety: up(e+3) overwrites slot (e-1) % 4: S(e-1) was last read by down(e-1), issued just before it by the same thread
+// (MMAs execute in issue order); its upper half held Y(e-2), read by iteration e of group e % 2 before the arrive on
+// cmp[e & 7].  down(e-1) writes the upper half of slot e % 4: U(e), in registers since iteration e.  Out chunk q is staged over
+// x chunk q + 1 (slices 4q+4 .. 4q+7, last read by up(2q+3) at event 2q, complete before iteration 2q+2 passes its wait on
+// event 2q+1): a slot is free again one chunk time earlier than with in-place staging, which is what lets the x chunk for
+// up(e+3) arrive in time.  cmp / ev are rings of 8 indexed by block: a warp's waits depend on events b-3 and b-1 only, so it
+// may run ahead of a slower warp of its group, never 8 events ahead (event e needs cmp[e]).
 // kUpMats / kDnMats: tap matrices per K slice of the up / down filter -- 2 = bf16 hi + lo (16 mantissa bits), 1 = the taps
 // rounded to bf16 (8 bits).  kDebug: harness dumps and clock stamps; compiled out of the product instantiation.
 #ifndef AFA_TC_BOUND_THREADS
@@ -245,6 +249,14 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: role code runs on the uniform datapath
     if (warp == 1) AFA_TC_STAMP(3, 1, 0);
+    if (kDebug && a.debug == 4 && tid == 32) {                  // harness: per-CTA life span (globaltimer ns) and SM id
+        unsigned long long t;
+        uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        reinterpret_cast<unsigned long long*>(a.dbg)[blockIdx.x * 4 + 0] = t;
+        reinterpret_cast<unsigned long long*>(a.dbg)[blockIdx.x * 4 + 2] = smid;
+    }
     const int NY = a.NY, NB = NY >> 1;                            // NB blocks of 32 outputs per lane
     const int NCH_IN = (NY >> 2) + 1, NCH_OUT = NY >> 2;          // x chunks (slices 0 .. NY + 2) / out chunks of this CTA's strip
     const int R = 1 << a.R_log2, G = 128 >> a.R_log2;
@@ -319,15 +331,26 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (warp == 1) AFA_TC_STAMP(3, 1, 1);
 
     if (warp == 0) {
-        // ===== TMA store of finished output chunks, then the slot takes the x chunk kSlots further down the strip =====
+        // ===== TMA store of finished output chunks; the slot then takes the next x chunk of the strip =====
+        // x chunk 0 has no output staged over it (out chunk q lives in the slot of x chunk q + 1): its slot takes x chunk kSlots
+        // as soon as up(0) and up(1) have read it
+        if (kSlots < NCH_IN) {
+            mbar_wait(bars + 8 * (kBarEv + 1), 0);
+            if (elect_one()) {
+                mbar_expect_tx(bars + 8 * (kBarFull + 0), (uint32_t)kChunkBytes);
+                for (int g = 0; g < G; ++g)
+                    tma_load_2d(sbase + g * R * 128, &tm_x, t_cta0 + g * span - 8 + 64 * kSlots, row0, bars + 8 * (kBarFull + 0));
+            }
+            __syncwarp();
+        }
         for (int qc = 0; qc < NCH_OUT; ++qc) {
-            const int slot = qc % kSlots;
+            const int slot = (qc + 1) % kSlots;
             mbar_wait(bars + 8 * (kBarOut + slot), (uint32_t)(qc / kSlots) & 1u);
             if (elect_one()) {
                 for (int g = 0; g < G; ++g)
                     tma_store_2d(&tm_y, t_cta0 + g * span + 64 * qc, row0, sbase + slot * kChunkBytes + g * R * 128);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                const int nc = qc + kSlots;                         // next x chunk for this slot
+                const int nc = qc + 1 + kSlots;                     // next x chunk for this slot
                 if (nc < NCH_IN) {
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has finished reading the slot
                     mbar_expect_tx(bars + 8 * (kBarFull + slot), (uint32_t)kChunkBytes);
@@ -368,10 +391,11 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if (kUpMats == 2) mma_ss(d, xd[k], bup + (uint64_t)((kUpSlices + k) * (kWupBytes >> 4)), idesc_up, 1);
             }
         };
-        // Y(bd) <- the four s slices of S(bd) (columns 0, 8, 16, 24 of its slot) and the first of S(bd + 1)
+        // Y(bd) <- the four s slices of S(bd) (columns 0, 8, 16, 24 of its slot) and the first of S(bd + 1); lands in the upper
+        // half of the slot of block bd + 1
         auto down = [&](int bd) {
             const uint32_t sl0 = tmem + (uint32_t)(kSlotCols * (bd & 3)), sl1 = tmem + (uint32_t)(kSlotCols * ((bd + 1) & 3));
-            const uint32_t d = sl0 + 32;
+            const uint32_t d = sl1 + 32;
 #pragma unroll
             for (int k = 0; k < kDnSlices; ++k) {
                 const uint32_t aa = k < 4 ? sl0 + 8u * k : sl1;
@@ -383,18 +407,19 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // chunks themselves are awaited here, in the order the up-filter products need them
         mbar_wait(bars + 8 * kBarPre, 0);
         mbar_wait(bars + 8 * (kBarFull + 0), 0);
-        mbar_wait(bars + 8 * (kBarFull + 1), 0);                        // up(1) reads slice 4 (NY >= 4: two chunks at least)
+        mbar_wait(bars + 8 * (kBarFull + 1), 0);                        // up(1), up(2) read slices 4 .. 6 (NY >= 4: two chunks at least)
         int nfull = 2;
         tc_fence_after();
-        if (elect_one()) {                                   // events -2, -1
+        if (elect_one()) {                                   // events -3 .. -1
             up(tmem + 0 * kSlotCols, 0, 0); tc_commit(bars + 8 * (kBarEv + 0));
             up(tmem + 1 * kSlotCols, 1, 0); tc_commit(bars + 8 * (kBarEv + 1));
+            up(tmem + 2 * kSlotCols, 2, 1); tc_commit(bars + 8 * (kBarEv + 2));
         }
         __syncwarp();
-        int xs = 1;                                          // ring slot of the chunk holding slice 2 (e + 2) = chunk (e + 2) / 2
+        int xs = 1;                                          // ring slot of the chunk holding slice 2 (e + 3) = chunk (e + 3) / 2
         for (int e = 0; e <= NB; ++e) {
             AFA_TC_STAMP(0, e, 0);
-            const int bu = e + 2;
+            const int bu = e + 3;
             if (bu <= NB) {
                 const int p = (bu + 1) >> 1;                 // chunk of slice 2 bu + 2
                 while (nfull <= p) { mbar_wait(bars + 8 * (kBarFull + nfull % kSlots), (uint32_t)(nfull / kSlots) & 1u); ++nfull; }
@@ -438,8 +463,8 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
         // replicate padding of x (resample.py:32), patched into the staged chunks by group 0 (the TMA unit zero-filled what lies
         // outside the tensor): x[0] over the 8 samples before the row, x[T-1] over the 16 samples behind it (3 are read).  Chunk c
-        // is patched after it has landed and before the first product that reads it (up(2c-1), issued at event 2c-3): chunks 0 and
-        // 1 here, chunk c >= 2 at iteration 2c-4 of group 0, ahead of that iteration's arrive on cmp.
+        // is patched after it has landed and before the first product that reads it (up(2c-1), issued at event 2c-4): chunks 0, 1
+        // and 2 here, chunk c >= 3 at iteration 2c-6 of group 0, ahead of that iteration's arrive on cmp.
         auto patch_chunk = [&](int c) {
             const bool need = row < a.rows && ((left_lane && c == 0) || (right_lane && ((cb >> 3) == c || ((cb + 1) >> 3) == c)));
             if (__any_sync(0xffffffffu, need)) {
@@ -464,6 +489,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (grp == 0) {
             patch_chunk(0);
             patch_chunk(1);
+            if (2 < NCH_IN) patch_chunk(2);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 8 * kBarPre);
@@ -476,7 +502,11 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int e = 0; e < 8; ++e) {
                 u2[e] = make_float2(__uint_as_float(u[2 * e]), __uint_as_float(u[2 * e + 1]));
                 const float2 th = __fmul2_rn(u2[e], a2);
+#if defined(AFA_TC_EXPERIMENT) && AFA_TC_EXPERIMENT == 1      // harness only: no MUFU (energy / pipe-share experiments; results are wrong)
+                sn[e] = th;
+#else
                 sn[e] = make_float2(__sinf(th.x), __sinf(th.y));
+#endif
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -491,7 +521,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 mbar_wait(bars + 8 * (kBarEv + (b & 7)), (uint32_t)(b >> 3) & 1u);
                 tc_fence_after();
                 if (q == 2) AFA_TC_STAMP(1 + grp, b, 1);
-                if ((b & 1) == 0 && (b >> 1) + 2 < NCH_IN) patch_chunk((b >> 1) + 2);     // group 0 only: b even
+                if ((b & 1) == 0 && (b >> 1) + 3 < NCH_IN) patch_chunk((b >> 1) + 3);     // group 0 only: b even
                 const uint32_t tslot = tlane + (uint32_t)(kSlotCols * (b & 3));
                 uint32_t ua[16], ub[16], uc[16], sp[16];
                 tmem_ld16(tslot, ua);
@@ -570,12 +600,13 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if (q == 2) AFA_TC_STAMP(1 + grp, b, 2);
             }
             if (has_y) {
-                // Y(b-2): fp32 accumulators -> bf16 -> the lane's row of out chunk (b-2)/2, in place over x slices 2b-4, 2b-3
+                // Y(b-2) (upper half of slot (b-1) % 4): fp32 accumulators -> bf16 -> the lane's row of out chunk (b-2)/2, staged
+                // in the ring slot of x chunk (b-2)/2 + 1
                 const int i = b - 2;
-                mbar_wait(bars + 8 * (kBarEv + ((b + 1) & 7)), (uint32_t)((b + 1) >> 3) & 1u);
+                mbar_wait(bars + 8 * (kBarEv + ((b + 2) & 7)), (uint32_t)((b + 2) >> 3) & 1u);
                 tc_fence_after();
                 if (q == 2) AFA_TC_STAMP(1 + grp, b, 3);
-                const uint32_t yslot = tlane + (uint32_t)(kSlotCols * (i & 3) + 32);
+                const uint32_t yslot = tlane + (uint32_t)(kSlotCols * ((i + 1) & 3) + 32);
                 uint32_t ya[16], yb[16];
                 tmem_ld16(yslot, ya);
                 tmem_ld16(yslot + 16, yb);
@@ -587,14 +618,14 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     pk[8 + e] = pack_bf16(__uint_as_float(yb[2 * e]), __uint_as_float(yb[2 * e + 1]));
                 }
                 const uint32_t c0 = (uint32_t)(i & 1) * 4u;
-                const uint32_t base = srow + (uint32_t)((i >> 1) % kSlots) * kChunkBytes;
+                const uint32_t base = srow + (uint32_t)(((i >> 1) + 1) % kSlots) * kChunkBytes;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((c0 + c) ^ sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                                  "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + (i >> 1) % kSlots));
+                if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + ((i >> 1) + 1) % kSlots));
             }
             if (has_u) {
                 tmem_wait_st();
@@ -608,6 +639,11 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 1) AFA_TC_STAMP(3, 1, 3);
+    if (kDebug && a.debug == 4 && tid == 32) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(a.dbg)[blockIdx.x * 4 + 1] = t;
+    }
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");

@@ -191,7 +191,23 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(hdbg.data(), ddbg, hdbg.size() * 4, cudaMemcpyDeviceToHost));
     }
 
-    if (debug >= 3) {
+    if (debug == 4) {
+        const unsigned long long* st = reinterpret_cast<const unsigned long long*>(hdbg.data());
+        const long long n = rg * ts;
+        unsigned long long t0 = ~0ull, t1 = 0;
+        for (long long i = 0; i < n; ++i) { t0 = std::min(t0, st[i * 4]); t1 = std::max(t1, st[i * 4 + 1]); }
+        std::vector<double> life(n), start(n), end(n);
+        for (long long i = 0; i < n; ++i) { start[i] = (double)(st[i * 4] - t0) * 1e-3; end[i] = (double)(st[i * 4 + 1] - t0) * 1e-3; life[i] = end[i] - start[i]; }
+        auto pct = [&](std::vector<double> v, double p) { std::sort(v.begin(), v.end()); return v[(size_t)(p * (v.size() - 1))]; };
+        printf("CTA spans (us since the first CTA start): grid span %.2f | start p0 %.2f p50 %.2f p100 %.2f | end p0 %.2f p10 %.2f p50 %.2f p90 %.2f p100 %.2f | life p0 %.2f p50 %.2f p100 %.2f\n",
+               (double)(t1 - t0) * 1e-3, pct(start, 0), pct(start, .5), pct(start, 1), pct(end, 0), pct(end, .1), pct(end, .5), pct(end, .9), pct(end, 1), pct(life, 0), pct(life, .5), pct(life, 1));
+        int per_sm[256] = {};
+        for (long long i = 0; i < n; ++i) per_sm[st[i * 4 + 2] & 255]++;
+        int h[8] = {};
+        for (int i = 0; i < 256; ++i) h[std::min(per_sm[i], 7)]++;
+        printf("CTAs per SM histogram: 0:%d 1:%d 2:%d 3:%d 4+:%d\n", h[0], h[1], h[2], h[3], h[4] + h[5] + h[6] + h[7]);
+    }
+    if (debug == 3) {
         const uint32_t* st = reinterpret_cast<const uint32_t*>(hdbg.data());
         uint32_t t0 = 0xffffffffu;
         for (int i = 0; i < 3 * 32 * 8; ++i) if (i < 3 * 32 * 8 && st[i] && st[i] < t0) t0 = st[i];
