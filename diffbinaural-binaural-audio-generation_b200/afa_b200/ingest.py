@@ -157,7 +157,11 @@ class BatchedVocoder:
             by_len.setdefault(k, []).append(r)
         flat = pcm.view(clips, t_out, 2)
         # rare lengths run eagerly: no cuDNN autotuning for a shape that will not come back (it costs seconds per new length)
-        with torch.backends.cudnn.flags(enabled=True, benchmark=False):
+        # (the context manager resets EVERY cuDNN flag to its own default -- allow_tf32=True among them -- unless told otherwise:
+        # the caller's precision and determinism settings are passed through)
+        with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, benchmark=False,
+                                        deterministic=torch.backends.cudnn.deterministic,
+                                        allow_tf32=torch.backends.cudnn.allow_tf32):
             for k, rs in sorted(by_len.items()):
                 if k == 0:
                     continue                                       # a silent channel stays silence

@@ -7,19 +7,22 @@
 //
 // Why: the register-walk kernel of afa_kernels.cuh spends 24 of its 27 instructions per output on the two
 // 12-tap FIRs and is bound by the FP32 FMA pipe -- at bf16 I/O it reaches 0.29-0.44 of the HBM roofline
-// (VERDICT round 1).  The FIRs are linear and shift invariant, so a block of 32 time steps of 128 rows is a
-// product with a small CONSTANT banded Toeplitz matrix (K = 16 samples per tcgen05.mma):
+// (VERDICT round 1).  The FIRs are linear and shift invariant, so 16 outputs of 128 rows are a product with a small
+// CONSTANT banded Toeplitz matrix (K = 16 samples per tcgen05.mma, N = 16):
 //
-//   U_b [128 rows x 64 u-values] = sum_{k<3} X_{2b+k} [128 x 16] * Wup_k [16 x 64]        (x slices of 16 samples)
-//   Y_b [128 rows x 32 outputs ] = sum_{k<5} S_{4b+k} [128 x 16] * Wdn_k [16 x 32]        (s slices of 16 values)
+//   U [128 rows x 16 u-values] = X [128 x 16 samples, starting at the block's own first sample] * Wup [16 x 16]
+//   Y [128 rows x 16 outputs ] = S_a [128 x 16] * Wdn_a + S_b * Wdn_b + S_c * Wdn_c        (three s slices of 16 values)
 //
-// with M = 128 rows of the tensor (one TMEM lane each) and N = the block's outputs.  Only Snake (2 MUFU + 6
-// FMA-pipe instructions per output) stays on the CUDA cores.
+// with M = 128 rows of the tensor (one TMEM lane each).  The products are cut to the band: 16 u-values need 14 consecutive
+// samples, i.e. ONE K slice when it starts at an 8-sample (16-byte) granular address inside the swizzled row; 16 outputs need
+// 43 s-values, three slices.  (N = 64 / 32 products need fewer instructions but multiply 2.2 x as many zeros: tensor-pipe time
+// and, on a board that runs this kernel at its power cap, energy.)  Only Snake (2 MUFU + 6 FMA-pipe instructions per output)
+// stays on the CUDA cores.
 //   * taps are split hi + lo into two bf16 matrices (16 mantissa bits), both products accumulate in fp32 in
 //     TMEM; x is bf16 by contract, so U is exact to fp32 rounding.  s is rounded to bf16 once, as the A operand
 //     of the down filter (the same rounding step the bf16 output applies anyway).  (A single fp16 tap matrix
 //     against bf16 activations is rejected by the hardware -- "illegal instruction" -- although the descriptor
-//     has separate format fields; kMats = 1 uses the bf16 hi part alone and exists for measurements.)
+//     has separate format fields; kUpMats / kDnMats = 1 use the bf16 hi part alone and exist for measurements.)
 //   * up filter in SS mode: A = the x slices straight from the 128-byte swizzled chunks the tensor-map TMA
 //     wrote (no thread touches x).  Down filter in TS mode: A = S from TENSOR MEMORY.  Shared memory therefore
 //     sees each byte of x and y once plus the operand reads of the up filter.
@@ -28,8 +31,8 @@
 //     the half of U_(b+1) that Snake has consumed by then -- so the output accumulators cost no columns of their own.
 //   * a CTA owns 128 lanes = R rows x G time groups (R * G = 128; R = 16 for one binaural clip at C = 24) and
 //     NY / 2 blocks of 32 outputs per lane.  x arrives as 64-sample chunks through a recycled ring of 5 slots;
-//     out-of-range samples and rows are zero-filled by the TMA unit; y leaves through the same chunks in place
-//     (TMA store clips what lies outside the tensor).
+//     out-of-range samples and rows are zero-filled by the TMA unit; y is staged over the NEXT x chunk of the ring
+//     (dead by then) and leaves by TMA store (which clips what lies outside the tensor).
 //   * warp roles: warp 0 = TMA producer / TMEM allocator / TMA store; warp 1 = MMA issuer (one elected thread);
 //     warps 2-9 = two compute groups of four warps (one thread per TMEM lane) that alternate over the blocks.
 //     All hand-offs are mbarriers (tcgen05.commit on the MMA side); no CTA-wide barrier inside the block loop.
@@ -37,9 +40,10 @@
 // Index algebra (t_org = the lane's first staged sample, t_org % 8 == 0, first output t_org + 8):
 //   x slice k   : x_ext[t_org + 16k + (0..15)]
 //   u block b   : u_ext[n0 + e], n0 = 2*t_org + 64b + 6, e = 0..63;  u[n] = 2 * sum_i f[n + 5 - 2i] * x_ext[i]
-//                 -> Wup[kappa][e] = 2 f[e + 11 - 2 kappa],  kappa = 0..47 over slices 2b, 2b+1, 2b+2
+//                 -> sub-block m (e = 16m .. 16m+15) reads samples t_org + 32b + 8m + (0..13):  Wup[kappa][e'] = 2 f[e' + 11 - 2 kappa]
 //   y block b   : y[t_org + 8 + 32b + e], e = 0..31;  y[t] = sum_k f[k] * s_ext[2t + k - 5]
-//                 -> Wdn[kappa][e] = f[kappa - 2e - 5],  kappa = 0..79 over the 4 s slices of block b and the first of b+1
+//                 -> sub-block h (e = 16h .. 16h+15) reads s-values 32h + (0..47) of the block (columns 16h, 16h+8, 16h+16; column
+//                    32 is the first slice of block b+1):  Wdn[kappa][e'] = f[kappa - 2e' - 5],  kappa = 0..47
 //   replicate padding: x_ext clamps in the 1x domain (chunks with t < 0 or t >= T, always whole 8-sample
 //   chunks because T % 8 == 0); s_ext clamps the ACTIVATED signal in the 2x domain (filter.py:98): elements
 //   e < 10 of block 0 of a row's first lane, and elements e >= e_b (e_b = 10, 26, 42 or 58) of the block holding 2T.
@@ -52,17 +56,20 @@
 namespace afa_tc {
 
 constexpr int kThreads = 320;            // warp 0: TMA producer / TMEM allocator / TMA store, warp 1: MMA, warps 2..9: compute
-constexpr int kSlots = 5;                // shared-memory chunk ring: slots of 64 samples x 128 lanes, recycled along the strip
+#ifndef AFA_TC_SLOTS
+#define AFA_TC_SLOTS 5
+#endif
+constexpr int kSlots = AFA_TC_SLOTS;                // shared-memory chunk ring: slots of 64 samples x 128 lanes, recycled along the strip
 constexpr int kChunkBytes = 128 * 128;   // 128 lanes x 64 bf16
 constexpr int kTmemCols = 256;           // 4 slots x 64 columns
 constexpr int kRing = 4;                 // tensor-memory slots: U(b) = 64 fp32 columns; then S(b) = 64 bf16 in columns 0..31 and
 constexpr int kSlotCols = 64;            //   Y(b) = 32 fp32 outputs in columns 32..63 (the half of U that Snake has consumed)
-constexpr int kUpSlices = 3, kDnSlices = 5;          // K = 16 slices per product: 64 u need 38 samples, 32 y need 75 s-values
-constexpr int kWupBytes = 64 * 16 * 2, kWdnBytes = 32 * 16 * 2;
+constexpr int kUpVariants = 3, kDnSlices = 3;        // B matrices: up = plain / shifted +8 / shifted -8 rows; down = K slices a, b, c
+constexpr int kWBytes = 16 * 16 * 2;                 // every B matrix is [N = 16 x K = 16] bf16
 // shared memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int kOffWup = kSlots * kChunkBytes;                    // [hi/lo][slice] x (64 x 16 bf16 = 2048 B)
-constexpr int kOffWdn = kOffWup + 2 * kUpSlices * kWupBytes;     // [hi/lo][slice] x (32 x 16 bf16 = 1024 B)
-constexpr int kOffBar = kOffWdn + 2 * kDnSlices * kWdnBytes;
+constexpr int kOffWup = kSlots * kChunkBytes;                    // [hi/lo][variant] x 512 B
+constexpr int kOffWdn = kOffWup + 2 * kUpVariants * kWBytes;     // [hi/lo][slice] x 512 B
+constexpr int kOffBar = kOffWdn + 2 * kDnSlices * kWBytes;
 constexpr int kBarFull = 0, kBarPre = kSlots, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 8, kBarOut = kBarEv + 8;
 constexpr int kNumBars = kBarOut + kSlots;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
@@ -302,23 +309,29 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         asm volatile("bar.sync 1, 288;" ::: "memory");
         uint16_t* wup = reinterpret_cast<uint16_t*>(sgen + kOffWup);
         uint16_t* wdn = reinterpret_cast<uint16_t*>(sgen + kOffWdn);
-        for (int i = t2; i < 64 * 6 + 32 * 12; i += kThreads - 32) {
-            if (i < 384) {                                          // up: column e, i-th tap of its phase: tap = e + 11 - 2 kappa
+        for (int i = t2; i < 16 * 6 + 16 * 12; i += kThreads - 32) {
+            if (i < 96) {                                           // up: column e, i-th tap of its phase: tap = e + 11 - 2 kappa
                 const int e = i / 6, ii = i - e * 6;
                 const int tap = ((e + 11) & 1) + 2 * ii;
-                const int kappa = (e + 11 - tap) >> 1;              // 0 .. 37 over slices 0 .. 2
-                const int sl = kappa >> 4, k = kappa & 15;
-                const int off = (k >> 3) * (64 * 8) + e * 8 + (k & 7);
-                wup[(0 * kUpSlices + sl) * (kWupBytes / 2) + off] = a.up_hi[tap];
-                if (kUpMats == 2) wup[(1 * kUpSlices + sl) * (kWupBytes / 2) + off] = a.up_lo[tap];
+                const int kappa = (e + 11 - tap) >> 1;              // 0 .. 13: 16 u-values need 14 samples = ONE K slice
+                // variant 0: the slice starts at the block's first sample; variants 1 / 2 serve the block that straddles two
+                // chunks: rows moved down by 8 (samples 8..15 of the slice = the block's first 8) / up by 8 (its last 6)
+                const int var = kappa < 8 ? 1 : 2, kv = kappa < 8 ? kappa + 8 : kappa - 8;
+                const int off0 = (kappa >> 3) * (16 * 8) + e * 8 + (kappa & 7), offv = (kv >> 3) * (16 * 8) + e * 8 + (kv & 7);
+                wup[(0 * kUpVariants + 0) * (kWBytes / 2) + off0] = a.up_hi[tap];
+                wup[(0 * kUpVariants + var) * (kWBytes / 2) + offv] = a.up_hi[tap];
+                if (kUpMats == 2) {
+                    wup[(1 * kUpVariants + 0) * (kWBytes / 2) + off0] = a.up_lo[tap];
+                    wup[(1 * kUpVariants + var) * (kWBytes / 2) + offv] = a.up_lo[tap];
+                }
             } else {                                                // down: column e, tap: kappa = 2 e + 5 + tap
-                const int i2 = i - 384;
+                const int i2 = i - 96;
                 const int e = i2 / 12, tap = i2 - e * 12;
-                const int kappa = 2 * e + 5 + tap;                  // 5 .. 78 over slices 0 .. 4
+                const int kappa = 2 * e + 5 + tap;                  // 5 .. 46 over slices a, b, c
                 const int sl = kappa >> 4, k = kappa & 15;
-                const int off = (k >> 3) * (32 * 8) + e * 8 + (k & 7);
-                wdn[(0 * kDnSlices + sl) * (kWdnBytes / 2) + off] = a.dn_hi[tap];
-                if (kDnMats == 2) wdn[(1 * kDnSlices + sl) * (kWdnBytes / 2) + off] = a.dn_lo[tap];
+                const int off = (k >> 3) * (16 * 8) + e * 8 + (k & 7);
+                wdn[(0 * kDnSlices + sl) * (kWBytes / 2) + off] = a.dn_hi[tap];
+                if (kDnMats == 2) wdn[(1 * kDnSlices + sl) * (kWBytes / 2) + off] = a.dn_lo[tap];
             }
         }
         if (warp == 1) AFA_TC_STAMP(3, 0, 3);
@@ -367,41 +380,49 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // InstrDescriptor: D f32 [4,6) = 1, A bf16 [7,10) = 1, B bf16 [10,13) = 1, K-major both, N >> 3 [17,23), M >> 4 [24,29)
-        constexpr uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        constexpr uint32_t idesc_dn = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t bup = bdesc_kmajor(sbase + kOffWup, 64 * 16);     // + kWupBytes >> 4 per matrix; the lo set follows the hi set
-        const uint64_t bdn = bdesc_kmajor(sbase + kOffWdn, 32 * 16);     // + kWdnBytes >> 4 per matrix
-        const uint64_t ax = adesc_sw128(sbase);                          // x slice k: chunk slot (k / 4) % kSlots, + (k % 4) * 32 bytes
-        // U(bu) <- x slices 2 bu .. 2 bu + 2; xs = ring slot of the chunk that holds slice 2 bu
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bup = bdesc_kmajor(sbase + kOffWup, 16 * 16);     // + kWBytes >> 4 per matrix; the lo set follows the hi set
+        const uint64_t bdn = bdesc_kmajor(sbase + kOffWdn, 16 * 16);
+        const uint64_t ax = adesc_sw128(sbase);                          // chunk slot s: + s * (kChunkBytes >> 4); 8 samples = one 16-byte unit
+        constexpr uint64_t kW = kWBytes >> 4;
+        // The products are cut to the band: N = 16 everywhere, so the dense K x N rectangle the tensor core multiplies is 16 x 16
+        // around a band of 6-7 (up) / 12 (down) taps -- 160 MACs per output against 352 with N = 64 / 32 products, i.e. less
+        // than half the tensor-pipe time and energy for 22 instead of 16 instructions per block.
+        // U(bu) <- four blocks of 16 u-values, each from ONE K slice that starts at the block's own first sample (8-sample = 16-byte
+        // granular start inside the 128-byte swizzled row); xs = ring slot of the chunk that holds sample 32 bu of the lane's window
         auto up = [&](uint32_t d, int bu, int xs) {
-            const int xs1 = xs + 1 == kSlots ? 0 : xs + 1;
-            uint64_t xd[3];
-            if (bu & 1) {                                                // sub-slices 2, 3 of the chunk, 0 of the next
-                xd[0] = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 4);
-                xd[1] = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 6);
-                xd[2] = ax + (uint64_t)(xs1 * (kChunkBytes >> 4));
-            } else {                                                     // sub-slices 0, 1, 2
-                xd[0] = ax + (uint64_t)(xs * (kChunkBytes >> 4));
-                xd[1] = xd[0] + 2;
-                xd[2] = xd[0] + 4;
-            }
+            const uint64_t cb = ax + (uint64_t)(xs * (kChunkBytes >> 4) + (bu & 1) * 4);
 #pragma unroll
-            for (int k = 0; k < kUpSlices; ++k) {
-                mma_ss(d, xd[k], bup + (uint64_t)(k * (kWupBytes >> 4)), idesc_up, k > 0);
-                if (kUpMats == 2) mma_ss(d, xd[k], bup + (uint64_t)((kUpSlices + k) * (kWupBytes >> 4)), idesc_up, 1);
+            for (int m = 0; m < 4; ++m) {
+                if (m == 3 && (bu & 1)) {
+                    // samples 56 .. 69 of the chunk: the slice would leave the 128-byte row.  Two slices instead: samples 48..63 of
+                    // this chunk against the taps moved down 8 rows, samples 0..15 of the next chunk against the taps moved up 8
+                    const int xs1 = xs + 1 == kSlots ? 0 : xs + 1;
+                    const uint64_t a1 = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 6), a2 = ax + (uint64_t)(xs1 * (kChunkBytes >> 4));
+                    mma_ss(d + 48, a1, bup + 1 * kW, idesc, 0);
+                    if (kUpMats == 2) mma_ss(d + 48, a1, bup + (kUpVariants + 1) * kW, idesc, 1);
+                    mma_ss(d + 48, a2, bup + 2 * kW, idesc, 1);
+                    if (kUpMats == 2) mma_ss(d + 48, a2, bup + (kUpVariants + 2) * kW, idesc, 1);
+                } else {
+                    mma_ss(d + 16 * m, cb + m, bup, idesc, 0);
+                    if (kUpMats == 2) mma_ss(d + 16 * m, cb + m, bup + kUpVariants * kW, idesc, 1);
+                }
             }
         };
-        // Y(bd) <- the four s slices of S(bd) (columns 0, 8, 16, 24 of its slot) and the first of S(bd + 1); lands in the upper
-        // half of the slot of block bd + 1
+        // Y(bd) <- two blocks of 16 outputs, each from three s slices (columns 16 h + 0, 8, 16 of S(bd); column 32 is the first
+        // slice of S(bd + 1)); lands in the upper half of the slot of block bd + 1
         auto down = [&](int bd) {
             const uint32_t sl0 = tmem + (uint32_t)(kSlotCols * (bd & 3)), sl1 = tmem + (uint32_t)(kSlotCols * ((bd + 1) & 3));
             const uint32_t d = sl1 + 32;
 #pragma unroll
-            for (int k = 0; k < kDnSlices; ++k) {
-                const uint32_t aa = k < 4 ? sl0 + 8u * k : sl1;
-                mma_ts(d, aa, bdn + (uint64_t)(k * (kWdnBytes >> 4)), idesc_dn, k > 0);
-                if (kDnMats == 2) mma_ts(d, aa, bdn + (uint64_t)((kDnSlices + k) * (kWdnBytes >> 4)), idesc_dn, 1);
-            }
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k = 0; k < kDnSlices; ++k) {
+                    const int col = 16 * h + 8 * k;
+                    const uint32_t aa = col < 32 ? sl0 + (uint32_t)col : sl1;
+                    mma_ts(d + 16 * h, aa, bdn + (uint64_t)k * kW, idesc, k > 0);
+                    if (kDnMats == 2) mma_ts(d + 16 * h, aa, bdn + (uint64_t)(kDnSlices + k) * kW, idesc, 1);
+                }
         };
         // the compute threads have patched the replicate padding of x into the chunks that hold a row end (pre barrier); the
         // chunks themselves are awaited here, in the order the up-filter products need them
