@@ -394,7 +394,8 @@ def _tc_forward(x, alpha, beta, logscale, mode, ny=0, rlog2=-1):
 
 
 TC_EDGE = [(1, 8, 64), (1, 8, 72), (2, 3, 128), (3, 5, 1000), (1, 24, 8), (2, 24, 256), (1, 128, 264), (1, 130, 512),
-           (2, 24, 2040), (5, 7, 4104), (1, 16, 16), (2, 12, 24), (1, 9, 40)]
+           (2, 24, 2040), (5, 7, 4104), (1, 16, 16), (2, 12, 24), (1, 9, 40),
+           (2, 6, 1040), (1, 10, 2072), (1, 4, 1936)]      # T % 32 = 16 / 24 / 16: the row end at every position (element 10, 26, 42, 58) of a 64-value block
 
 
 @pytest.mark.parametrize("kind,logscale", [("snakebeta", True), ("snake", True), ("snakebeta", False), ("snake", False)])
