@@ -34,7 +34,8 @@ int g_tc_rlog2 = -1;      // forced log2(rows per CTA) (-1 = heuristic)
 int g_tc_mats = 22;       // tap matrices per K slice, up * 10 + down: 2 = bf16 hi + lo (16 mantissa bits), 1 = taps rounded to bf16
 int g_tc_dbg_j0 = 0;      // harness: first block of the clock-stamp window
 
-// [rows, T] bf16 row-major, box = R rows x 64 samples, 128-byte swizzle, zero fill outside the tensor
+// [rows, T] bf16 row-major, box = R rows x 64 samples, 128-byte swizzle, zero fill outside the tensor.  Callers with
+// T % 8 == 4 pass PAIRS of rows as one map row (rows / 2, 2 T): the row pitch of a tensor map is a multiple of 16 bytes.
 int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled is not available from this driver");
@@ -104,10 +105,11 @@ void tc_set_tuning(int enable, int ny, int rlog2) {
 // large enough to fill the machine; everything else stays on the register-walk kernels of afa_kernels.cuh.
 bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, int64_t T, int dtype) {
     if (!g_tc_enable || dtype != AFA_DTYPE_BF16) return false;
-    if (T < 64 || (T % 8) != 0 || T >= (1ll << 30)) return false;
+    if (T < 64 || (T % 4) != 0 || T >= (1ll << 28)) return false;
     if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return false;
     const int64_t rows = batch * channels;
     if (rows < 8 || rows >= (1ll << 30)) return false;
+    if ((T % 8) != 0 && (rows % 2) != 0) return false;       // rows of 8-byte alignment travel as 16-byte aligned pairs
     if (g_tc_enable == 1) {
         // Built-in choice, fitted to same-box sustained sweeps against the register-walk kernel (profiles/r02_tc_sweep_v9.log):
         // this kernel wins by 20-60 % on eight-clip launches (3.5-3.9 against 2.2-3.1 TB/s), by 25-30 % on the training
@@ -119,7 +121,9 @@ bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, 
     return encode_fn() != nullptr;
 }
 
-void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rgroups, int64_t* n_tstrips) {
+void tc_plan(int64_t rows_in, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rgroups, int64_t* n_tstrips) {
+    const int64_t halves = (T % 8) != 0 ? 2 : 1;               // tensor rows per tensor-map row
+    const int64_t rows = rows_in / halves;
     int rlog2 = 3;
     for (int cand = 7; cand >= 3; --cand) {
         const int64_t R = 1ll << cand;
@@ -139,8 +143,8 @@ void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rg
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = 2 * (sms > 0 ? sms : 148);
     }
-    const int64_t tb = (T + 15) / 16;                                  // blocks per row
-    auto strips = [&](int64_t ny) { return (tb + G * ny - 1) / (G * ny); };
+    const int64_t tb = (T + 4 * (halves - 1) + 15) / 16;               // blocks per row (the second row of a pair starts 4 samples early)
+    auto strips = [&](int64_t ny) { return (halves * ((tb + ny - 1) / ny) + G - 1) / G; };      // CTAs per row group: G lane strips each
     int64_t ny = 16, best = -1;
     auto consider = [&](int64_t cand) {
         cand = (cand + 3) / 4 * 4;
@@ -152,7 +156,7 @@ void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rg
     for (int cand = 4; cand <= 16; cand += 4) consider(cand);
     for (int w = 1; w <= 8; ++w) {
         const int64_t nts = (int64_t)slots * w / rg;                   // strips per row group that fill w waves
-        if (nts >= 1) consider((tb + G * nts - 1) / (G * nts));
+        if (nts >= 1) consider((halves * tb + G * nts - 1) / (G * nts));
     }
     if (g_tc_ny >= 4 && g_tc_ny % 4 == 0) ny = g_tc_ny;
     *rlog2_out = rlog2;
@@ -170,11 +174,15 @@ int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta,
     tc_plan(rows, T, &rlog2, &ny, &rg, &ts);
     if (rg * ts >= (1ll << 31)) return set_error(AFA_ERR_TOO_LARGE, "grid of %lld CTAs", (long long)(rg * ts));
     CUtensorMap tmx, tmy;
-    if (int rc = make_map(&tmx, x, rows, T, 1 << rlog2)) return rc;
-    if (int rc = make_map(&tmy, y, rows, T, 1 << rlog2)) return rc;
+    const int64_t halves = (T % 8) != 0 ? 2 : 1;
+    if (int rc = make_map(&tmx, x, rows / halves, T * halves, 1 << rlog2)) return rc;
+    if (int rc = make_map(&tmy, y, rows / halves, T * halves, 1 << rlog2)) return rc;
     afa_tc::Args a;
     memset(&a, 0, sizeof(a));
     a.x = static_cast<const __nv_bfloat16*>(x);
+    a.y = static_cast<__nv_bfloat16*>(y);
+    a.halves = (int32_t)halves;
+    a.spr = (int32_t)(((T + 4 * (halves - 1) + 15) / 16 + ny - 1) / ny);      // the second row of a pair is covered 4 samples early
     a.alpha = alpha;
     a.beta = beta;
     const int mats = g_tc_mats;

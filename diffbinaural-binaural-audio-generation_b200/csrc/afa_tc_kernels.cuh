@@ -3,7 +3,9 @@
 //
 // What it replaces (reference, /root/reference/BigVGAN): alias_free_activation/act.py:25-30 =
 // resample.py:29-38 (UpSample1d) + activations.py:51-62 / 113-126 (Snake / SnakeBeta) + filter.py:94-101
-// (LowPassFilter1d, stride 2), for dense row-major [rows = batch*channels, T] bf16 tensors with T % 8 == 0.
+// (LowPassFilter1d, stride 2), for dense row-major [rows = batch*channels, T] bf16 tensors with T % 8 == 0 -- or T % 8 == 4 and
+// an even number of rows (stage 0 of a clip with an odd number of mel frames: T = 4 * 861): such rows are only 8-byte aligned
+// and travel through the tensor maps as 16-byte aligned PAIRS (see `halves` below).
 //
 // Why: the register-walk kernel of afa_kernels.cuh spends 24 of its 27 instructions per output on the two
 // 12-tap FIRs and is bound by the FP32 FMA pipe -- at bf16 I/O it reaches 0.29-0.44 of the HBM roofline
@@ -77,6 +79,7 @@ constexpr int kSmemBytes = kOffTmem + 16 + 1024;         // + slack for the manu
 
 struct Args {
     const __nv_bfloat16* x;
+    __nv_bfloat16* y;
     const float* alpha;
     const float* beta;
     uint16_t up_hi[12], up_lo[12];   // 2 * upsample taps (ratio folded, resample.py:33): bf16 hi + lo, or fp16 in up_hi (kMats = 1)
@@ -85,6 +88,8 @@ struct Args {
     int32_t R_log2;        // lanes = R rows x G groups, R = 1 << R_log2
     int32_t NY;            // outputs per lane and CTA in units of 16: a multiple of 4, any length (the chunk ring is recycled)
     int32_t n_tstrips;     // CTAs along time; blockIdx.x = row_group * n_tstrips + tstrip
+    int32_t halves;        // 1: tensor-map rows = tensor rows.  2 (T % 8 == 4, even row count): tensor-map rows = PAIRS of rows, 2T wide
+    int32_t spr;           // lane strips (16 * NY outputs) per tensor row
     int32_t debug;         // harness only: 1 = dump U blocks, 2 = dump S, 3 = clock stamps of CTA dbg_cta
     int32_t dbg_cta;
     int32_t dbg_blocks;    // harness: 64-value blocks per lane the U / S dump holds (NY / 2 + 1)
@@ -271,7 +276,14 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int rgroup = (int)(blockIdx.x / (uint32_t)a.n_tstrips);
     const int row0 = rgroup * R;
     const int span = 16 * NY;                       // outputs per lane
-    const int t_cta0 = tstrip * G * span;           // first output of time group 0
+    // Time group g of this CTA is lane strip vs = tstrip * G + g of the tensor-map row: strips 0 .. spr-1 belong to the first
+    // tensor row of the pair (or to the only one), spr .. 2 spr - 1 to the second, which starts T elements into the map row.
+    // first_out(g): first output of the group relative to ITS tensor row; col0(g): the same position as a map column.  The TMA
+    // unit moves 16-byte units: map columns must be multiples of 8 elements, and the second row of a pair starts at column T
+    // = 4 (mod 8) -- its strips are shifted 4 samples to the left (first_out = -4 for its first strip).
+    auto half_of = [&](int g) { const int vs = tstrip * G + g; return vs / a.spr; };
+    auto first_out = [&](int g) { const int vs = tstrip * G + g; return (vs % a.spr) * span - ((a.halves == 2 && vs / a.spr == 1) ? 4 : 0); };
+    auto col0 = [&](int g) { const int hh = half_of(g); return (hh < a.halves ? hh * a.T : 2 * a.halves * a.T + 64) + first_out(g); };
     const int T = a.T;
     const uint32_t bars = sbase + kOffBar;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + kOffTmem);
@@ -284,7 +296,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
                 mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
                 for (int g = 0; g < G; ++g)
-                    tma_load_2d(sbase + p * kChunkBytes + g * R * 128, &tm_x, t_cta0 + g * span - 8 + 64 * p, row0,
+                    tma_load_2d(sbase + p * kChunkBytes + g * R * 128, &tm_x, col0(g) - 8 + 64 * p, row0,
                                 bars + 8 * (kBarFull + p));
             }
             mbar_init(bars + 8 * kBarPre, 8);
@@ -352,7 +364,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (elect_one()) {
                 mbar_expect_tx(bars + 8 * (kBarFull + 0), (uint32_t)kChunkBytes);
                 for (int g = 0; g < G; ++g)
-                    tma_load_2d(sbase + g * R * 128, &tm_x, t_cta0 + g * span - 8 + 64 * kSlots, row0, bars + 8 * (kBarFull + 0));
+                    tma_load_2d(sbase + g * R * 128, &tm_x, col0(g) - 8 + 64 * kSlots, row0, bars + 8 * (kBarFull + 0));
             }
             __syncwarp();
         }
@@ -360,15 +372,20 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int slot = (qc + 1) % kSlots;
             mbar_wait(bars + 8 * (kBarOut + slot), (uint32_t)(qc / kSlots) & 1u);
             if (elect_one()) {
-                for (int g = 0; g < G; ++g)
-                    tma_store_2d(&tm_y, t_cta0 + g * span + 64 * qc, row0, sbase + slot * kChunkBytes + g * R * 128);
+                for (int g = 0; g < G; ++g) {
+                    // the first row of a pair must not write past its end (the second row's samples follow it in the map row):
+                    // chunks beyond the end are dropped, the chunk that crosses it is written by the compute threads
+                    const int hh = half_of(g), o0 = first_out(g) + 64 * qc;
+                    if ((hh + 1 < a.halves && o0 + 64 > T) || o0 < 0) continue;      // (o0 < 0: the shifted first chunk of a second row)
+                    tma_store_2d(&tm_y, col0(g) + 64 * qc, row0, sbase + slot * kChunkBytes + g * R * 128);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 const int nc = qc + 1 + kSlots;                     // next x chunk for this slot
                 if (nc < NCH_IN) {
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has finished reading the slot
                     mbar_expect_tx(bars + 8 * (kBarFull + slot), (uint32_t)kChunkBytes);
                     for (int g = 0; g < G; ++g)
-                        tma_load_2d(sbase + slot * kChunkBytes + g * R * 128, &tm_x, t_cta0 + g * span - 8 + 64 * nc, row0,
+                        tma_load_2d(sbase + slot * kChunkBytes + g * R * 128, &tm_x, col0(g) - 8 + 64 * nc, row0,
                                     bars + 8 * (kBarFull + slot));
                 }
             }
@@ -464,16 +481,19 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int l = q * 32 + lane;                             // TMEM lane = row of the MMA tile
         const int g = l >> a.R_log2, r = l & (R - 1);
-        const int row = row0 + r;
-        const int t_org = t_cta0 + g * span - 8;
+        const int hh = half_of(g);
+        const int row = hh < a.halves ? (row0 + r) * a.halves + hh : a.rows;      // tensor row of this lane (a.rows: none)
+        const int t_org = first_out(g) - 8;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t srow = sbase + (uint32_t)l * 128u;
         const uint32_t sw = (uint32_t)(l & 7);
         float a_eff = 1.f, ib = 1.f;
-        const bool left_lane = t_org < 0;                        // the lane starts its row (t_org = -8)
-        // first 8-sample chunk of the lane's window that lies beyond the row (T % 8 == 0: chunk granular), if any
+        const bool left_lane = t_org < 0;                        // the lane starts its row (t_org = -8; -12 for the second row of a pair)
+        // first 8-sample (16-byte) chunk of the lane's window that holds samples beyond the row, if any; T % 8 == 4: its first
+        // four samples still belong to the row
         const int cb = (T - t_org) >> 3;
         const bool right_lane = T > t_org && cb < 8 * NCH_IN;       // cb: 8-sample units from the lane's window start
+        const bool half_chunk = ((T - t_org) & 7) != 0;
         if (row < a.rows) {
             const int c = row % a.C;
             float al = __ldg(a.alpha + c);
@@ -496,12 +516,16 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     if (left_lane && c == 0) {
                         const uint32_t v = __ldg(xr16), xl = v | (v << 16);
                         asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(cbase + ((0u ^ sw) << 4)), "r"(xl) : "memory");
+                        if (t_org == -12) asm volatile("st.shared.v2.b32 [%0], {%1,%1};" ::"r"(cbase + ((1u ^ sw) << 4)), "r"(xl) : "memory");
                     }
                     if (right_lane) {
                         const uint32_t v = __ldg(xr16 + (T - 1)), xr = v | (v << 16);
                         for (int cc = cb; cc < cb + 2; ++cc)
-                            if ((cc >> 3) == c)
-                                asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(cbase + (((uint32_t)(cc & 7) ^ sw) << 4)), "r"(xr) : "memory");
+                            if ((cc >> 3) == c) {
+                                const uint32_t ad = cbase + (((uint32_t)(cc & 7) ^ sw) << 4);
+                                if (cc == cb && half_chunk) asm volatile("st.shared.v2.b32 [%0], {%1,%1};" ::"r"(ad + 8), "r"(xr) : "memory");
+                                else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(ad), "r"(xr) : "memory");
+                            }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -560,26 +584,27 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tmem_ld16(tslot + 48, uc);
                 snake16(ub, sp + 8);
                 // replicate padding of the ACTIVATED signal (filter.py:98), in the 2x domain; rare -> uniform branch.  eb = element
-                // of n = 2T in this block (10, 26, 42 or 58 when inside): elements >= eb repeat element eb - 1.
+                // of n = 2T in this block (10, 26, 42, 58 -- or 2, 18, 34, 50 when T % 8 == 4 -- when inside): elements >= eb
+                // repeat element eb - 1.  kc = eb / 2 = first register (pair of elements) to overwrite, within a half of 16 registers
                 const int eb = 2 * (T - t_org) - 64 * b - 6;
-                const bool lclamp = left_lane && b == 0, rclamp = eb >= 10 && eb <= 58;
+                const bool lclamp = left_lane && b == 0, rclamp = eb >= 2 && eb <= 58;
                 uint32_t fill = 0;
                 const bool any_clamp = __any_sync(0xffffffffu, lclamp || rclamp);
+                auto clamp_from = [&](int kc) {                   // kc in {1, 5, 9, 13}: fill = upper element of register kc - 1
+                    fill = __byte_perm(kc == 1 ? sp[0] : kc == 5 ? sp[4] : kc == 9 ? sp[8] : sp[12], 0, 0x3232);
+#pragma unroll
+                    for (int e = 1; e < 16; ++e)
+                        if (e >= kc) sp[e] = fill;
+                };
                 if (any_clamp) {
-                    if (lclamp) {                                 // n < 0 <-> e < 10: s[0] is element 10
-                        const uint32_t s0 = __byte_perm(sp[5], sp[5], 0x1010);
+                    if (lclamp) {                                 // n < 0 <-> e < 10 (18 with t_org = -12): s[0] is element 10 (18)
+                        const int k0 = t_org == -12 ? 9 : 5;
+                        const uint32_t s0 = __byte_perm(k0 == 9 ? sp[9] : sp[5], 0, 0x1010);
 #pragma unroll
-                        for (int e = 0; e < 5; ++e) sp[e] = s0;
+                        for (int e = 0; e < 9; ++e)
+                            if (e < k0) sp[e] = s0;
                     }
-                    if (eb == 10) {
-                        fill = __byte_perm(sp[4], sp[4], 0x3232);
-#pragma unroll
-                        for (int e = 5; e < 16; ++e) sp[e] = fill;
-                    } else if (eb == 26) {
-                        fill = __byte_perm(sp[12], sp[12], 0x3232);
-#pragma unroll
-                        for (int e = 13; e < 16; ++e) sp[e] = fill;
-                    }
+                    if (rclamp && eb < 32) clamp_from(eb >> 1);
                 }
                 if (kDebug && a.debug == 2 && dbg_row) {
 #pragma unroll
@@ -596,18 +621,12 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 }
                 snake16(ua, sp);
                 snake16(uc, sp + 8);
-                if (any_clamp) {
-                    if (eb == 10 || eb == 26) {
+                if (any_clamp && rclamp) {
+                    if (eb < 32) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) sp[e] = fill;
-                    } else if (eb == 42) {
-                        fill = __byte_perm(sp[4], sp[4], 0x3232);
-#pragma unroll
-                        for (int e = 5; e < 16; ++e) sp[e] = fill;
-                    } else if (eb == 58) {
-                        fill = __byte_perm(sp[12], sp[12], 0x3232);
-#pragma unroll
-                        for (int e = 13; e < 16; ++e) sp[e] = fill;
+                    } else {
+                        clamp_from((eb - 32) >> 1);
                     }
                 }
                 if (kDebug && a.debug == 2 && dbg_row) {
@@ -644,6 +663,19 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 for (int c = 0; c < 4; ++c)
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((c0 + c) ^ sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                                  "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+                if (a.halves == 2) {
+                    // first row of a pair, chunk that crosses the row end -- or second row, first chunk (it starts 4 samples before
+                    // the row): the TMA store skips it (it would write into the other row); the lanes write their valid outputs
+                    // themselves, 4 samples (8 bytes: what the row start is aligned to) at a time
+                    const int o0 = t_org + 8 + 64 * (i >> 1);
+                    if (row < a.rows && ((hh == 0 && o0 < T && o0 + 64 > T) || o0 < 0)) {
+                        const int tb0 = t_org + 8 + 32 * i;
+                        __nv_bfloat16* yr = a.y + (size_t)row * (size_t)T;
+#pragma unroll
+                        for (int v = 0; v < 8; ++v)
+                            if (tb0 + 4 * v >= 0 && tb0 + 4 * v < T) *reinterpret_cast<uint2*>(yr + tb0 + 4 * v) = make_uint2(pk[2 * v], pk[2 * v + 1]);
+                    }
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + ((i >> 1) + 1) % kSlots));

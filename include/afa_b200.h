@@ -258,7 +258,7 @@ int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map,
  * which=2: channels-last forward, segment length = 12 * chunks + 2 samples.
  * which=3: tensor path of the fused activation+convolution: chunks = 1 tcgen05 (default), 0 legacy mma.sync.
  * which=4: its input staging: chunks = 1 bulk-copy the tile's input rows into shared memory (default), 0 global loads.
- * which=5: tensor-core forward (bf16 tensors, T % 8 == 0, 16-byte aligned x and y: both FIR filters as banded-Toeplitz
+ * which=5: tensor-core forward (bf16 tensors, T % 8 == 0 -- or T % 8 == 4 with an even batch * channels --, 16-byte aligned x and y: both FIR filters as banded-Toeplitz
  *          tcgen05 products, csrc/afa_tc_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible;
  *          threads = blocks of 16 outputs per TMEM lane and CTA (a multiple of 4 up to 4096; 0 = built-in choice).
  * which=6: its rows per CTA as log2 (3..7; -1 = built-in choice).

@@ -395,7 +395,10 @@ def _tc_forward(x, alpha, beta, logscale, mode, ny=0, rlog2=-1):
 
 TC_EDGE = [(1, 8, 64), (1, 8, 72), (2, 3, 128), (3, 5, 1000), (1, 24, 8), (2, 24, 256), (1, 128, 264), (1, 130, 512),
            (2, 24, 2040), (5, 7, 4104), (1, 16, 16), (2, 12, 24), (1, 9, 40),
-           (2, 6, 1040), (1, 10, 2072), (1, 4, 1936)]      # T % 32 = 16 / 24 / 16: the row end at every position (element 10, 26, 42, 58) of a 64-value block
+           (2, 6, 1040), (1, 10, 2072), (1, 4, 1936),      # T % 32 = 16 / 24 / 16: the row end at every position (element 10, 26, 42, 58) of a 64-value block
+           # T % 8 == 4 with an even row count: rows travel as 16-byte aligned PAIRS (second row shifted 4 samples, edge chunks written by
+           # the lanes); T % 32 = 4, 12, 20, 28 puts the row end at elements 2, 18, 34, 50
+           (1, 8, 68), (2, 7, 100), (4, 5, 260), (3, 6, 1004), (2, 24, 2052), (1, 130, 516), (5, 8, 4100), (1, 16, 2060), (2, 4, 1972), (1, 12, 3444)]
 
 
 @pytest.mark.parametrize("kind,logscale", [("snakebeta", True), ("snake", True), ("snakebeta", False), ("snake", False)])
@@ -429,7 +432,8 @@ def test_tensor_core_forward_edge_grid(kind, logscale):
             assert (y.float() - y_walk.float()).abs().max().item() <= 4 * 2.0 ** -8 * max(1.0, float(np.abs(y_ref).max())), tag
 
 
-@pytest.mark.parametrize("shape", [(2, 24, 220416), (16, 768, 3440), (16, 384, 13776), (32, 96, 2048), (2, 512, 8192), (16, 24, 220416)])
+@pytest.mark.parametrize("shape", [(2, 24, 220416), (16, 768, 3440), (16, 384, 13776), (32, 96, 2048), (2, 512, 8192), (16, 24, 220416),
+                                   (16, 768, 3444), (2, 768, 3444)])
 def test_tensor_core_forward_model_sizes(shape):
     """bf16 at the sizes the bench runs (the full-size test was fp32 only): against the torch-op oracle in
     fp32 on the same device evaluated on the bf16 input, bitwise run-to-run determinism, and the DC identity."""
