@@ -996,6 +996,39 @@ def run_gpu(args):
             torch_gpu = gpu_torch_baseline(dev, args.clips, args.t_mel)
         except Exception as exc:  # noqa: BLE001
             per_shape = {"error": repr(exc)[:200]}
+    bf16_step = None
+    if rank == 0 and world == 1 and not args.no_per_shape and args.dtype == "fp32":
+        # the same 109-call step with bf16 tensors (BASELINE config 2 names fp32 + bf16): the tensor-core forward
+        # wherever it is eligible, the register-walk kernel elsewhere; same timing rules as the headline
+        try:
+            torch.cuda.empty_cache()
+            wl16 = Workload(dev, args.clips, args.t_mel, torch.bfloat16)
+            wl16.step_device()
+            torch.cuda.synchronize(dev)
+            g16 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g16):
+                wl16.step_device()
+            for _ in range(max(3, args.warmup)):
+                g16.replay()
+            torch.cuda.synchronize(dev)
+            with ClockSampler(local_rank) as clocks16:
+                e0.record()
+                for _ in range(args.steps):
+                    g16.replay()
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms16 = e0.elapsed_time(e1) / args.steps
+            by16 = wl16.elements * 4
+            n_tc = sum(s["calls"] for s in wl16.stages if (s["shape"][2] % 8 == 0 or (s["shape"][2] % 4 == 0 and (s["shape"][0] * s["shape"][1]) % 2 == 0))
+                       and s["shape"][2] >= 256 and s["shape"][0] * s["shape"][1] * s["shape"][2] >= (6 << 20))
+            bf16_step = {"metric": METRIC, "value": round(by16 / (ms16 * 1e-3) / 1e9, 3), "unit": UNIT, "dtype": "bf16 I/O, f32 math",
+                         "ms_per_step": round(ms16, 4), "steps": args.steps, "frac_of_measured_peak": round(by16 / (ms16 * 1e-3) / 1e9 / peak, 4),
+                         "algorithmic_bytes_per_step": by16, "launches_per_step": wl16.launches,
+                         "kernels": f"{n_tc} x afa_tc::afa_tc_fwd_kernel (tcgen05), {wl16.launches - n_tc} x afa::afa_fwd_kernel",
+                         "clocks": clocks16.summary()}
+            del wl16, g16
+        except Exception as exc:  # noqa: BLE001
+            bf16_step = {"error": repr(exc)[:200]}
     train = None
     if not args.no_train:
         try:
@@ -1041,6 +1074,7 @@ def run_gpu(args):
             "channels_last_amp_kernels": channels_last,
             "log_mel": mel,
             "roofline_per_shape": per_shape,
+            "bf16_step": bf16_step,
             "gpu_torch_baseline": torch_gpu,
             "train": train,
         }
