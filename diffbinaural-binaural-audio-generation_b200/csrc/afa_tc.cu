@@ -111,10 +111,11 @@ bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, 
     if (rows < 8 || rows >= (1ll << 30)) return false;
     if ((T % 8) != 0 && (rows % 2) != 0) return false;       // rows of 8-byte alignment travel as 16-byte aligned pairs
     if (g_tc_enable == 1) {
-        // Built-in choice, fitted to same-box sustained sweeps against the register-walk kernel (profiles/r02_tc_sweep_v9.log):
-        // this kernel wins by 20-60 % on eight-clip launches (3.5-3.9 against 2.2-3.1 TB/s), by 25-30 % on the training
-        // shapes (batch 32) and by 0-15 % on single-clip launches; the walk kernel keeps the short launches (< 6 M elements,
-        // where this kernel's set-up and pipeline fill weigh most) and rows shorter than 256 samples.
+        // Built-in choice, fitted to same-box sustained sweeps against the register-walk kernel
+        // (profiles/r02_tc_sweep_v10_sustained.log): this kernel wins by 30-70 % on eight-clip launches (3.8-4.2 against
+        // 2.2-3.1 TB/s), by 25-30 % on the training shapes (batch 32) and by 3-25 % on single-clip launches; the walk kernel
+        // keeps the short launches (< 6 M elements, where this kernel's set-up and pipeline fill weigh most) and rows shorter
+        // than 256 samples.
         const int64_t n = rows * T;
         if (T < 256 || n < (6ll << 20)) return false;
     }
@@ -136,7 +137,8 @@ void tc_plan(int64_t rows_in, int64_t T, int* rlog2_out, int* ny_out, int64_t* n
     // Blocks of 16 outputs per lane and CTA (NY, a multiple of 4).  A CTA streams its strip through a recycled chunk ring, so a
     // strip may be any length: its set-up, pipeline fill and drain cost ~5 block-times once, and the grid runs in waves of
     // 2 CTAs per SM.  Candidates: the short strips (4 ... 16) and the strip lengths that make the grid exactly w waves; the
-    // cheapest under  waves * (5 + NY)  wins, the longer strip on ties (profiles/r02_tc_sweep*.log).
+    // cheapest under  waves * (5 + NY)  wins, the longer strip on ties (profiles/r02_tc_sweep_v8_sustained_ny.log,
+    // profiles/r02_tc_timeline_power.txt section 7).
     static int slots = 0;
     if (!slots) {
         int dev = 0, sms = 148;
