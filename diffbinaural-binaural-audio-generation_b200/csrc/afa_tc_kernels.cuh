@@ -73,7 +73,8 @@ constexpr int kOffWup = kSlots * kChunkBytes;                    // [hi/lo][vari
 constexpr int kOffWdn = kOffWup + 2 * kUpVariants * kWBytes;     // [hi/lo][slice] x 512 B
 constexpr int kOffBar = kOffWdn + 2 * kDnSlices * kWBytes;
 constexpr int kBarFull = 0, kBarPre = kSlots, kBarCmp = kBarPre + 1, kBarEv = kBarCmp + 8, kBarOut = kBarEv + 8;
-constexpr int kNumBars = kBarOut + kSlots;
+constexpr int kBarEvY = kBarOut + kSlots;      // Y(e-1) complete: committed between the down and the up products of event e
+constexpr int kNumBars = kBarEvY + 8;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;         // + slack for the manual 1024-byte alignment
 
@@ -228,12 +229,13 @@ __device__ __forceinline__ float snake_f(float u, float a, float ib) {
 //                               down(e-1): S(e-1) and the first slice of S(e) -> Y(e-1) in columns 32..63 of slot e % 4 (the
 //                               half of U(e) that Snake has consumed);
 //                               up(e+3): x slices 2e+6 .. 2e+8 straight from the swizzled chunks -> U(e+3) in slot (e-1) % 4;
-//                               ONE commit -> ev[(e+3) & 7]  (tcgen05.commit tracks every MMA issued before it)
+//                               commit -> evy[e & 7] after the down products, commit -> ev[(e+3) & 7] after the up products
+//                               (tcgen05.commit tracks every MMA issued before it)
 //   iteration b of its group:   wait ev[b & 7]  (event b-3: U(b) is complete -- issued a whole iteration of the OTHER group ago,
 //                               so the MMA round trip is off the group's critical path)
 //                               U(b) -> registers (4 loads of 16 columns, the next in flight behind the math) -> Snake ->
 //                               S(b) over columns 0..31 (two tcgen05.st)
-//                               wait ev[(b+2) & 7]  (event b-1: Y(b-2) is complete) -> registers -> bf16 -> shared memory
+//                               wait evy[(b-1) & 7]  (event b-1: Y(b-2) is complete) -> registers -> bf16 -> shared memory
 //                               (out chunk (b-2)/2, staged in the ring slot of x chunk (b-2)/2 + 1) -> proxy fence -> arrive out[...]
 //                               tcgen05.wait::st -> arrive cmp[b & 7]
 //   warp 0:                     wait out[q] (8 warp arrivals) -> TMA store of out chunk q -> the slot takes x chunk q + 6
@@ -302,6 +304,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_init(bars + 8 * kBarPre, 8);
             for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarCmp + i), 4);
             for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEv + i), 1);
+            for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEvY + i), 1);
             for (int i = 0; i < kSlots; ++i) mbar_init(bars + 8 * (kBarOut + i), 8);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
@@ -467,6 +470,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             AFA_TC_STAMP(0, e, 1);
             if (elect_one()) {
                 if (e >= 1) down(e - 1);
+                tc_commit(bars + 8 * (kBarEvY + (e & 7)));           // the groups wait for Y, not for the 8-10 up products behind it
                 if (bu <= NB) up(tmem + (uint32_t)(kSlotCols * (bu & 3)), bu, xs);
                 tc_commit(bars + 8 * (kBarEv + (bu & 7)));
             }
@@ -643,7 +647,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 // Y(b-2) (upper half of slot (b-1) % 4): fp32 accumulators -> bf16 -> the lane's row of out chunk (b-2)/2, staged
                 // in the ring slot of x chunk (b-2)/2 + 1
                 const int i = b - 2;
-                mbar_wait(bars + 8 * (kBarEv + ((b + 2) & 7)), (uint32_t)((b + 2) >> 3) & 1u);
+                mbar_wait(bars + 8 * (kBarEvY + ((b - 1) & 7)), (uint32_t)((b - 1) >> 3) & 1u);
                 tc_fence_after();
                 if (q == 2) AFA_TC_STAMP(1 + grp, b, 3);
                 const uint32_t yslot = tlane + (uint32_t)(kSlotCols * ((i + 1) & 3) + 32);
