@@ -291,32 +291,32 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + kOffTmem);
 
     if (warp == 0) {
-        if (elect_one()) {
-            // the loads first: the first kSlots chunks of the strip, G boxes of R rows x 64 samples per chunk
-            for (int p = 0; p < kSlots; ++p) mbar_init(bars + 8 * (kBarFull + p), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
-                mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
-                for (int g = 0; g < G; ++g)
-                    tma_load_2d(sbase + p * kChunkBytes + g * R * 128, &tm_x, col0(g) - 8 + 64 * p, row0,
-                                bars + 8 * (kBarFull + p));
-            }
-            mbar_init(bars + 8 * kBarPre, 8);
-            for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarCmp + i), 4);
-            for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEv + i), 1);
-            for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * (kBarEvY + i), 1);
-            for (int i = 0; i < kSlots; ++i) mbar_init(bars + 8 * (kBarOut + i), 8);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
+        // Barriers and the first loads, spread over the lanes: one elected thread needed ~115 cycles per TMA instruction and ~2000
+        // cycles for the 40-odd mbarrier inits -- with 8 boxes per chunk (one binaural clip: R = 16) the CTA's first data was
+        // requested 5300 cycles after kernel entry.  Lane i initialises barriers i and i + 32; lane g issues box g of every chunk.
+        for (int i = lane; i < kNumBars; i += 32) {
+            const uint32_t cnt = i == kBarPre ? 8u : (i >= kBarCmp && i < kBarEv) ? 4u : (i >= kBarOut && i < kBarEvY) ? 8u : 1u;
+            mbar_init(bars + 8 * i, cnt);
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
+            if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
+            __syncwarp();
+            if (lane < G)
+                tma_load_2d(sbase + p * kChunkBytes + lane * R * 128, &tm_x, col0(lane) - 8 + 64 * p, row0, bars + 8 * (kBarFull + p));
+        }
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
         __syncwarp();
         AFA_TC_STAMP(3, 0, 0);
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        AFA_TC_STAMP(3, 0, 1);
     } else {
         // banded Toeplitz B matrices (hi + lo bf16 split of the taps), K-major core-matrix layout: element (n, k) of a matrix at
         // (k / 8) * (N * 8) + n * 8 + (k % 8).  Zero fill by 16-byte stores, then the 6 (up) / 12 (down) taps of every column.
+        if (warp == 1) {                                           // tensor-memory allocation, beside warp 0's loads
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+            AFA_TC_STAMP(3, 0, 1);
+        }
         if (warp == 1) AFA_TC_STAMP(3, 0, 2);
         const int t2 = tid - 32;                                   // 0 .. 287
         uint4* wz = reinterpret_cast<uint4*>(sgen + kOffWup);
@@ -364,37 +364,37 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // as soon as up(0) and up(1) have read it
         if (kSlots < NCH_IN) {
             mbar_wait(bars + 8 * (kBarEv + 1), 0);
-            if (elect_one()) {
-                mbar_expect_tx(bars + 8 * (kBarFull + 0), (uint32_t)kChunkBytes);
-                for (int g = 0; g < G; ++g)
-                    tma_load_2d(sbase + g * R * 128, &tm_x, col0(g) - 8 + 64 * kSlots, row0, bars + 8 * (kBarFull + 0));
-            }
+            if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + 0), (uint32_t)kChunkBytes);
+            __syncwarp();
+            if (lane < G)
+                tma_load_2d(sbase + lane * R * 128, &tm_x, col0(lane) - 8 + 64 * kSlots, row0, bars + 8 * (kBarFull + 0));
             __syncwarp();
         }
+        // lane g moves box g (its own bulk group: commit / wait are per thread)
+        const int hh0 = half_of(lane < G ? lane : 0), fo0 = first_out(lane < G ? lane : 0), cl0 = col0(lane < G ? lane : 0);
         for (int qc = 0; qc < NCH_OUT; ++qc) {
             const int slot = (qc + 1) % kSlots;
             mbar_wait(bars + 8 * (kBarOut + slot), (uint32_t)(qc / kSlots) & 1u);
-            if (elect_one()) {
-                for (int g = 0; g < G; ++g) {
-                    // the first row of a pair must not write past its end (the second row's samples follow it in the map row):
-                    // chunks beyond the end are dropped, the chunk that crosses it is written by the compute threads
-                    const int hh = half_of(g), o0 = first_out(g) + 64 * qc;
-                    if ((hh + 1 < a.halves && o0 + 64 > T) || o0 < 0) continue;      // (o0 < 0: the shifted first chunk of a second row)
-                    tma_store_2d(&tm_y, col0(g) + 64 * qc, row0, sbase + slot * kChunkBytes + g * R * 128);
-                }
+            if (lane < G) {
+                // the first row of a pair must not write past its end (the second row's samples follow it in the map row):
+                // chunks beyond the end are dropped, the chunk that crosses it is written by the compute threads
+                const int o0 = fo0 + 64 * qc;
+                if (!((hh0 + 1 < a.halves && o0 + 64 > T) || o0 < 0))      // (o0 < 0: the shifted first chunk of a second row)
+                    tma_store_2d(&tm_y, cl0 + 64 * qc, row0, sbase + slot * kChunkBytes + lane * R * 128);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                const int nc = qc + 1 + kSlots;                     // next x chunk for this slot
-                if (nc < NCH_IN) {
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has finished reading the slot
-                    mbar_expect_tx(bars + 8 * (kBarFull + slot), (uint32_t)kChunkBytes);
-                    for (int g = 0; g < G; ++g)
-                        tma_load_2d(sbase + slot * kChunkBytes + g * R * 128, &tm_x, col0(g) - 8 + 64 * nc, row0,
-                                    bars + 8 * (kBarFull + slot));
-                }
+            }
+            const int nc = qc + 1 + kSlots;                         // next x chunk for this slot
+            if (nc < NCH_IN) {
+                if (lane < G) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stores have finished reading the slot
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + slot), (uint32_t)kChunkBytes);
+                __syncwarp();
+                if (lane < G)
+                    tma_load_2d(sbase + slot * kChunkBytes + lane * R * 128, &tm_x, cl0 - 8 + 64 * nc, row0, bars + 8 * (kBarFull + slot));
             }
             __syncwarp();
         }
-        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (lane < G) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         AFA_TC_STAMP(3, 1, 4);
     } else if (warp == 1) {
@@ -701,7 +701,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         reinterpret_cast<unsigned long long*>(a.dbg)[blockIdx.x * 4 + 1] = t;
     }
-    if (warp == 0) {
+    if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
     }
