@@ -36,7 +36,26 @@ int g_tc_dbg_j0 = 0;      // harness: first block of the clock-stamp window
 
 // [rows, T] bf16 row-major, box = R rows x 64 samples, 128-byte swizzle, zero fill outside the tensor.  Callers with
 // T % 8 == 4 pass PAIRS of rows as one map row (rows / 2, 2 T): the row pitch of a tensor map is a multiple of 16 bytes.
+// A map depends on (base, rows, T, R) only: the last few are kept per host thread, so an eager generator pass -- the same
+// buffers call after call -- pays the driver's encode (~1 us each, two per launch) once.
+struct MapKey {
+    const void* base;
+    int64_t rows, T;
+    int R;
+};
+struct MapSlot {
+    MapKey k;
+    CUtensorMap tm;
+    bool used;
+};
 int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) {
+    static thread_local MapSlot cache[16];
+    static thread_local unsigned next = 0;
+    for (MapSlot& c : cache)
+        if (c.used && c.k.base == base && c.k.rows == rows && c.k.T == T && c.k.R == R) {
+            *tm = c.tm;
+            return 0;
+        }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)rows};
@@ -47,6 +66,10 @@ int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) 
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    MapSlot& c = cache[next++ % 16];
+    c.k = MapKey{base, rows, T, R};
+    c.tm = *tm;
+    c.used = true;
     return 0;
 }
 
