@@ -35,7 +35,7 @@
 //     NY / 2 blocks of 32 outputs per lane.  x arrives as 64-sample chunks through a recycled ring of 5 slots;
 //     out-of-range samples and rows are zero-filled by the TMA unit; y is staged over the NEXT x chunk of the ring
 //     (dead by then) and leaves by TMA store (which clips what lies outside the tensor).
-//   * warp roles: warp 0 = TMA producer / TMEM allocator / TMA store; warp 1 = MMA issuer (one elected thread);
+//   * warp roles: warp 0 = TMA producer / TMA store; warp 1 = TMEM allocator and MMA issuer (one elected thread);
 //     warps 2-9 = two compute groups of four warps (one thread per TMEM lane) that alternate over the blocks.
 //     All hand-offs are mbarriers (tcgen05.commit on the MMA side); no CTA-wide barrier inside the block loop.
 //
@@ -57,7 +57,7 @@
 
 namespace afa_tc {
 
-constexpr int kThreads = 320;            // warp 0: TMA producer / TMEM allocator / TMA store, warp 1: MMA, warps 2..9: compute
+constexpr int kThreads = 320;            // warp 0: TMA producer / TMA store, warp 1: TMEM allocator + MMA issuer, warps 2..9: compute
 #ifndef AFA_TC_SLOTS
 #define AFA_TC_SLOTS 5
 #endif
