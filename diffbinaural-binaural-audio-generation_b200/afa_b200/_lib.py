@@ -11,11 +11,13 @@ AFA_DTYPE_F32 = 0
 AFA_DTYPE_BF16 = 1
 AFA_FLAG_LOGSCALE = 1
 AFA_FLAG_SNAKE = 2
+AFA_ERR_ALIGNMENT = -5
 
 EXPORTED_SYMBOLS = (
     "afa_version",
     "afa_last_error",
     "afa_activation1d_fwd",
+    "afa_activation1d_fwd_pitched",
     "afa_bwd_workspace_bytes",
     "afa_activation1d_bwd",
     "afa_amp_activation1d_fwd_cl",
@@ -62,6 +64,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.afa_last_error.restype = ctypes.c_char_p
         lib.afa_activation1d_fwd.restype = i32
         lib.afa_activation1d_fwd.argtypes = [vp, vp, vp, vp, fp, fp, i64, i64, i64, i32, i32, vp]
+        lib.afa_activation1d_fwd_pitched.restype = i32
+        lib.afa_activation1d_fwd_pitched.argtypes = [vp, i64, vp, i64, vp, vp, fp, fp, i64, i64, i64, i32, i32, vp]
         lib.afa_bwd_workspace_bytes.restype = ctypes.c_size_t
         lib.afa_bwd_workspace_bytes.argtypes = [i64, i64, i64, i32]
         lib.afa_activation1d_bwd.restype = i32

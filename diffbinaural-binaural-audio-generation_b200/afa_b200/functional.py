@@ -50,10 +50,38 @@ def _check_inputs(x: torch.Tensor, alpha: torch.Tensor, beta):
             raise RuntimeError(f"{name} is on {p.device}, x is on {x.device}")
 
 
+def _row_pitch(t) -> int:
+    """Elements between consecutive (batch, channel) rows of a [B, C, T] tensor whose rows are dense and equally spaced
+    (e.g. a time slice x[:, :, :T] of a longer buffer), or 0 when the layout is anything else."""
+    if t.dim() != 3 or t.stride(2) != 1:
+        return 0
+    B, C, T = t.shape
+    pitch = t.stride(1)
+    if pitch < T or (B > 1 and t.stride(0) != C * pitch):
+        return 0
+    return pitch
+
+
 def activation1d_forward_raw(x, alpha, beta, taps_up, taps_down, logscale: bool, out=None):
-    """One call of afa_activation1d_fwd on the current stream. x contiguous [B,C,T] fp32/bf16."""
+    """One call of afa_activation1d_fwd on the current stream.  x: [B,C,T] fp32/bf16; a bf16 tensor whose rows are equally
+    spaced views (x[:, :, :T] of a longer buffer) goes through afa_activation1d_fwd_pitched without a copy when the kernel
+    can take it (include/afa_b200.h), everything else non-contiguous is copied first."""
     _check_inputs(x, alpha, beta)
     if not x.is_contiguous():
+        pitch = _row_pitch(x) if (out is None and x.dtype == torch.bfloat16) else 0
+        if pitch:
+            B, C, T = x.shape
+            y = torch.empty((B, C, T), dtype=x.dtype, device=x.device)
+            flags = (_lib.AFA_FLAG_LOGSCALE if logscale else 0) | (_lib.AFA_FLAG_SNAKE if beta is None else 0)
+            lib = _lib.load_library()
+            with torch.cuda.device_of(x):
+                rc = lib.afa_activation1d_fwd_pitched(
+                    x.data_ptr(), pitch, y.data_ptr(), T, alpha.data_ptr(), None if beta is None else beta.data_ptr(),
+                    taps_up, taps_down, B, C, T, _dtype_code(x), flags, torch.cuda.current_stream(x.device).cuda_stream)
+            if rc == 0:
+                return y
+            if rc != _lib.AFA_ERR_ALIGNMENT:
+                _lib.check(rc, "afa_activation1d_fwd_pitched")
         x = x.contiguous()
     y = torch.empty_like(x) if out is None else out
     B, C, T = x.shape
@@ -102,6 +130,10 @@ class _Activation1dFn(torch.autograd.Function):
     def forward(ctx, x, alpha, beta, taps_up, taps_down, logscale):
         a32 = alpha.detach().float().contiguous()
         b32 = None if beta is None else beta.detach().float().contiguous()
+        if not any(ctx.needs_input_grad[:3]):
+            # inference: nothing is saved for a backward pass, so a strided view (x[:, :, :T] of a longer buffer) can go to the
+            # kernel as it is (afa_activation1d_fwd_pitched) instead of through a dense copy
+            return activation1d_forward_raw(x.detach(), a32, b32, taps_up, taps_down, logscale)
         xc = x.detach().contiguous()
         y = activation1d_forward_raw(xc, a32, b32, taps_up, taps_down, logscale)
         ctx.save_for_backward(xc, a32, b32 if b32 is not None else a32)

@@ -330,6 +330,25 @@ int afa_activation1d_fwd(const void* x, void* y, const float* alpha, const float
     return dtype == AFA_DTYPE_F32 ? launch_fwd<float>(pl, a, st) : launch_fwd<__nv_bfloat16>(pl, a, st);
 }
 
+int afa_activation1d_fwd_pitched(const void* x, int64_t x_row_pitch, void* y, int64_t y_row_pitch, const float* alpha,
+                                 const float* beta, const float* taps_up12, const float* taps_down12, int64_t batch,
+                                 int64_t channels, int64_t T, int dtype, int flags, void* stream) {
+    if (!x || !y || !alpha || !taps_up12 || !taps_down12) return fail(AFA_ERR_BAD_ARG, "null pointer argument");
+    if (!(flags & AFA_FLAG_SNAKE) && !beta) return fail(AFA_ERR_BAD_ARG, "beta is required unless AFA_FLAG_SNAKE is set");
+    if (x == y) return fail(AFA_ERR_BAD_ARG, "y must not alias x");
+    if (batch < 0 || channels < 0 || T < 0) return fail(AFA_ERR_BAD_ARG, "negative size");
+    if (batch == 0 || channels == 0 || T == 0) return 0;
+    if (x_row_pitch == T && y_row_pitch == T)
+        return afa_activation1d_fwd(x, y, alpha, beta, taps_up12, taps_down12, batch, channels, T, dtype, flags, stream);
+    if (dtype != AFA_DTYPE_BF16 && dtype != AFA_DTYPE_F32) return fail(AFA_ERR_BAD_DTYPE, "dtype must be AFA_DTYPE_F32 or AFA_DTYPE_BF16");
+    if (!afa_internal::tc_pitched_ok(x, x_row_pitch, y, y_row_pitch, batch, channels, T, dtype))
+        return fail(AFA_ERR_ALIGNMENT,
+                    "pitched rows are served by the tensor-core kernel only: bf16, T %% 8 == 0, T >= 64, pitches >= T and multiples of 8 "
+                    "elements, 16-byte aligned x and y (and afa_set_tuning(5, ...) not 0); copy to a dense tensor otherwise");
+    return afa_internal::tc_fwd_launch(x, y, alpha, beta, taps_up12, taps_down12, batch, channels, T, flags, (cudaStream_t)stream,
+                                       0, nullptr, x_row_pitch, y_row_pitch);
+}
+
 size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int dtype) {
     // An upper bound over every kernel variant the call may select: the query sees no pointers, and a misaligned base
     // pointer or a forced segment size moves the launch to a variant with shorter segments (more partial sums).  The

@@ -17,6 +17,8 @@ bool tc_eligible(const void* x, const void* y, int64_t batch, int64_t channels, 
 void tc_plan(int64_t rows, int64_t T, int* rlog2_out, int* ny_out, int64_t* n_rgroups, int64_t* n_tstrips);
 int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta, const float* taps_up12,
                   const float* taps_down12, int64_t batch, int64_t channels, int64_t T, int flags, cudaStream_t st,
-                  int debug, float* dbg);
+                  int debug, float* dbg, int64_t x_pitch = 0, int64_t y_pitch = 0);      // pitches in elements; 0 = dense (T)
+bool tc_pitched_ok(const void* x, int64_t x_pitch, const void* y, int64_t y_pitch, int64_t batch, int64_t channels, int64_t T,
+                   int dtype);
 int tc_kernel_info(int32_t out[6]);
 }  // namespace afa_internal

@@ -40,7 +40,7 @@ int g_tc_dbg_j0 = 0;      // harness: first block of the clock-stamp window
 // buffers call after call -- pays the driver's encode (~1 us each, two per launch) once.
 struct MapKey {
     const void* base;
-    int64_t rows, T;
+    int64_t rows, T, pitch;
     int R;
 };
 struct MapSlot {
@@ -48,18 +48,18 @@ struct MapSlot {
     CUtensorMap tm;
     bool used;
 };
-int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) {
+int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int64_t pitch, int R) {
     static thread_local MapSlot cache[16];
     static thread_local unsigned next = 0;
     for (MapSlot& c : cache)
-        if (c.used && c.k.base == base && c.k.rows == rows && c.k.T == T && c.k.R == R) {
+        if (c.used && c.k.base == base && c.k.rows == rows && c.k.T == T && c.k.pitch == pitch && c.k.R == R) {
             *tm = c.tm;
             return 0;
         }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)T * 2};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)R};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -67,7 +67,7 @@ int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t T, int R) 
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     MapSlot& c = cache[next++ % 16];
-    c.k = MapKey{base, rows, T, R};
+    c.k = MapKey{base, rows, T, pitch, R};
     c.tm = *tm;
     c.used = true;
     return 0;
@@ -190,9 +190,22 @@ void tc_plan(int64_t rows_in, int64_t T, int* rlog2_out, int* ny_out, int64_t* n
     *n_tstrips = strips(ny);
 }
 
+// Rows `x_pitch` / `y_pitch` elements apart (0 = dense): the tensor maps carry the pitch, nothing else changes.
+bool tc_pitched_ok(const void* x, int64_t x_pitch, const void* y, int64_t y_pitch, int64_t batch, int64_t channels, int64_t T,
+                   int dtype) {
+    if (!g_tc_enable || dtype != AFA_DTYPE_BF16 || encode_fn() == nullptr) return false;
+    if (T < 64 || (T % 8) != 0 || T >= (1ll << 28)) return false;
+    if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return false;
+    if (x_pitch < T || y_pitch < T || (x_pitch % 8) != 0 || (y_pitch % 8) != 0 || x_pitch >= (1ll << 38) || y_pitch >= (1ll << 38)) return false;
+    const int64_t rows = batch * channels;
+    return rows >= 1 && rows < (1ll << 30);
+}
+
 int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta, const float* taps_up12,
                   const float* taps_down12, int64_t batch, int64_t channels, int64_t T, int flags, cudaStream_t st,
-                  int debug, float* dbg) {
+                  int debug, float* dbg, int64_t x_pitch, int64_t y_pitch) {
+    if (x_pitch <= 0) x_pitch = T;
+    if (y_pitch <= 0) y_pitch = T;
     const int64_t rows = batch * channels;
     int rlog2, ny;
     int64_t rg, ts;
@@ -200,12 +213,14 @@ int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta,
     if (rg * ts >= (1ll << 31)) return set_error(AFA_ERR_TOO_LARGE, "grid of %lld CTAs", (long long)(rg * ts));
     CUtensorMap tmx, tmy;
     const int64_t halves = (T % 8) != 0 ? 2 : 1;
-    if (int rc = make_map(&tmx, x, rows / halves, T * halves, 1 << rlog2)) return rc;
-    if (int rc = make_map(&tmy, y, rows / halves, T * halves, 1 << rlog2)) return rc;
+    if (int rc = make_map(&tmx, x, rows / halves, T * halves, x_pitch * halves, 1 << rlog2)) return rc;
+    if (int rc = make_map(&tmy, y, rows / halves, T * halves, y_pitch * halves, 1 << rlog2)) return rc;
     afa_tc::Args a;
     memset(&a, 0, sizeof(a));
     a.x = static_cast<const __nv_bfloat16*>(x);
     a.y = static_cast<__nv_bfloat16*>(y);
+    a.x_pitch = x_pitch;
+    a.y_pitch = y_pitch;
     a.halves = (int32_t)halves;
     a.spr = (int32_t)(((T + 4 * (halves - 1) + 15) / 16 + ny - 1) / ny);      // the second row of a pair is covered 4 samples early
     a.alpha = alpha;

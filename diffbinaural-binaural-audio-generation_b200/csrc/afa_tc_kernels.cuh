@@ -89,6 +89,7 @@ struct Args {
     int32_t R_log2;        // lanes = R rows x G groups, R = 1 << R_log2
     int32_t NY;            // outputs per lane and CTA in units of 16: a multiple of 4, any length (the chunk ring is recycled)
     int32_t n_tstrips;     // CTAs along time; blockIdx.x = row_group * n_tstrips + tstrip
+    int64_t x_pitch, y_pitch;   // elements between consecutive rows of x / y (T for dense tensors)
     int32_t halves;        // 1: tensor-map rows = tensor rows.  2 (T % 8 == 4, even row count): tensor-map rows = PAIRS of rows, 2T wide
     int32_t spr;           // lane strips (16 * NY outputs) per tensor row
     int32_t debug;         // harness only: 1 = dump U blocks, 2 = dump S, 3 = clock stamps of CTA dbg_cta
@@ -514,7 +515,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const bool need = row < a.rows && ((left_lane && c == 0) || (right_lane && ((cb >> 3) == c || ((cb + 1) >> 3) == c)));
             if (__any_sync(0xffffffffu, need)) {
                 if (need) {
-                    const unsigned short* xr16 = reinterpret_cast<const unsigned short*>(a.x) + (size_t)row * (size_t)T;
+                    const unsigned short* xr16 = reinterpret_cast<const unsigned short*>(a.x) + (size_t)row * (size_t)a.x_pitch;
                     mbar_wait(bars + 8 * (kBarFull + c % kSlots), (uint32_t)(c / kSlots) & 1u);
                     const uint32_t cbase = srow + (uint32_t)(c % kSlots) * kChunkBytes;
                     if (left_lane && c == 0) {
@@ -674,7 +675,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     const int o0 = t_org + 8 + 64 * (i >> 1);
                     if (row < a.rows && ((hh == 0 && o0 < T && o0 + 64 > T) || o0 < 0)) {
                         const int tb0 = t_org + 8 + 32 * i;
-                        __nv_bfloat16* yr = a.y + (size_t)row * (size_t)T;
+                        __nv_bfloat16* yr = a.y + (size_t)row * (size_t)a.y_pitch;
 #pragma unroll
                         for (int v = 0; v < 8; ++v)
                             if (tb0 + 4 * v >= 0 && tb0 + 4 * v < T) *reinterpret_cast<uint2*>(yr + tb0 + 4 * v) = make_uint2(pk[2 * v], pk[2 * v + 1]);

@@ -66,6 +66,19 @@ int afa_activation1d_fwd(const void *x, void *y,
                          int64_t batch, int64_t channels, int64_t T,
                          int dtype, int flags, void *stream);
 
+/*
+ * The same forward for tensors whose ROWS are `row_pitch` elements apart (x_row_pitch, y_row_pitch >= T), e.g. a time slice
+ * x[:, :, :T] of a longer buffer: what the reference's torch ops accept through strides (act.py:25-30 never asks for a dense
+ * tensor).  Served by the tensor-core kernel, whose tensor maps carry the pitch: bf16, T % 8 == 0, T >= 64, both pitches
+ * multiples of 8 elements, x and y 16-byte aligned; anything else returns AFA_ERR_ALIGNMENT (the caller copies to a dense
+ * tensor and calls afa_activation1d_fwd).  Pitches equal to T forward to afa_activation1d_fwd.
+ */
+int afa_activation1d_fwd_pitched(const void *x, int64_t x_row_pitch, void *y, int64_t y_row_pitch,
+                                 const float *alpha, const float *beta,
+                                 const float *taps_up12, const float *taps_down12,
+                                 int64_t batch, int64_t channels, int64_t T,
+                                 int dtype, int flags, void *stream);
+
 /* Scratch the backward needs (per-segment parameter-gradient partials), in bytes. */
 size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int dtype);
 

@@ -637,3 +637,56 @@ def test_bf16_backward_unaligned_and_half_aligned_workspace():
         assert O.max_normalised_error(gx.float().cpu().numpy(), gx_ref) <= TOL_BF16, shift
         assert O.max_normalised_error(ga.cpu().numpy(), ga_ref) <= 1e-3, shift
         assert O.max_normalised_error(gb.cpu().numpy(), gb_ref) <= 1e-3, shift
+
+
+def test_pitched_rows_without_a_copy():
+    """afa_activation1d_fwd_pitched: a time slice x[:, :, :T] of a longer buffer (rows `pitch` elements apart) gives bit for bit
+    what the dense copy gives on the same (tensor-core) kernel; the module takes the view as it is in inference; layouts the
+    kernel cannot take report AFA_ERR_ALIGNMENT through the C ABI and fall back to a copy in the Python shim; the buffer
+    outside the slice is not touched and nothing is written outside y."""
+    afa_b200, _lib, Fn, _, SnakeBeta = _mods()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    taps = Fn.host_taps(TP.make_taps())
+    lib = _lib.load_library()
+    for (B, C, T, pitch) in ((2, 24, 4096, 4104), (3, 7, 1024, 2048), (1, 130, 512, 520), (2, 5, 264, 272)):
+        buf = torch.randn(B, C, pitch, device=dev).to(torch.bfloat16)
+        keep = buf.clone()
+        x = buf[:, :, :T]
+        assert not x.is_contiguous() and Fn._row_pitch(x) == pitch
+        a = torch.randn(C, device=dev) * 0.5
+        b = torch.randn(C, device=dev) * 0.5
+        n0 = _lib.launch_count()
+        y = Fn.activation1d_forward_raw(x, a, b, taps, taps, True)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == n0 + 1 and y.is_contiguous() and y.shape == (B, C, T)
+        _lib.set_tuning(5, 2, 0)
+        try:
+            y_dense = Fn.activation1d_forward_raw(x.contiguous(), a, b, taps, taps, True)
+        finally:
+            _lib.set_tuning(5, 1, 0)
+        assert torch.equal(y, y_dense), (B, C, T, pitch)
+        assert torch.equal(buf, keep)
+        # pitched OUTPUT as well, straight through the C ABI, inside a sentinel-filled buffer
+        ybuf = torch.full((B, C, pitch), 777.0, device=dev, dtype=torch.bfloat16)
+        rc = lib.afa_activation1d_fwd_pitched(x.data_ptr(), pitch, ybuf.data_ptr(), pitch, a.data_ptr(), b.data_ptr(), taps, taps,
+                                              B, C, T, 1, 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert rc == 0, lib.afa_last_error()
+        assert torch.equal(ybuf[:, :, :T], y) and torch.all(ybuf[:, :, T:] == 777.0)
+    # layouts outside the contract: an error code from the C ABI, a dense copy in the shim
+    x32 = torch.randn(2, 8, 520, device=dev)[:, :, :512]
+    a = torch.zeros(8, device=dev)
+    rc = lib.afa_activation1d_fwd_pitched(x32.data_ptr(), 520, torch.empty(2, 8, 512, device=dev).data_ptr(), 512, a.data_ptr(), a.data_ptr(),
+                                          taps, taps, 2, 8, 512, 0, 1, torch.cuda.current_stream().cuda_stream)
+    assert rc == _lib.AFA_ERR_ALIGNMENT and b"tensor-core" in lib.afa_last_error()
+    odd = torch.randn(2, 8, 523, device=dev).to(torch.bfloat16)[:, :, :512]           # pitch not a multiple of 8
+    y = Fn.activation1d_forward_raw(odd, a, a, taps, taps, True)
+    assert torch.equal(y, Fn.activation1d_forward_raw(odd.contiguous(), a, a, taps, taps, True))
+    # module, inference: the view goes in as it is; training still saves a dense x
+    m = afa_b200.Activation1d(activation=SnakeBeta(24, alpha_logscale=True)).to(dev).to(torch.bfloat16)
+    buf = torch.randn(2, 24, 2056, device=dev).to(torch.bfloat16)
+    with torch.no_grad():
+        y1 = m(buf[:, :, :2048])
+        y2 = m(buf[:, :, :2048].contiguous())
+    assert (y1.float() - y2.float()).abs().max().item() <= 2 * 2.0 ** -8 * max(1.0, y2.float().abs().max().item())
