@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 140            /* 0.1.4: + tensor-core (tcgen05) forward for bf16 activations */
+#define AFA_VERSION 150            /* 0.1.5: + afa_activation1d_fwd_pitched; 0.1.4: tensor-core (tcgen05) forward for bf16 activations */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
