@@ -23,6 +23,7 @@ _UNITS = {
     "afa_capi.cu": ["afa_kernels.cuh", "afa_cl_kernels.cuh", "afa_actconv_kernels.cuh"],
     "afa_mel.cu": [],
     "afa_tc.cu": ["afa_tc_kernels.cuh"],
+    "afa_tc_cl.cu": ["afa_tc_kernels.cuh", "afa_tc_cl_kernels.cuh"],
     "afa_ingest.cu": [],
 }
 

@@ -110,10 +110,13 @@ int grid_for(const void* kernel, size_t smem, uint32_t n_wtiles, uint32_t* grid)
 // edge-mode warp, so short rows want short segments; small launches want many small tiles.
 int default_chunks(int which, int dtype, int64_t elements, int64_t T) {
     const int vec = dtype == AFA_DTYPE_F32 ? 4 : 8;
-    if (which == 1) {   // backward: two staged tensors -> fewer resident warps; long segments only pay on long rows
+    if (which == 1) {   // backward: two staged tensors -> fewer resident warps; long segments only pay on long fp32 rows of big launches
+        // (same-box sweeps, profiles/r02_bwd_sweep_segment_length.log: bf16 is fastest at 5 chunks on every shape; fp32 one-clip
+        //  launches 36-38 us at 5 chunks against 43-44 at 13; fp32 (16, 384, 13776) 223 us at 5 against 238 at 9)
+        if (dtype != AFA_DTYPE_F32 || elements < (16ll << 20)) return 5;
         const int64_t wtiles13 = elements / (32 * 13 * vec);
         if (wtiles13 >= 2 * 148 * 8 && T >= 32768) return 13;
-        return (dtype == AFA_DTYPE_F32 && T >= 8192 && elements >= (16ll << 20)) ? 9 : 5;
+        return T >= 16384 ? 9 : 5;
     }
     if (elements < (16ll << 20)) return 9;
     if (dtype == AFA_DTYPE_F32) return T < 8192 ? 13 : 17;
@@ -279,6 +282,12 @@ int afa_set_tuning(int which, int chunks, int threads) {
         afa_internal::tc_set_tuning(g_tc_mode, g_tc_ny, g_tc_rlog2);
         return 0;
     }
+    if (which == 7) {   // channels-last tensor-core Activation1d (bf16, no residual prologue): chunks = 0 off / 1 heuristic / 2 whenever eligible
+        if (chunks < 0 || chunks > 2 || threads < 0 || threads > 4096 || threads % 4)
+            return fail(AFA_ERR_BAD_ARG, "channels-last tensor-core path: mode 0..2, blocks per CTA 0 or a multiple of 4 up to 4096");
+        afa_internal::tc_cl_set_tuning(chunks, threads);
+        return 0;
+    }
     if (which == 4) {   // fused activation+convolution, tcgen05 path: 1 = input rows staged by a bulk copy (default), 0 = global loads
         if (chunks != 0 && chunks != 1) return fail(AFA_ERR_BAD_ARG, "input staging must be 0 or 1");
         g_actconv_xs = chunks;
@@ -294,7 +303,7 @@ int afa_set_tuning(int which, int chunks, int threads) {
         g_tune_chunks[2] = chunks;
         return 0;
     }
-    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd)");
+    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd), 7 (channels-last tensor-core fwd)");
     bool ok = chunks == 0;
 #define X(CH) ok = ok || chunks == CH;
     AFA_CHUNK_LIST(X)
@@ -349,6 +358,11 @@ int afa_activation1d_fwd_pitched(const void* x, int64_t x_row_pitch, void* y, in
                                        0, nullptr, x_row_pitch, y_row_pitch);
 }
 
+// slice sums [C][kFinalizeMaxSplit][2] + per-channel counters of the split second reduction stage
+static size_t finalize_extra_bytes(int64_t channels) {
+    return (size_t)channels * (afa::kFinalizeMaxSplit * 2 * sizeof(float) + sizeof(uint32_t));
+}
+
 size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int dtype) {
     // An upper bound over every kernel variant the call may select: the query sees no pointers, and a misaligned base
     // pointer or a forced segment size moves the launch to a variant with shorter segments (more partial sums).  The
@@ -357,7 +371,8 @@ size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int d
     if (make_plan(1, nullptr, nullptr, nullptr, batch, channels, T, dtype, &pl)) return 0;
     const int64_t lmin = 5 * pl.vec;
     const int64_t nseg = T > 0 ? (T + lmin - 1) / lmin : 0;
-    return (size_t)(batch * channels * nseg) * 2 * sizeof(float) + 16;
+    if (batch * channels * nseg == 0) return 16;
+    return (size_t)(batch * channels * nseg) * 2 * sizeof(float) + finalize_extra_bytes(channels) + 16;
 }
 
 int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha, float* gbeta, const float* alpha,
@@ -376,7 +391,13 @@ int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha,
         if (e == cudaSuccess && !snake) e = cudaMemsetAsync(gbeta, 0, sizeof(float) * channels, st);
         return e == cudaSuccess ? 0 : cuda_fail(e, "cudaMemsetAsync");
     }
-    const size_t need = (size_t)pl.total_segs * 2 * sizeof(float);
+    // second reduction stage (afa_param_grad_finalize): `split` CTAs per channel, enough to fill the machine twice over
+    const int64_t per_channel = batch * (int64_t)pl.nseg;
+    int split = (int)((4 * 148 + channels - 1) / channels);
+    if (split > afa::kFinalizeMaxSplit) split = afa::kFinalizeMaxSplit;
+    while (split > 1 && per_channel / split < 16 * afa::kFinalizeThreads) --split;   // a slice must be worth its arrival round trip
+    const size_t part_bytes = (size_t)pl.total_segs * 2 * sizeof(float);
+    const size_t need = part_bytes + (split > 1 ? finalize_extra_bytes(channels) : 0);
     if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 3))
         return fail(AFA_ERR_WORKSPACE, "workspace of %zu bytes needed (got %zu)", need, workspace_bytes);
     afa::BwdArgs a;
@@ -386,12 +407,15 @@ int afa_activation1d_bwd(const void* x, const void* gy, void* gx, float* galpha,
     a.alpha = alpha;
     a.beta = beta;
     a.part = (float*)workspace;
+    float* part2 = split > 1 ? (float*)((char*)workspace + part_bytes) : nullptr;
+    a.cnt = split > 1 ? (uint32_t*)(part2 + (size_t)channels * afa::kFinalizeMaxSplit * 2) : nullptr;
+    a.n_cnt = (int32_t)channels;
     fold_bwd_taps(taps_up12, taps_down12, &a.taps);
     a.g = make_geometry(pl, batch, channels, T, flags);
     int rc = dtype == AFA_DTYPE_F32 ? launch_bwd<float>(pl, a, st) : launch_bwd<__nv_bfloat16>(pl, a, st);
     if (rc) return rc;
-    afa::afa_param_grad_finalize<<<(unsigned)channels, afa::kFinalizeThreads, 0, st>>>(
-        a.part, galpha, gbeta, pl.total_segs, pl.nseg, (int)batch, (int)channels, snake ? 1 : 0);
+    afa::afa_param_grad_finalize<<<dim3((unsigned)channels, (unsigned)split), afa::kFinalizeThreads, 0, st>>>(
+        a.part, galpha, gbeta, pl.total_segs, pl.nseg, (int)batch, (int)channels, snake ? 1 : 0, part2, a.cnt);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "afa_param_grad_finalize launch");
@@ -403,6 +427,7 @@ int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]) {
 
 int afa_kernel_info_shape(int which, int dtype, int64_t batch, int64_t channels, int64_t T, int32_t out[6]) {
     if (out && which == 5) return afa_internal::tc_kernel_info(out);   // the tensor-core forward (one variant)
+    if (out && which == 7) return afa_internal::tc_cl_kernel_info(out);   // its channels-last variant
     if (!out || which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "bad argument");
     Plan pl;
     if (int rc = make_plan(which, nullptr, nullptr, nullptr, batch, channels, T, dtype, &pl)) return rc;
@@ -495,6 +520,10 @@ int afa_amp_activation1d_fwd_cl(const void* x, int64_t x_bstride, const void* re
     const size_t esz = dtype == AFA_DTYPE_F32 ? 4 : 2;
     if (((uintptr_t)x | (uintptr_t)res | (uintptr_t)xsum | (uintptr_t)y) & (esz - 1)) return fail(AFA_ERR_ALIGNMENT, "tensor pointers must be aligned to the element size");
     if (batch == 0 || T == 0) return 0;
+    // bf16 without a residual prologue: both FIR filters on the tensor cores (afa_tc_cl_kernels.cuh)
+    if (afa_internal::tc_cl_eligible(x, x_bstride, res, y, y_bstride, y_tpad, batch, channels, T, dtype))
+        return afa_internal::tc_cl_fwd_launch(x, x_bstride, bias, y, y_bstride, y_tpad, alpha, beta, taps_up12, taps_down12, batch,
+                                              channels, T, flags, (cudaStream_t)stream);
     const int L = cl_segment(batch, channels, T, res != nullptr);
     const int64_t nseg = (T + L - 1) / L;
     const int64_t total = batch * nseg * channels;

@@ -21,4 +21,17 @@ int tc_fwd_launch(const void* x, void* y, const float* alpha, const float* beta,
 bool tc_pitched_ok(const void* x, int64_t x_pitch, const void* y, int64_t y_pitch, int64_t batch, int64_t channels, int64_t T,
                    int dtype);
 int tc_kernel_info(int32_t out[6]);
+void* tc_encode_tiled();                 // cuTensorMapEncodeTiled from the driver (nullptr: not available)
+void tc_split_bf16(float v, uint16_t* hi, uint16_t* lo);
+int tc_mats();
+int tc_mode();                           // afa_set_tuning(5, mode, ...): 0 off / 1 heuristic / 2 whenever eligible
+
+// afa_tc_cl.cu: the same kernel for channels-last [batch, T, channels] bf16 activations (the generator engine's layout)
+void tc_cl_set_tuning(int enable, int ny);      // enable: 0 off / 1 heuristic / 2 whenever eligible; ny: forced blocks of 16 per CTA
+bool tc_cl_eligible(const void* x, int64_t x_bs, const void* res, const void* y, int64_t y_bs, int64_t y_tpad, int64_t batch,
+                    int64_t channels, int64_t T, int dtype);
+int tc_cl_fwd_launch(const void* x, int64_t x_bs, const float* bias, void* y, int64_t y_bs, int64_t y_tpad, const float* alpha,
+                     const float* beta, const float* taps_up12, const float* taps_down12, int64_t batch, int64_t channels,
+                     int64_t T, int flags, cudaStream_t st);
+int tc_cl_kernel_info(int32_t out[6]);
 }  // namespace afa_internal

@@ -110,6 +110,8 @@ struct BwdArgs {
     const float* alpha;
     const float* beta;
     float* part;  // [2][total_segs] per-segment parameter-gradient partials
+    uint32_t* cnt;  // per-channel arrival counters of the split second stage (afa_param_grad_finalize), or nullptr: zeroed by CTA 0
+    int32_t n_cnt;
     BwdTaps taps;
     Geometry g;
 };
@@ -935,6 +937,9 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
 
     const uint32_t GW = gridDim.x * NW;
     uint32_t wt = blockIdx.x * NW + warp;
+    // the workspace is not zeroed by the caller: the counters of the finalize kernel (next launch on this stream) start at 0
+    if (blockIdx.x == 0 && args.cnt != nullptr)
+        for (int i = threadIdx.x; i < args.n_cnt; i += NW * 32) args.cnt[i] = 0u;
     if (wt >= g.n_wtiles) return;
 
     if (ALIGNED) {
@@ -1037,47 +1042,92 @@ __global__ void __launch_bounds__(NW * 32, ALIGNED ? AFA_BWD_MINB : 1) afa_bwd_k
     if (ALIGNED && lane == 0) tma_store_wait_read();
 }
 
-// Second stage of the deterministic parameter-gradient reduction: one CTA per channel sums the
-// per-segment partials of every (batch, segment) of that channel in a fixed order (thread-strided
-// serial sums, then a fixed shuffle/shared-memory tree), so results are run-to-run identical.
+// Second stage of the deterministic parameter-gradient reduction.  Channel c owns batch * nseg per-segment partials
+// (runs of nseg consecutive values, one run per batch entry).  grid = (C, split): CTA (c, k) sums the k-th contiguous
+// slice of the channel's flattened (batch, segment) range -- four independent thread-strided serial sums per thread (four
+// loads in flight), combined in a fixed order, then a fixed shuffle / shared-memory tree -- and, with split > 1, leaves its two
+// sums in part2; the CTA that arrives LAST on the channel's counter adds the `split` slice sums in slice order.  Every sum
+// has a fixed order whatever the timing, so results are run-to-run identical.  (One CTA per channel -- the first version --
+// left 24 CTAs walking 68 k partials each at C = 24: 40 us behind a 210 us backward kernel.)
 constexpr int kFinalizeThreads = 256;
+constexpr int kFinalizeMaxSplit = 32;
 __global__ void __launch_bounds__(kFinalizeThreads)
 afa_param_grad_finalize(const float* __restrict__ part, float* __restrict__ galpha, float* __restrict__ gbeta,
-                        uint32_t total_segs, uint32_t nseg, int batch, int C, int snake) {
+                        uint32_t total_segs, uint32_t nseg, int batch, int C, int snake, float* part2, uint32_t* cnt) {
     const int c = blockIdx.x;
+    const int split = gridDim.y, k = blockIdx.y;
     const int tid = threadIdx.x;
     const uint32_t per_channel = (uint32_t)batch * nseg;
-    float sa = 0.f, sb = 0.f;
-    for (uint32_t i = tid; i < per_channel; i += kFinalizeThreads) {
+    const uint32_t slice = (per_channel + split - 1) / split;
+    const uint32_t lo = min(per_channel, (uint32_t)k * slice), hi = min(per_channel, lo + slice);
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+    auto at = [&](uint32_t i) {
         const uint32_t b = i / nseg, s = i - b * nseg;
-        const size_t idx = ((size_t)b * C + c) * nseg + s;
-        sa += part[idx];
-        sb += part[(size_t)total_segs + idx];
+        return ((size_t)b * C + c) * nseg + s;
+    };
+    uint32_t i = lo + tid;
+    for (; i + 3 * kFinalizeThreads < hi; i += 4 * kFinalizeThreads) {
+        float va[4], vb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t idx = at(i + j * kFinalizeThreads);
+            va[j] = __ldcs(part + idx);
+            vb[j] = __ldcs(part + (size_t)total_segs + idx);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sa[j] += va[j];
+            sb[j] += vb[j];
+        }
     }
 #pragma unroll
+    for (int j = 0; j < 3; ++j) {                              // at most three left: they continue the sums j = 0, 1, 2
+        if (i + j * kFinalizeThreads < hi) {
+            const size_t idx = at(i + j * kFinalizeThreads);
+            sa[j] += __ldcs(part + idx);
+            sb[j] += __ldcs(part + (size_t)total_segs + idx);
+        }
+    }
+    float ta = (sa[0] + sa[1]) + (sa[2] + sa[3]), tb = (sb[0] + sb[1]) + (sb[2] + sb[3]);
+#pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        sa += __shfl_xor_sync(0xffffffffu, sa, off);
-        sb += __shfl_xor_sync(0xffffffffu, sb, off);
+        ta += __shfl_xor_sync(0xffffffffu, ta, off);
+        tb += __shfl_xor_sync(0xffffffffu, tb, off);
     }
     __shared__ float red[2][kFinalizeThreads / 32];
     if ((tid & 31) == 0) {
-        red[0][tid >> 5] = sa;
-        red[1][tid >> 5] = sb;
+        red[0][tid >> 5] = ta;
+        red[1][tid >> 5] = tb;
     }
     __syncthreads();
-    if (tid == 0) {
-        float ta = 0.f, tb = 0.f;
+    if (tid != 0) return;
+    ta = 0.f;
+    tb = 0.f;
 #pragma unroll
-        for (int w = 0; w < kFinalizeThreads / 32; ++w) {
-            ta += red[0][w];
-            tb += red[1][w];
+    for (int w = 0; w < kFinalizeThreads / 32; ++w) {
+        ta += red[0][w];
+        tb += red[1][w];
+    }
+    if (split > 1) {
+        float* mine = part2 + ((size_t)c * split + k) * 2;
+        __stcg(mine, ta);
+        __stcg(mine + 1, tb);
+        __threadfence();
+        if (atomicAdd(cnt + c, 1u) != (uint32_t)split - 1u) return;
+        __threadfence();
+        ta = 0.f;
+        tb = 0.f;
+        for (int q = 0; q < split; ++q) {
+            ta += __ldcg(part2 + ((size_t)c * split + q) * 2);
+            tb += __ldcg(part2 + ((size_t)c * split + q) * 2 + 1);
         }
-        if (snake) {
-            galpha[c] = ta + tb;  // beta aliases alpha                              activations.py:57-60
-        } else {
-            galpha[c] = ta;
-            gbeta[c] = tb;
-        }
+        cnt[c] = 0u;
+    }
+    if (snake) {
+        galpha[c] = ta + tb;  // beta aliases alpha                              activations.py:57-60
+    } else {
+        galpha[c] = ta;
+        gbeta[c] = tb;
     }
 }
 

@@ -115,6 +115,11 @@ cudaError_t launch_kernel(unsigned grid, cudaStream_t st, const CUtensorMap& tmx
 
 namespace afa_internal {
 
+void* tc_encode_tiled() { return (void*)encode_fn(); }
+void tc_split_bf16(float v, uint16_t* hi, uint16_t* lo) { split_bf16(v, hi, lo); }
+int tc_mats() { return g_tc_mats; }
+int tc_mode() { return g_tc_enable; }
+
 void tc_set_mats(int mats) { g_tc_mats = (mats == 11 || mats == 12 || mats == 21) ? mats : 22; }
 void tc_set_debug_window(int j0) { g_tc_dbg_j0 = j0; }
 

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 150            /* 0.1.5: + afa_activation1d_fwd_pitched; 0.1.4: tensor-core (tcgen05) forward for bf16 activations */
+#define AFA_VERSION 151            /* 0.1.5: + afa_activation1d_fwd_pitched, split parameter-gradient finalize; 0.1.4: tensor-core (tcgen05) forward for bf16 activations */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
@@ -79,14 +79,16 @@ int afa_activation1d_fwd_pitched(const void *x, int64_t x_row_pitch, void *y, in
                                  int64_t batch, int64_t channels, int64_t T,
                                  int dtype, int flags, void *stream);
 
-/* Scratch the backward needs (per-segment parameter-gradient partials), in bytes. */
+/* Scratch the backward needs (per-segment parameter-gradient partials, slice sums, counters), in bytes. */
 size_t afa_bwd_workspace_bytes(int64_t batch, int64_t channels, int64_t T, int dtype);
 
 /*
  * gx = d<y,gy>/dx ; galpha / gbeta = gradients w.r.t. the RAW parameters (float32 [channels],
  * log-scale chain rule and Snake aliasing applied; gbeta may be NULL with AFA_FLAG_SNAKE).
  * The intermediate 2x-rate signal is recomputed from x; only x is needed from the forward.
- * Reductions are two-stage and deterministic (no atomics).
+ * Reductions are staged and deterministic: fixed-order sums per segment, per slice of a channel's
+ * segments, per channel (an arrival counter only elects the CTA that adds the slice sums, in slice
+ * order; no floating-point atomics).  The workspace need not be initialised.
  */
 int afa_activation1d_bwd(const void *x, const void *gy, void *gx,
                          float *galpha, float *gbeta,
@@ -275,8 +277,13 @@ int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map,
  *          tcgen05 products, csrc/afa_tc_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible;
  *          threads = blocks of 16 outputs per TMEM lane and CTA (a multiple of 4 up to 4096; 0 = built-in choice).
  * which=6: its rows per CTA as log2 (3..7; -1 = built-in choice).
+ * which=7: the channels-last tensor-core forward (afa_amp_activation1d_fwd_cl on bf16 tensors without res / xsum,
+ *          channels % 8 == 0, T % 4 == 0, 16-byte aligned x, y and batch strides, at most 8 zero rows behind T;
+ *          csrc/afa_tc_cl_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible; threads = blocks of
+ *          16 outputs per CTA (a multiple of 4 up to 4096; 0 = built-in choice).  which=5 with chunks = 0 turns it off as well.
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
- * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects (which = 5: the tensor-core forward).
+ * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects (which = 5: the tensor-core forward,
+ * 7: its channels-last variant).
  */
 int afa_set_tuning(int which, int chunks, int threads);
 int afa_kernel_info(int which, int dtype, int64_t T, int32_t out[6]);

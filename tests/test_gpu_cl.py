@@ -122,6 +122,71 @@ def test_cl_activation_grid(dtype):
                 assert O.max_normalised_error(xsum.double().cpu().numpy(), xs_ref) <= (1e-6 if dtype == torch.float32 else 4e-3), tag
 
 
+def test_cl_tensor_core_activation_grid():
+    """The channels-last tensor-core forward (afa_tc_cl_fwd_kernel; bf16, no residual prologue), forced onto small tensors
+    the built-in choice leaves to the walk kernel: T around the 32-output block / 64-step chunk / strip boundaries with both
+    residues of T % 8, channel counts around the 64-channel boxes and the 128-lane groups, Snake / SnakeBeta, log-scale on /
+    off, bias on / off, padded batch strides, zero rows behind T, guard rows behind those; forced strip lengths.  Against the
+    float64 oracle on the bf16 inputs, and against the walk kernel (both round y to bf16 once: they differ by the rounding
+    of s to bf16 in front of the down filter)."""
+    from afa_b200 import _lib
+
+    _, FC = _fc()
+    t32, taps, taps64 = _taps()
+    rng = np.random.default_rng(11)
+    Ts = [64, 68, 72, 100, 124, 128, 132, 252, 256, 260, 316, 508, 512, 516, 1000, 1028, 2052, 4100]
+    Cs = [8, 24, 64, 72, 96, 128, 136, 192, 200, 264]
+    n = 0
+    try:
+        for T in Ts:
+            for C in Cs:
+                if (n % 3) == 2 and T > 600:
+                    n += 1
+                    continue
+                B = 1 + (n % 3)
+                kind = ("snakebeta", "snake")[n % 2]
+                logscale = (n % 4) < 3
+                with_bias = (n % 3) != 0
+                ny = (0, 4, 8, 12)[n % 4]
+                n += 1
+                x = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.bfloat16, device=DEV)
+                bias = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV) if with_bias else None
+                if logscale:
+                    alpha = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+                    beta = torch.tensor(rng.standard_normal(C) * 0.5, dtype=torch.float32, device=DEV)
+                else:
+                    alpha = torch.tensor(rng.random(C) * 2 + 0.25, dtype=torch.float32, device=DEV)
+                    beta = torch.tensor(rng.random(C) * 2 + 0.25, dtype=torch.float32, device=DEV)
+                if kind == "snake":
+                    beta = None
+                tpad = T + (n % 4) * 2
+                xin = _padded(x, T + 8) if n % 2 else x
+                tag = f"T={T} C={C} B={B} {kind} log={logscale} bias={with_bias} ny={ny} tpad={tpad}"
+                out = torch.full((B, tpad + 4, C), 7.0, dtype=torch.bfloat16, device=DEV)
+                _lib.set_tuning(7, 2, ny)
+                before = _lib.launch_count()
+                y = FC.amp_activation1d_cl(xin, T, alpha, beta, taps[0], taps[1], logscale, bias=bias, out=out, out_tpad=tpad)
+                torch.cuda.synchronize()
+                assert _lib.launch_count() == before + 1, tag
+                _lib.set_tuning(7, 0, 0)
+                yw = FC.amp_activation1d_cl(xin, T, alpha, beta, taps[0], taps[1], logscale, bias=bias, out_tpad=tpad)
+                torch.cuda.synchronize()
+                _, y_ref = A.amp_activation1d_cl(
+                    x.double().cpu().numpy(), alpha.double().cpu().numpy(), None if beta is None else beta.double().cpu().numpy(),
+                    logscale, None if bias is None else bias.double().cpu().numpy(), None, taps64, taps64)
+                got = y[:, :T].double().cpu().numpy()
+                assert O.max_normalised_error(got, y_ref) <= TOL_BF16, (tag, O.max_normalised_error(got, y_ref))
+                assert O.max_normalised_error(got, yw[:, :T].double().cpu().numpy()) <= TOL_BF16, tag
+                if tpad > T:
+                    assert torch.all(out[:, T:tpad] == 0), tag
+                assert torch.all(out[:, tpad:] == 7.0), tag
+    finally:
+        _lib.set_tuning(7, 1, 0)
+    # the built-in choice takes it on the engine's wide stages and leaves residual calls, fp32 and narrow tensors alone
+    info = _lib.kernel_info(7, 1, 8192)
+    assert info["threads"] == 320 and info["registers"] <= 102, info
+
+
 def test_cl_activation_matches_reference_golden(golden_cases):
     """The reference's own Activation1d outputs (tests/golden/activation1d_golden.npz), fed channels-last."""
     _, FC = _fc()

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(EXPORTED_SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.afa_version() == 150
+    assert lib.afa_version() == 151
 
 
 def test_argument_errors_need_no_gpu(lib):

@@ -7,7 +7,7 @@ from afa_b200 import Activation1d, _lib, functional as Fn
 from afa_b200.activations import SnakeBeta
 
 dev = torch.device("cuda:0")
-shapes = [(16, 768, 3444), (16, 192, 27552), (16, 24, 220416), (2, 96, 55104), (32, 96, 2048)]
+shapes = [(16, 768, 3444), (16, 384, 13776), (16, 24, 220416), (2, 96, 55104), (2, 24, 220416), (2, 384, 13776), (2, 768, 3444), (32, 96, 2048), (32, 24, 8192)]
 for dtype in (torch.float32, torch.bfloat16):
     for ch in (5, 9, 13, 17):
         _lib.set_tuning(1, ch, 0)
