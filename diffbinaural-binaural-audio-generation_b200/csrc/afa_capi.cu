@@ -23,6 +23,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_tune_chunks[3] = {0, 0, 0};   // [2]: channels-last walk, segment length in units of 12 samples
 int g_tune_threads[3] = {0, 0, 0};
+int g_tail_chunks = 0;    // tail kernel: walk length 12 n + 2 (which=8; 0 = 98)
 int g_actconv_xs = 1;     // fused activation+convolution, tcgen05 path: stage the input rows in shared memory (which=4)
 int g_tc_mode = 1, g_tc_ny = 0, g_tc_rlog2 = -1;   // tensor-core Activation1d (which = 5, 6)
 int g_actconv_path = 1;   // fused activation+convolution: 1 = tcgen05 (falls back to mma.sync when the tile does not fit), 0 = mma.sync
@@ -282,6 +283,11 @@ int afa_set_tuning(int which, int chunks, int threads) {
         afa_internal::tc_set_tuning(g_tc_mode, g_tc_ny, g_tc_rlog2);
         return 0;
     }
+    if (which == 8) {   // tail kernel: walk length = 12 * chunks + 2 samples (0 = built-in 98)
+        if (chunks < 0 || chunks > 4096) return fail(AFA_ERR_BAD_ARG, "tail walk length must be 12 * [1, 4096] + 2");
+        g_tail_chunks = chunks;
+        return 0;
+    }
     if (which == 7) {   // channels-last tensor-core Activation1d (bf16, no residual prologue): chunks = 0 off / 1 heuristic / 2 whenever eligible
         if (chunks < 0 || chunks > 2 || threads < 0 || threads > 4096 || threads % 4)
             return fail(AFA_ERR_BAD_ARG, "channels-last tensor-core path: mode 0..2, blocks per CTA 0 or a multiple of 4 up to 4096");
@@ -303,7 +309,7 @@ int afa_set_tuning(int which, int chunks, int threads) {
         g_tune_chunks[2] = chunks;
         return 0;
     }
-    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd), 7 (channels-last tensor-core fwd)");
+    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd), 7 (channels-last tensor-core fwd), 8 (tail)");
     bool ok = chunks == 0;
 #define X(CH) ok = ok || chunks == CH;
     AFA_CHUNK_LIST(X)
@@ -564,7 +570,7 @@ int afa_tail_fwd_cl(const void* x, int64_t x_bstride, const float* alpha, const 
         hop = 1;
     }
     if (batch == 0 || T == 0) return 0;
-    const int L = 98;                                  // walk length (12 n + 2); 92 outputs per segment
+    const int L = g_tail_chunks ? 12 * g_tail_chunks + 2 : 98;      // walk length (12 n + 2); L - 6 outputs per segment (afa_set_tuning(8, n))
     const int64_t nseg = (T + (L - 6) - 1) / (L - 6);
     const int64_t warps = batch * nseg;
     if (warps >= (1ll << 31) / 32) return fail(AFA_ERR_TOO_LARGE, "too many segments");

@@ -21,6 +21,11 @@
 //     32 lanes of a warp filling 64 contiguous bytes of one swizzled row (conflict free), then the TMA store as before.
 //   * rows [T, T_out) of y (the zero padding a polyphase dilated convolution reads next, afa_cl_fwd_kernel) are written
 //     as zeros by the same stores.
+// No residual prologue here (x' = x + res, xsum = x'): tried and dropped -- the compute threads added
+// res (16-byte global loads issued an iteration ahead) into the staged chunk in place and wrote xsum: bit-exact xsum, but
+// that call moves 8 bytes per element and afa_cl_fwd_kernel already does it at 3.7 TB/s (88-92 us at B = 8): 75 us at
+// C = 384, 85-89 us at C = 96 / 192, and the activation of the ROUNDED sum misses the 1e-2 budget against the contract
+// (E = 0.8-1.4e-2).
 #pragma once
 #include "afa_tc_kernels.cuh"
 
@@ -388,6 +393,7 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     }
                 }
                 const uint32_t rbase = (uint32_t)(((i >> 1) + 1) % kSlots) * kChunkBytes + (uint32_t)(i & 1) * (32u * 128u);
+#if !(defined(AFA_TC_CL_EXPERIMENT) && AFA_TC_CL_EXPERIMENT == 1)      // harness only: 1 = no drain stores (results are wrong)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const uint32_t p0 = pack_bf16(__uint_as_float(ya[2 * e]), __uint_as_float(ya[2 * e + 1]));
@@ -396,6 +402,9 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     sts16_pair(rbase + jx[(2 * e) & 7] + (uint32_t)(2 * e) * 128u, rbase + jx[(2 * e + 1) & 7] + (uint32_t)(2 * e + 1) * 128u, p0);
                     sts16_pair(rbase + jx[(2 * e) & 7] + (uint32_t)(16 + 2 * e) * 128u, rbase + jx[(2 * e + 1) & 7] + (uint32_t)(17 + 2 * e) * 128u, p1);
                 }
+#else
+                if (ya[0] == 0x12345678u && yb[3] == 0x9abcdef0u) sts16(rbase + jx[0], ya[1]);
+#endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + 8 * (kBarOut + ((i >> 1) + 1) % kSlots));

@@ -281,6 +281,7 @@ int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map,
  *          channels % 8 == 0, T % 4 == 0, 16-byte aligned x, y and batch strides, at most 8 zero rows behind T;
  *          csrc/afa_tc_cl_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible; threads = blocks of
  *          16 outputs per CTA (a multiple of 4 up to 4096; 0 = built-in choice).  which=5 with chunks = 0 turns it off as well.
+ * which=8: tail kernel (afa_tail_fwd_cl): walk length = 12 * chunks + 2 samples per warp segment (0 = built-in 98).
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
  * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects (which = 5: the tensor-core forward,
  * 7: its channels-last variant).

@@ -308,6 +308,21 @@ def test_tail_edge_grid():
             err = np.abs(wave.double().cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-3)
             assert err <= TOL_F32, (T, C, err)
             assert np.array_equal(pcm.cpu().numpy(), A.pcm_interleave(wave.cpu().numpy(), 2)), (T, C)
+    # the walk length of a warp segment is a tuning knob (afa_set_tuning(8, n): 12 n + 2 samples): same wave whatever the cut
+    from afa_b200 import _lib
+
+    x = torch.tensor(rng.standard_normal((2, 1000, 24)), dtype=torch.float32, device=DEV)
+    alpha = torch.tensor(rng.standard_normal(24) * 0.5, dtype=torch.float32, device=DEV)
+    beta = torch.tensor(rng.standard_normal(24) * 0.5, dtype=torch.float32, device=DEV)
+    w = torch.tensor(rng.standard_normal((24, 7)) * 0.05, dtype=torch.float32, device=DEV)
+    base = FC.tail_cl(x, 1000, alpha, beta, taps[0], taps[1], True, w, None, use_tanh=False, want_pcm=True)
+    try:
+        for n in (1, 3, 20):
+            _lib.set_tuning(8, n)
+            other = FC.tail_cl(x, 1000, alpha, beta, taps[0], taps[1], True, w, None, use_tanh=False, want_pcm=True)
+            assert torch.equal(base[0], other[0]) and torch.equal(base[1], other[1]), n
+    finally:
+        _lib.set_tuning(8, 0)
 
 
 def _engine_from_sd(sd, h, dtype):
