@@ -55,6 +55,9 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.afa_set_tuning(5, 1, 7) == -1 and lib.afa_set_tuning(6, 8, 0) == -1 and lib.afa_set_tuning(5, 1, 0) == 0 and lib.afa_set_tuning(6, -1, 0) == 0
     assert lib.afa_set_tuning(0, 9, 0) == 0 and lib.afa_set_tuning(0, 0, 0) == 0
     assert lib.afa_set_tuning(2, 4, 0) == 0 and lib.afa_set_tuning(2, 0, 0) == 0 and lib.afa_set_tuning(2, -1, 0) == -1
+    # channels-last tensor-core forward (7: mode 0..3, forced blocks per CTA a multiple of 4) and the tail's walk length (8)
+    assert lib.afa_set_tuning(7, 4, 0) == -1 and lib.afa_set_tuning(7, 1, 6) == -1 and lib.afa_set_tuning(7, 2, 8) == 0 and lib.afa_set_tuning(7, 1, 0) == 0
+    assert lib.afa_set_tuning(8, -1, 0) == -1 and lib.afa_set_tuning(8, 3, 0) == 0 and lib.afa_set_tuning(8, 0, 0) == 0
     # channels-last AMP entry points: argument checks come before any CUDA call
     i64 = ctypes.c_int64
     cl = lib.afa_amp_activation1d_fwd_cl
@@ -75,6 +78,8 @@ def test_argument_errors_need_no_gpu(lib):
     ws = lib.afa_bwd_workspace_bytes(2, 3, 1000, 0)
     assert ws >= 2 * 4 * 2 * 3 and lib.afa_bwd_workspace_bytes(4, 3, 1000, 0) > ws
     assert lib.afa_bwd_workspace_bytes(2, 3, 0, 0) <= 16
+    # the bound covers the shortest compiled segment (5 chunks of 4 fp32) plus the slice sums and counters of the split finalize
+    assert ws >= 2 * 3 * 50 * 2 * 4 + 3 * (32 * 2 * 4 + 4)
 
 
 def test_module_checkpoint_contract(golden):
