@@ -639,8 +639,8 @@ def run_cl_step(dev, clips: int, t_mel: int, steps: int = 5):
     ms = e0.elapsed_time(e1) / steps
     elems = sum(B * T * c * 18 for (c, T, *_r) in work)
 
-    # the activation without residual prologue on the wide stages, per call: channels-last tensor-core kernel (tcgen05, the
-    # built-in choice for C >= 96) against the channels-last walk kernel, same buffers, same box
+    # the activation without residual prologue, per call: channels-last tensor-core kernel (tcgen05, the built-in choice)
+    # against the channels-last walk kernel, same buffers, same box
     def plain_us(c, T, bufs, outs, alpha, beta, bias, mode):
         _lib.set_tuning(7, mode, 0)
         try:
@@ -663,8 +663,6 @@ def run_cl_step(dev, clips: int, t_mel: int, steps: int = 5):
 
     per_stage = []
     for (c, T, bufs, outs, alpha, beta, bias) in work:
-        if c < 96:
-            continue
         us_walk, us_tc = plain_us(c, T, bufs, outs, alpha, beta, bias, 0), plain_us(c, T, bufs, outs, alpha, beta, bias, 1)
         n = B * T * c
         per_stage.append({"C": c, "T": T, "B": B, "walk_us": round(us_walk, 2), "tensor_core_us": round(us_tc, 2),
@@ -672,8 +670,8 @@ def run_cl_step(dev, clips: int, t_mel: int, steps: int = 5):
     return {"ms_per_pass": round(ms, 3), "gbps": round(bytes_total / (ms * 1e-3) / 1e9, 1), "launches_per_pass": launches,
             "activation_elements_per_pass": elems, "gelem_per_s": round(elems / (ms * 1e-3) / 1e9, 1),
             "dtype": "bf16 I/O, f32 math", "layout": "[B, T, C]", "clips": clips,
-            "kernels": "afa_tc_cl_fwd_kernel (tcgen05) x48 (no residual prologue, C >= 96), afa_cl_fwd_kernel<bf16,false> x24 (C = 48, 24), "
-                       "afa_cl_fwd_kernel<bf16,true> x36, afa_mean_kernel x6, afa_cl_tail_kernel x1",
+            "kernels": "afa_tc_cl_fwd_kernel (tcgen05) x72 (no residual prologue), afa_cl_fwd_kernel<bf16,true> x36, afa_mean_kernel x6, "
+                       "afa_cl_tail_kernel x1",
             "plain_activation_per_call": {"rows": per_stage,
                                           "how": "12 calls per CUDA-graph replay over 4 input / 3 output buffers (4 B/element algorithmic), "
                                                  "afa_set_tuning(7, 0 | 1): channels-last walk kernel against the channels-last tensor-core kernel"}}

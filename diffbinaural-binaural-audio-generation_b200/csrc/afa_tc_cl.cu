@@ -19,7 +19,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 int g_cl_enable = 1;
 int g_cl_ny = 0;
 
-// [B, T, C] bf16, channels contiguous: dims (C, T, B), box = 64 channels x 64 time steps, 128-byte swizzle, zero fill outside.
+// [B, T, C] bf16, channels contiguous: dims (C, T, B), box = 32 channels x 64 time steps, 64-byte swizzle, zero fill outside.
 struct MapKey {
     const void* base;
     int64_t C, T, B, bs;
@@ -41,10 +41,10 @@ int make_map3(CUtensorMap* tm, const void* base, int64_t C, int64_t T, int64_t B
     if (!fn) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)bs * 2};
-    const cuuint32_t box[3] = {64, 64, 1};
+    const cuuint32_t box[3] = {32, 64, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return afa_internal::set_error(AFA_ERR_BAD_ARG, "cuTensorMapEncodeTiled (channels-last) failed (CUresult %d)", (int)r);
     MapSlot& c = cache[next++ % 16];
@@ -76,34 +76,35 @@ cudaError_t launch_kernel(unsigned grid, cudaStream_t st, const CUtensorMap& tmx
     return cudaGetLastError();
 }
 
-// Blocks of 16 outputs per CTA (NY, a multiple of 4): the cost model of afa_tc.cu's tc_plan (waves of 2 CTAs per SM, set-up +
-// pipeline fill + drain ~ 5 block times per CTA), with one strip per CTA.
-void cl_plan(int64_t batch, int64_t channels, int64_t T_out, int* ny_out, int64_t* n_cgroups, int64_t* n_tstrips) {
+// Blocks of 16 outputs per unit (NY, a multiple of 4): the cost model of afa_tc.cu's tc_plan (waves of 2 CTAs per SM, set-up +
+// pipeline fill + drain ~ 5 block times per CTA).  A CTA takes four consecutive units (batch entry, strip, channel quad).
+void cl_plan(int64_t batch, int64_t channels, int64_t T_out, int* ny_out, int64_t* n_cquads, int64_t* n_tstrips) {
     static int slots = 0;
     if (!slots) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = 2 * (sms > 0 ? sms : 148);
     }
-    const int64_t cgs = (channels + 127) / 128, rg = batch * cgs;
+    const int64_t cqs = (channels + 31) / 32, rg = batch * cqs;       // units per strip
     const int64_t tb = (T_out + 15) / 16;
     auto strips = [&](int64_t ny) { return (tb + ny - 1) / ny; };
+    auto ctas = [&](int64_t ny) { return (rg * strips(ny) + 3) / 4; };
     int64_t ny = 16, best = -1;
     auto consider = [&](int64_t cand) {
         cand = (cand + 3) / 4 * 4;
         if (cand < 4) cand = 4;
         if (cand > 4096) cand = 4096;
-        const int64_t cost = ((rg * strips(cand) + slots - 1) / slots) * (5 + cand);
+        const int64_t cost = ((ctas(cand) + slots - 1) / slots) * (5 + cand);
         if (best < 0 || cost < best || (cost == best && cand > ny)) { best = cost; ny = cand; }
     };
     for (int cand = 4; cand <= 16; cand += 4) consider(cand);
     for (int w = 1; w <= 8; ++w) {
-        const int64_t nts = (int64_t)slots * w / rg;
+        const int64_t nts = (int64_t)slots * w * 4 / rg;                 // strips that fill w waves
         if (nts >= 1) consider((tb + nts - 1) / nts);
     }
     if (g_cl_ny >= 4 && g_cl_ny % 4 == 0) ny = g_cl_ny;
     *ny_out = (int)ny;
-    *n_cgroups = cgs;
+    *n_cquads = cqs;
     *n_tstrips = strips(ny);
 }
 
@@ -126,10 +127,10 @@ bool tc_cl_eligible(const void* x, int64_t x_bs, const void* res, const void* y,
     if ((channels % 8) != 0 || (x_bs % 8) != 0 || (y_bs % 8) != 0 || channels >= (1ll << 20) || batch >= (1ll << 16)) return false;
     if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return false;
     if (g_cl_enable == 1) {
-        // 128 TMEM lanes per CTA: a channel count that leaves more than a quarter of the last group idle, or a launch that cannot
-        // fill the machine, stays on the walk kernel
-        const int64_t cgs = (channels + 127) / 128;
-        if (channels * 4 < cgs * 128 * 3) return false;
+        // units of 32 channels: a channel count that leaves more than a quarter of the lanes of its last unit idle (8, 16, 40 ...),
+        // or a launch that cannot fill the machine, stays on the walk kernel
+        const int64_t cqs = (channels + 31) / 32;
+        if (channels * 4 < cqs * 32 * 3) return false;
         if (batch * channels * T < (4ll << 20)) return false;
     }
     return tc_encode_tiled() != nullptr;
@@ -141,7 +142,8 @@ int tc_cl_fwd_launch(const void* x, int64_t x_bs, const float* bias, void* y, in
     int ny;
     int64_t cgs, ts;
     cl_plan(batch, channels, y_tpad, &ny, &cgs, &ts);
-    if (batch * cgs * ts >= (1ll << 31)) return set_error(AFA_ERR_TOO_LARGE, "grid of %lld CTAs", (long long)(batch * cgs * ts));
+    const int64_t n_ctas = (batch * cgs * ts + 3) / 4;
+    if (n_ctas >= (1ll << 29)) return set_error(AFA_ERR_TOO_LARGE, "grid of %lld CTAs", (long long)n_ctas);
     CUtensorMap tmx, tmy;
     if (int rc = make_map3(&tmx, x, channels, T, batch, x_bs)) return rc;
     if (int rc = make_map3(&tmy, y, channels, y_tpad, batch, y_bs)) return rc;
@@ -168,8 +170,9 @@ int tc_cl_fwd_launch(const void* x, int64_t x_bs, const float* bias, void* y, in
     a.flags = flags;
     a.NY = ny;
     a.n_tstrips = (int32_t)ts;
-    a.n_cgroups = (int32_t)cgs;
-    const unsigned grid = (unsigned)(batch * cgs * ts);
+    a.n_cquads = (int32_t)cgs;
+    a.B = (int32_t)batch;
+    const unsigned grid = (unsigned)n_ctas;
     const cudaError_t e = tc_mats() == 22 ? launch_kernel<2, 2>(grid, st, tmx, tmy, a) : launch_kernel<2, 1>(grid, st, tmx, tmy, a);
     count_launch();
     return e == cudaSuccess ? 0 : cuda_error(e, "afa_tc_cl_fwd_kernel launch");

@@ -7,18 +7,20 @@
 //
 // Same arithmetic, schedule, tensor-memory ring and barrier protocol as afa_tc_fwd_kernel -- read its header first.  What
 // the layout changes:
-//   * a CTA owns ONE batch entry, 128 consecutive channels (one TMEM lane = one MMA row each) and a strip of time; every
-//     lane walks the same time window, so the replicate-padding cases are CTA-uniform.
-//   * x chunk = 64 time steps x 128 channels = two tensor-map boxes [64 steps][64 channels] (3-D map (C, T, B), 128-byte
-//     swizzle): a row of a box is one time step.  That is the canonical MN-MAJOR operand layout of tcgen05.mma
-//     (((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in 16-bit elements: 64 channels contiguous, the next 64 channels LBO = one
-//     box = 8 KB on, 8-step groups SBO = 1 KB apart), so the up filter still reads x straight from what the TMA unit
-//     wrote (SS mode, A MN-major: instruction-descriptor bit 15); a K = 16 slice starts at ANY multiple of 8 time steps
-//     = a whole number of swizzle atoms.  No alignment condition on T (rows of the map are whole time steps).
+//   * lanes = channels.  The 128 TMEM lanes (= MMA rows) of a CTA are FOUR UNITS of 32 consecutive channels; a unit = (batch
+//     entry, channel quad, strip of time) has its own coordinates, so any channel count that is a multiple of 32 fills every
+//     lane (96 = 3 units, 192 = 6: with one 128-channel group per CTA a quarter of the lanes idled there).  The 32 lanes of a
+//     unit are one compute warp per group and walk the same time window: the replicate-padding cases are warp-uniform.
+//   * x chunk = 64 time steps x 4 units = four tensor-map boxes [64 steps][32 channels] (3-D map (C, T, B), 64-byte swizzle): a
+//     row of a box is one time step.  That is the canonical MN-MAJOR operand layout of tcgen05.mma (((8,4,m),(8,k)) :
+//     ((1,8,LBO),(32,SBO)) in 16-bit elements: 32 channels contiguous, the next unit LBO = one box = 4 KB on, 8-step groups
+//     SBO = 512 B apart), so the up filter still reads x straight from what the TMA unit wrote (SS mode, A MN-major:
+//     instruction-descriptor bit 15); a K = 16 slice starts at ANY multiple of 8 time steps = a whole number of swizzle atoms.
+//     No alignment condition on T (rows of the map are whole time steps).
 //   * the bias the tensor still lacks (the caller's "pending" bias) enters after the up filter: the filter is linear and
 //     replicate padding keeps all six taps of a phase, u(x + b) = u(x) + b * (sum of the phase's taps).
-//   * drain: a thread holds 32 consecutive outputs of ONE channel, the out chunk wants rows of 64 channels: 2-byte stores,
-//     32 lanes of a warp filling 64 contiguous bytes of one swizzled row (conflict free), then the TMA store as before.
+//   * drain: a thread holds 32 consecutive outputs of ONE channel, the out chunk wants rows of 32 channels: 2-byte stores,
+//     the 32 lanes of a warp filling the 64 bytes of one swizzled row, then the TMA store as before.
 //   * rows [T, T_out) of y (the zero padding a polyphase dilated convolution reads next, afa_cl_fwd_kernel) are written
 //     as zeros by the same stores.
 // No residual prologue here (x' = x + res, xsum = x'): tried and dropped -- the compute threads added
@@ -31,7 +33,7 @@
 
 namespace afa_tc {
 
-constexpr int kBoxBytes = 64 * 128;      // one tensor-map box: 64 time steps x 64 channels
+constexpr int kBoxBytes = 64 * 64;       // one tensor-map box: 64 time steps x 32 channels (a unit's share of a chunk)
 
 struct ClArgs {
     const __nv_bfloat16* x;
@@ -43,8 +45,9 @@ struct ClArgs {
     float bias_even, bias_odd;   // what a unit bias adds to u[n], n even / odd: 2 * (f[1] + f[3] + ...), 2 * (f[0] + f[2] + ...)
     int64_t x_bs;                // elements between batch entries of x
     int32_t C, T, T_out, flags;
-    int32_t NY;                  // outputs per CTA and channel in units of 16 (a multiple of 4)
-    int32_t n_tstrips, n_cgroups;   // blockIdx.x = (batch * n_cgroups + cgroup) * n_tstrips + tstrip
+    int32_t NY;                  // outputs per unit and channel in blocks of 16 (a multiple of 4)
+    int32_t n_tstrips, n_cquads;    // unit u = 4 * blockIdx.x + lane quarter = (batch * n_tstrips + tstrip) * n_cquads + channel quad
+    int32_t B;                      // batch entries (units beyond the last one load zeros and store nothing)
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
@@ -55,12 +58,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
                  ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
 }
-// MN-major, 128-byte swizzle: 64 MN elements (128 bytes) contiguous, the next 64 `LBO` bytes on; K: rows of 128 bytes,
-// 8-row groups SBO = 1024 bytes apart.  (cute::UMMA::make_umma_desc<Major::MN>: leading = stride of the MN atoms, stride =
-// stride of the K groups.)
-__device__ __forceinline__ uint64_t adesc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(1024u >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+// MN-major, 64-byte swizzle: 32 MN elements (64 bytes) contiguous, the next 32 `LBO` bytes on; K: rows of 64 bytes, 8-row
+// groups SBO = 512 bytes apart.  (cute::UMMA::make_umma_desc<Major::MN>: leading = stride of the MN atoms, stride = stride of
+// the K groups; layout type 4 = SWIZZLE_64B.)
+__device__ __forceinline__ uint64_t adesc_mn_sw64(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(512u >> 4) << 32) |
+           (1ull << 46) | (4ull << 61);
 }
 __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {          // low 16 bits of v
     asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tst.shared.b16 [%0], lo;\n\t}" ::"r"(addr), "r"(v) : "memory");
@@ -81,10 +84,14 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: role code runs on the uniform datapath
     const int NY = a.NY, NB = NY >> 1;                            // NB blocks of 32 outputs per channel
     const int NCH_IN = (NY >> 2) + 1, NCH_OUT = NY >> 2;          // x chunks / out chunks of this CTA's strip
-    const int tstrip = (int)(blockIdx.x % (uint32_t)a.n_tstrips);
-    const int rest = (int)(blockIdx.x / (uint32_t)a.n_tstrips);
-    const int cg = rest % a.n_cgroups, bi = rest / a.n_cgroups;
-    const int c0 = cg * 128;                        // first channel of the CTA
+    // this thread's unit: lane quarter `uq` of the CTA (warp 0: lane uq moves box uq; compute warps: uq = warp & 3)
+    const int uq = warp == 0 ? (lane & 3) : (warp & 3);
+    const uint32_t unit = blockIdx.x * 4u + (uint32_t)uq;
+    const int cq = (int)(unit % (uint32_t)a.n_cquads);
+    const uint32_t rest = unit / (uint32_t)a.n_cquads;
+    const int tstrip = (int)(rest % (uint32_t)a.n_tstrips);
+    const int bi = (int)(rest / (uint32_t)a.n_tstrips);      // >= B: no such unit (the TMA unit zero-fills its loads and drops its stores)
+    const int c0 = cq * 32;                         // first channel of the unit
     const int t_org = tstrip * (16 * NY) - 8;       // first staged time step; first output t_org + 8
     const int T = a.T;
     const uint32_t bars = sbase + kOffBar;
@@ -100,8 +107,8 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
             if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
             __syncwarp();
-            if (lane < 2)
-                tma_load_3d(sbase + p * kChunkBytes + lane * kBoxBytes, &tm_x, c0 + 64 * lane, t_org + 64 * p, bi, bars + 8 * (kBarFull + p));
+            if (lane < 4)
+                tma_load_3d(sbase + p * kChunkBytes + lane * kBoxBytes, &tm_x, c0, t_org + 64 * p, bi, bars + 8 * (kBarFull + p));
         }
         if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_y)) : "memory");
         __syncwarp();
@@ -153,29 +160,29 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             mbar_wait(bars + 8 * (kBarEv + 1), 0);
             if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + 0), (uint32_t)kChunkBytes);
             __syncwarp();
-            if (lane < 2)
-                tma_load_3d(sbase + lane * kBoxBytes, &tm_x, c0 + 64 * lane, t_org + 64 * kSlots, bi, bars + 8 * (kBarFull + 0));
+            if (lane < 4)
+                tma_load_3d(sbase + lane * kBoxBytes, &tm_x, c0, t_org + 64 * kSlots, bi, bars + 8 * (kBarFull + 0));
             __syncwarp();
         }
         for (int qc = 0; qc < NCH_OUT; ++qc) {
             const int slot = (qc + 1) % kSlots;
             mbar_wait(bars + 8 * (kBarOut + slot), (uint32_t)(qc / kSlots) & 1u);
-            if (lane < 2) {
-                tma_store_3d(&tm_y, c0 + 64 * lane, t_org + 8 + 64 * qc, bi, sbase + slot * kChunkBytes + lane * kBoxBytes);
+            if (lane < 4) {
+                tma_store_3d(&tm_y, c0, t_org + 8 + 64 * qc, bi, sbase + slot * kChunkBytes + lane * kBoxBytes);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             const int nc = qc + 1 + kSlots;                         // next x chunk for this slot
             if (nc < NCH_IN) {
-                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (lane < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + slot), (uint32_t)kChunkBytes);
                 __syncwarp();
-                if (lane < 2)
-                    tma_load_3d(sbase + slot * kChunkBytes + lane * kBoxBytes, &tm_x, c0 + 64 * lane, t_org + 64 * nc, bi, bars + 8 * (kBarFull + slot));
+                if (lane < 4)
+                    tma_load_3d(sbase + slot * kChunkBytes + lane * kBoxBytes, &tm_x, c0, t_org + 64 * nc, bi, bars + 8 * (kBarFull + slot));
             }
             __syncwarp();
         }
-        if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (lane < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -185,24 +192,24 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         constexpr uint32_t idesc_up = idesc_dn | (1u << 15);
         const uint64_t bup = bdesc_kmajor(sbase + kOffWup, 16 * 16);
         const uint64_t bdn = bdesc_kmajor(sbase + kOffWdn, 16 * 16);
-        const uint64_t ax = adesc_mn_sw128(sbase, kBoxBytes);            // chunk slot s: + s * (kChunkBytes >> 4); 8 time steps = 1024 B = 64 units
+        const uint64_t ax = adesc_mn_sw64(sbase, kBoxBytes);             // chunk slot s: + s * (kChunkBytes >> 4); 8 time steps = 512 B = 32 units of 16 B
         constexpr uint64_t kW = kWBytes >> 4;
         auto up = [&](uint32_t d, int bu, int xs) {
-            const uint64_t cb = ax + (uint64_t)(xs * (kChunkBytes >> 4) + (bu & 1) * 256);
+            const uint64_t cb = ax + (uint64_t)(xs * (kChunkBytes >> 4) + (bu & 1) * 128);
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 if (m == 3 && (bu & 1)) {
                     // time steps 56 .. 69 of the chunk: steps 48..63 of this chunk against the taps moved down 8 rows, steps 0..15 of
                     // the next chunk against the taps moved up 8
                     const int xs1 = xs + 1 == kSlots ? 0 : xs + 1;
-                    const uint64_t a1 = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 6 * 64), a2 = ax + (uint64_t)(xs1 * (kChunkBytes >> 4));
+                    const uint64_t a1 = ax + (uint64_t)(xs * (kChunkBytes >> 4) + 6 * 32), a2 = ax + (uint64_t)(xs1 * (kChunkBytes >> 4));
                     mma_ss(d + 48, a1, bup + 1 * kW, idesc_up, 0);
                     if (kUpMats == 2) mma_ss(d + 48, a1, bup + (kUpVariants + 1) * kW, idesc_up, 1);
                     mma_ss(d + 48, a2, bup + 2 * kW, idesc_up, 1);
                     if (kUpMats == 2) mma_ss(d + 48, a2, bup + (kUpVariants + 2) * kW, idesc_up, 1);
                 } else {
-                    mma_ss(d + 16 * m, cb + 64 * m, bup, idesc_up, 0);
-                    if (kUpMats == 2) mma_ss(d + 16 * m, cb + 64 * m, bup + kUpVariants * kW, idesc_up, 1);
+                    mma_ss(d + 16 * m, cb + 32 * m, bup, idesc_up, 0);
+                    if (kUpMats == 2) mma_ss(d + 16 * m, cb + 32 * m, bup + kUpVariants * kW, idesc_up, 1);
                 }
             }
         };
@@ -252,18 +259,17 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // ===== compute groups =====
         const int grp = (warp - 2) >> 2;
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int l = q * 32 + lane;                             // TMEM lane = channel c0 + l
-        const int ch = c0 + l;
-        const bool active = ch < a.C;
+        const int ch = c0 + lane;                                // TMEM lane q * 32 + lane = channel `lane` of unit q
+        const bool active = bi < a.B && ch < a.C;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        // this channel's 2 bytes inside a row (= time step) of a chunk: box l / 64, 16-byte unit ((l % 64) / 8) ^ (row % 8)
-        const uint32_t colbase = sbase + (uint32_t)(l >> 6) * kBoxBytes + (uint32_t)(l & 7) * 2u;
-        const uint32_t junit = (uint32_t)(l & 63) >> 3;
-        uint32_t jx[8];
+        // this channel's 2 bytes inside a row (= time step) of a chunk: box q, 16-byte unit (lane / 8) ^ ((row / 2) % 4)
+        const uint32_t colbase = sbase + (uint32_t)q * kBoxBytes + (uint32_t)(lane & 7) * 2u;
+        const uint32_t junit = (uint32_t)lane >> 3;
+        uint32_t jx[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) jx[k] = colbase + ((junit ^ (uint32_t)k) << 4);
+        for (int k = 0; k < 4; ++k) jx[k] = colbase + ((junit ^ (uint32_t)k) << 4);
         float a_eff = 1.f, ib = 1.f, bias_v = 0.f;
-        const bool left_cta = t_org < 0;                         // the strip starts the row (t_org = -8)
+        const bool left_cta = t_org < 0;                         // the unit's strip starts the row (t_org = -8); warp-uniform
         const int rT = T - t_org;                                // first staged row beyond the tensor (window row index)
         if (active) {
             float al = __ldg(a.alpha + ch);
@@ -280,7 +286,7 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         auto patch_chunk = [&](int c) {
             const int r_lo = max(rT, 64 * c), r_hi = min(rT + 16, 64 * c + 64);
             const bool left = left_cta && c == 0, right = r_lo < r_hi;
-            if (left || right) {                                 // CTA-uniform
+            if (left || right) {                                 // warp-uniform
                 mbar_wait(bars + 8 * (kBarFull + c % kSlots), (uint32_t)(c / kSlots) & 1u);
                 if (active) {
                     const unsigned short* xc = reinterpret_cast<const unsigned short*>(a.x) + (size_t)bi * (size_t)a.x_bs + ch;
@@ -288,13 +294,13 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     if (left) {
                         const uint32_t v = __ldg(xc);
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) sts16(cbase + jx[r] + (uint32_t)r * 128u, v);
+                        for (int r = 0; r < 8; ++r) sts16(cbase + jx[(r >> 1) & 3] + (uint32_t)r * 64u, v);
                     }
                     if (right) {
                         const uint32_t v = __ldg(xc + (size_t)(T - 1) * (size_t)a.C);
                         for (int r = r_lo; r < r_hi; ++r) {
                             const int rr = r - 64 * c;
-                            sts16(cbase + (colbase + ((junit ^ (uint32_t)(rr & 7)) << 4)) + (uint32_t)rr * 128u, v);
+                            sts16(cbase + (colbase + ((junit ^ (uint32_t)((rr >> 1) & 3)) << 4)) + (uint32_t)rr * 64u, v);
                         }
                     }
                 }
@@ -341,7 +347,7 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 tmem_ld16(tslot + 32, ua);
                 tmem_ld16(tslot + 48, uc);
                 snake16(ub, sp + 8);
-                // replicate padding of the ACTIVATED signal (filter.py:98), in the 2x domain; CTA-uniform here.  eb = element of
+                // replicate padding of the ACTIVATED signal (filter.py:98), in the 2x domain; warp-uniform here.  eb = element of
                 // n = 2T in this block (10, 26, 42, 58 -- or 2, 18, 34, 50 when T % 8 == 4 -- when inside): elements >= eb repeat
                 // element eb - 1.
                 const int eb = 2 * (T - t_org) - 64 * b - 6;
@@ -392,15 +398,15 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                         if (tb0 + 16 + e >= T) yb[e] = 0u;
                     }
                 }
-                const uint32_t rbase = (uint32_t)(((i >> 1) + 1) % kSlots) * kChunkBytes + (uint32_t)(i & 1) * (32u * 128u);
+                const uint32_t rbase = (uint32_t)(((i >> 1) + 1) % kSlots) * kChunkBytes + (uint32_t)(i & 1) * (32u * 64u);
 #if !(defined(AFA_TC_CL_EXPERIMENT) && AFA_TC_CL_EXPERIMENT == 1)      // harness only: 1 = no drain stores (results are wrong)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const uint32_t p0 = pack_bf16(__uint_as_float(ya[2 * e]), __uint_as_float(ya[2 * e + 1]));
                     const uint32_t p1 = pack_bf16(__uint_as_float(yb[2 * e]), __uint_as_float(yb[2 * e + 1]));
-                    // rows 2e, 2e+1 and 16+2e, 17+2e of this block; row % 8 = (2e) % 8, (2e+1) % 8 (static)
-                    sts16_pair(rbase + jx[(2 * e) & 7] + (uint32_t)(2 * e) * 128u, rbase + jx[(2 * e + 1) & 7] + (uint32_t)(2 * e + 1) * 128u, p0);
-                    sts16_pair(rbase + jx[(2 * e) & 7] + (uint32_t)(16 + 2 * e) * 128u, rbase + jx[(2 * e + 1) & 7] + (uint32_t)(17 + 2 * e) * 128u, p1);
+                    // rows 2e, 2e+1 and 16+2e, 17+2e of this block: (row / 2) % 4 = e % 4 for all four (static)
+                    sts16_pair(rbase + jx[e & 3] + (uint32_t)(2 * e) * 64u, rbase + jx[e & 3] + (uint32_t)(2 * e + 1) * 64u, p0);
+                    sts16_pair(rbase + jx[e & 3] + (uint32_t)(16 + 2 * e) * 64u, rbase + jx[e & 3] + (uint32_t)(17 + 2 * e) * 64u, p1);
                 }
 #else
                 if (ya[0] == 0x12345678u && yb[3] == 0x9abcdef0u) sts16(rbase + jx[0], ya[1]);

@@ -278,7 +278,8 @@ int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map,
  *          threads = blocks of 16 outputs per TMEM lane and CTA (a multiple of 4 up to 4096; 0 = built-in choice).
  * which=6: its rows per CTA as log2 (3..7; -1 = built-in choice).
  * which=7: the channels-last tensor-core forward (afa_amp_activation1d_fwd_cl on bf16 tensors without res / xsum,
- *          channels % 8 == 0, T % 4 == 0, 16-byte aligned x, y and batch strides, at most 8 zero rows behind T;
+ *          channels % 8 == 0 (units of 32 channels, the last one at least three quarters full), T % 4 == 0, 16-byte aligned
+ *          x, y and batch strides, at most 8 zero rows behind T;
  *          csrc/afa_tc_cl_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible; threads = blocks of
  *          16 outputs per CTA (a multiple of 4 up to 4096; 0 = built-in choice).  which=5 with chunks = 0 turns it off as well.
  * which=8: tail kernel (afa_tail_fwd_cl): walk length = 12 * chunks + 2 samples per warp segment (0 = built-in 98).

@@ -125,7 +125,8 @@ def test_cl_activation_grid(dtype):
 def test_cl_tensor_core_activation_grid():
     """The channels-last tensor-core forward (afa_tc_cl_fwd_kernel; bf16, no residual prologue), forced onto small tensors
     the built-in choice leaves to the walk kernel: T around the 32-output block / 64-step chunk / strip boundaries with both
-    residues of T % 8, channel counts around the 64-channel boxes and the 128-lane groups, Snake / SnakeBeta, log-scale on /
+    residues of T % 8, channel counts around the 32-channel units (four per CTA, each with its own batch entry / strip / channel
+    quad, the last CTA partly empty), Snake / SnakeBeta, log-scale on /
     off, bias on / off, padded batch strides, zero rows behind T, guard rows behind those; forced strip lengths.  Against the
     float64 oracle on the bf16 inputs, and against the walk kernel (both round y to bf16 once: they differ by the rounding
     of s to bf16 in front of the down filter)."""
@@ -135,7 +136,7 @@ def test_cl_tensor_core_activation_grid():
     t32, taps, taps64 = _taps()
     rng = np.random.default_rng(11)
     Ts = [64, 68, 72, 100, 124, 128, 132, 252, 256, 260, 316, 508, 512, 516, 1000, 1028, 2052, 4100]
-    Cs = [8, 24, 64, 72, 96, 128, 136, 192, 200, 264]
+    Cs = [8, 24, 32, 40, 64, 72, 96, 128, 136, 192, 200, 264]
     n = 0
     try:
         for T in Ts:
