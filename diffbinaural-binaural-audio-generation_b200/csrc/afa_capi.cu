@@ -251,6 +251,9 @@ size_t kernel_smem(int which) {
 }  // namespace
 
 namespace afa_internal {
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+void pdl_set(int on) { g_pdl = on; }
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -283,6 +286,11 @@ int afa_set_tuning(int which, int chunks, int threads) {
         afa_internal::tc_set_tuning(g_tc_mode, g_tc_ny, g_tc_rlog2);
         return 0;
     }
+    if (which == 9) {   // programmatic dependent launch of the tensor-core Activation1d kernels: 1 on (default), 0 off
+        if (chunks != 0 && chunks != 1) return fail(AFA_ERR_BAD_ARG, "programmatic dependent launch must be 0 or 1");
+        afa_internal::pdl_set(chunks);
+        return 0;
+    }
     if (which == 8) {   // tail kernel: walk length = 12 * chunks + 2 samples (0 = built-in 98)
         if (chunks < 0 || chunks > 4096) return fail(AFA_ERR_BAD_ARG, "tail walk length must be 12 * [1, 4096] + 2");
         g_tail_chunks = chunks;
@@ -309,7 +317,7 @@ int afa_set_tuning(int which, int chunks, int threads) {
         g_tune_chunks[2] = chunks;
         return 0;
     }
-    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd), 7 (channels-last tensor-core fwd), 8 (tail)");
+    if (which < 0 || which > 1) return fail(AFA_ERR_BAD_ARG, "which must be 0 (fwd), 1 (bwd), 2 (channels-last fwd), 3 / 4 (fused conv), 5 / 6 (tensor-core fwd), 7 (channels-last tensor-core fwd), 8 (tail), 9 (dependent launch)");
     bool ok = chunks == 0;
 #define X(CH) ok = ok || chunks == CH;
     AFA_CHUNK_LIST(X)

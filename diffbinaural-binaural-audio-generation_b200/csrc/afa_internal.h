@@ -4,7 +4,32 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace afa_internal {
+// Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization) of the tensor-core kernels (afa_tc_fwd_kernel,
+// afa_tc_cl_fwd_kernel): they call griddepcontrol.launch_dependents at entry and griddepcontrol.wait before the first access to
+// global memory a predecessor may have written, so the launch latency and the set-up of kernel N + 1 (barriers, tensor-memory
+// allocation, tap matrices) run in the shadow of kernel N's tail: 1-2 us per launch.  Without the attribute both instructions
+// are no-ops; afa_set_tuning(9, 0) launches without it (A/B measurements).  The register-walk kernels do NOT use it: measured
+// same-box (profiles/r02_pdl_ab.log), their one-clip launches got 10-15 % slower with it, the large ones did not change.
+bool pdl_enabled();
+void pdl_set(int on);
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int set_error(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 int cuda_error(cudaError_t e, const char* what);
 void count_launch();

@@ -107,8 +107,7 @@ cudaError_t launch_kernel(unsigned grid, cudaStream_t st, const CUtensorMap& tmx
     cudaGetDevice(&dev);
     cudaError_t e = prepare_kernel<kUp, kDn, kDebug>(dev);
     if (e != cudaSuccess) return e;
-    afa_tc::afa_tc_fwd_kernel<kUp, kDn, kDebug><<<grid, afa_tc::kThreads, afa_tc::kSmemBytes, st>>>(tmx, tmy, a);
-    return cudaGetLastError();
+    return afa_internal::launch_pdl(afa_tc::afa_tc_fwd_kernel<kUp, kDn, kDebug>, dim3(grid), dim3(afa_tc::kThreads), afa_tc::kSmemBytes, st, tmx, tmy, a);
 }
 
 }  // namespace

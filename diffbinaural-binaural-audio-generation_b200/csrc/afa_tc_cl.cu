@@ -72,8 +72,7 @@ cudaError_t launch_kernel(unsigned grid, cudaStream_t st, const CUtensorMap& tmx
     cudaGetDevice(&dev);
     cudaError_t e = prepare_kernel<kUp, kDn>(dev);
     if (e != cudaSuccess) return e;
-    afa_tc::afa_tc_cl_fwd_kernel<kUp, kDn><<<grid, afa_tc::kThreads, afa_tc::kSmemBytes, st>>>(tmx, tmy, a);
-    return cudaGetLastError();
+    return afa_internal::launch_pdl(afa_tc::afa_tc_cl_fwd_kernel<kUp, kDn>, dim3(grid), dim3(afa_tc::kThreads), afa_tc::kSmemBytes, st, tmx, tmy, a);
 }
 
 // Blocks of 16 outputs per unit (NY, a multiple of 4): the cost model of afa_tc.cu's tc_plan (waves of 2 CTAs per SM, set-up +

@@ -97,6 +97,10 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const uint32_t bars = sbase + kOffBar;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + kOffTmem);
 
+    // Programmatic dependent launch: the next kernel of the stream may start as soon as this one's CTAs have all started; ITS
+    // set-up (barriers, tensor-memory allocation, tap matrices) then runs in the shadow of this kernel's tail.  Everything that
+    // touches global memory a predecessor may have written -- x, alpha / beta / bias -- comes after griddepcontrol.wait.
+    pdl_launch_dependents();
     if (warp == 0) {
         for (int i = lane; i < kNumBars; i += 32) {
             const uint32_t cnt = i == kBarPre ? 8u : (i >= kBarCmp && i < kBarEv) ? 4u : (i >= kBarOut && i < kBarEvY) ? 8u : 1u;
@@ -104,6 +108,7 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
+        pdl_wait();
         for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
             if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
             __syncwarp();
@@ -148,6 +153,7 @@ afa_tc_cl_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        pdl_wait();
     }
     tc_fence_before();
     __syncthreads();

@@ -134,6 +134,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(src) : "memory");
 }
+// programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization; no-ops without it)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -291,6 +294,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t bars = sbase + kOffBar;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + kOffTmem);
 
+    pdl_launch_dependents();      // programmatic dependent launch: the next kernel's set-up may run in the shadow of this one's tail
     if (warp == 0) {
         // Barriers and the first loads, spread over the lanes: one elected thread needed ~115 cycles per TMA instruction and ~2000
         // cycles for the 40-odd mbarrier inits -- with 8 boxes per chunk (one binaural clip: R = 16) the CTA's first data was
@@ -301,6 +305,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
+        pdl_wait();               // x may be the predecessor's output: no global access before this point
         for (int p = 0; p < kSlots && p < NCH_IN; ++p) {
             if (lane == 0) mbar_expect_tx(bars + 8 * (kBarFull + p), (uint32_t)kChunkBytes);
             __syncwarp();
@@ -352,6 +357,7 @@ afa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
         if (warp == 1) AFA_TC_STAMP(3, 0, 3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        pdl_wait();               // alpha / beta and the edge samples of x are read after the CTA-wide barrier below
     }
     tc_fence_before();
     __syncthreads();

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define AFA_VERSION 151            /* 0.1.5: + afa_activation1d_fwd_pitched, split parameter-gradient finalize; 0.1.4: tensor-core (tcgen05) forward for bf16 activations */
+#define AFA_VERSION 152            /* 0.1.5: + afa_activation1d_fwd_pitched, split parameter-gradient finalize, channels-last tensor-core forward; 0.1.4: tensor-core (tcgen05) forward for bf16 activations */
 
 #define AFA_DTYPE_F32 0
 #define AFA_DTYPE_BF16 1
@@ -283,6 +283,8 @@ int afa_compact_zero_frames(const float *mel, float *packed, int32_t *frame_map,
  *          csrc/afa_tc_cl_kernels.cuh): chunks = 0 never, 1 built-in choice (default), 2 whenever eligible; threads = blocks of
  *          16 outputs per CTA (a multiple of 4 up to 4096; 0 = built-in choice).  which=5 with chunks = 0 turns it off as well.
  * which=8: tail kernel (afa_tail_fwd_cl): walk length = 12 * chunks + 2 samples per warp segment (0 = built-in 98).
+ * which=9: programmatic dependent launch of the two tensor-core kernels (their set-up overlaps the tail of the kernel in front
+ *          of them on the stream; they touch no global memory before griddepcontrol.wait): chunks = 1 on (default), 0 off.
  * afa_kernel_info: writes {regs, static+dynamic smem bytes, threads, elems per segment,
  * max resident CTAs/SM, launches so far} for the kernel that (which, dtype, T) selects (which = 5: the tensor-core forward,
  * 7: its channels-last variant).

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(EXPORTED_SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.afa_version() == 151
+    assert lib.afa_version() == 152
 
 
 def test_argument_errors_need_no_gpu(lib):
@@ -51,7 +51,7 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.afa_activation1d_fwd(vp(16), vp(32), vp(64), vp(64), taps, taps, -1, 1, 8, 0, 0, None) == -1
     assert lib.afa_activation1d_fwd(vp(18), vp(32), vp(64), vp(64), taps, taps, 1, 1, 8, 0, 0, None) == -5  # 2-byte aligned fp32
     assert lib.afa_activation1d_fwd(vp(16), vp(32), vp(64), vp(64), taps, taps, 1 << 20, 1 << 12, 1 << 20, 0, 0, None) == -3
-    assert lib.afa_set_tuning(0, 4, 0) == -1 and lib.afa_set_tuning(9, 0, 0) == -1 and lib.afa_set_tuning(3, 2, 0) == -1 and lib.afa_set_tuning(5, 3, 0) == -1
+    assert lib.afa_set_tuning(0, 4, 0) == -1 and lib.afa_set_tuning(10, 0, 0) == -1 and lib.afa_set_tuning(9, 2, 0) == -1 and lib.afa_set_tuning(9, 1, 0) == 0 and lib.afa_set_tuning(3, 2, 0) == -1 and lib.afa_set_tuning(5, 3, 0) == -1
     assert lib.afa_set_tuning(5, 1, 7) == -1 and lib.afa_set_tuning(6, 8, 0) == -1 and lib.afa_set_tuning(5, 1, 0) == 0 and lib.afa_set_tuning(6, -1, 0) == 0
     assert lib.afa_set_tuning(0, 9, 0) == 0 and lib.afa_set_tuning(0, 0, 0) == 0
     assert lib.afa_set_tuning(2, 4, 0) == 0 and lib.afa_set_tuning(2, 0, 0) == 0 and lib.afa_set_tuning(2, -1, 0) == -1

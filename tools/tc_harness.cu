@@ -29,6 +29,9 @@ int cuda_error(cudaError_t e, const char* what) {
     return (int)e;
 }
 void count_launch() {}
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+void pdl_set(int on) { g_pdl = on; }
 }  // namespace afa_internal
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); exit(2); } } while (0)
@@ -101,6 +104,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--check-rows")) check_rows = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--mats")) mats = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--j0")) j0 = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--pdl")) afa_internal::pdl_set(atoi(argv[i + 1]));
     }
     afa_internal::tc_set_mats(mats);
     afa_internal::tc_set_debug_window(j0);
