@@ -522,6 +522,69 @@ def test_tensor_core_forward_graph_capture_guard_band_and_module_dispatch():
         _lib.set_tuning(5, 1, 0)
 
 
+def test_tensor_core_dependent_launch_chain_is_bit_identical():
+    """Programmatic dependent launch (afa_set_tuning(9, ...)): each kernel of a chain reads the tensor the kernel in front of it
+    on the stream wrote (y1 = a(x), y2 = a(y1), ...), eagerly and as one CUDA graph; its set-up may overlap the predecessor's
+    tail, its reads may not.  Same bits with the attribute on and off, for the [B, C, T] kernel and the channels-last one."""
+    _, _lib, Fn, _, _ = _mods()
+    from afa_b200 import functional_cl as FC
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(21)
+    taps = Fn.host_taps(TP.make_taps())
+    B, C, T = 2, 96, 8192
+    a = torch.randn(C, device=dev) * 0.3
+    b = torch.randn(C, device=dev) * 0.3 + 1.0
+    x = (torch.randn(B, C, T, device=dev) * 0.5).to(torch.bfloat16)
+    xcl = x.transpose(1, 2).contiguous()
+    bias = torch.randn(C, device=dev) * 0.1
+
+    def chain(n=6):
+        bufs = [torch.empty_like(x) for _ in range(2)]
+        cur = x
+        for i in range(n):
+            Fn.activation1d_forward_raw(cur, a, b, taps, taps, True, out=bufs[i % 2])
+            cur = bufs[i % 2]
+        return cur.clone()
+
+    def chain_cl(n=6):
+        bufs = [torch.empty_like(xcl) for _ in range(2)]
+        cur = xcl
+        for i in range(n):
+            FC.amp_activation1d_cl(cur, T, a, b, taps, taps, True, bias=bias, out=bufs[i % 2])
+            cur = bufs[i % 2]
+        return cur.clone()
+
+    def graphed(fn):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        g.replay()
+        torch.cuda.synchronize()
+        return out.clone()
+
+    _lib.set_tuning(5, 2, 0)
+    _lib.set_tuning(7, 2, 0)
+    try:
+        res = {}
+        for pdl in (0, 1):
+            _lib.set_tuning(9, pdl)
+            before = _lib.launch_count()
+            res[pdl] = (chain(), chain_cl(), graphed(chain), graphed(chain_cl))
+            torch.cuda.synchronize()
+            assert _lib.launch_count() == before + 6 * 6, pdl      # one kernel per call: both tensor-core kernels were taken
+        for u, v in zip(res[0], res[1]):
+            assert torch.equal(u, v)
+        assert torch.equal(res[1][0], res[1][2]) and torch.equal(res[1][1], res[1][3])
+        assert torch.isfinite(res[1][0].float()).all() and torch.isfinite(res[1][1].float()).all()
+    finally:
+        _lib.set_tuning(9, 1)
+        _lib.set_tuning(5, 1, 0)
+        _lib.set_tuning(7, 1, 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # round-2 parity gaps (VERDICT round 1, "What's weak" 1)
 # ------------------------------------------------------------------------------------------------
