@@ -1097,7 +1097,8 @@ def run_gpu(args):
                              "shape": trec["shape"], "algorithmic_bytes": trec["algorithmic_bytes"], "dram_read_bytes": trec["dram_read_bytes"],
                              "traffic_over_algorithmic": round(trec["dram_bytes"] / trec["algorithmic_bytes"], 3), "source": trec["source"],
                              "note": "per launch of the largest stage shape of this workload (not the 109-launch average printed above)"},
-                         "tensor_core_forward": traffic_record("afa_tc::afa_tc_fwd_kernel", "bf16", (16, 384, 13776))},
+                         "tensor_core_forward": traffic_record("afa_tc::afa_tc_fwd_kernel", "bf16", (16, 384, 13776)),
+                         "tensor_core_forward_channels_last": traffic_record("afa_tc::afa_tc_cl_fwd_kernel", "bf16", (16, 55104, 96))},
             "cpu_baseline": cpu_base,
             "e2e": e2e,
             "gpu_launches": int(gpu_launches),
